@@ -1,0 +1,254 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the msmd_b200 hot path (contract: see DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+One JSON line on stdout (rank 0).  A "step" is one pass of the hot path over one batch of
+synthetic input.  Workloads:
+  sampler  BASELINE.json configs[2]: 64 clips x 10 s, style-conditioned sampling + FLAME decode (bf16)
+  flame    BASELINE.json configs[1]: FLAME decode 8192 frames x 5023 verts, 300+100 betas, fp32
+Multi-GPU (torchrun, one rank per GPU): clips / frames are partitioned by rank, no collective on
+the data path (weak scaling); time = max over ranks between two barriers.
+`--impl reference` times the CPU oracle port of the same path on the host cores (rank 0 only).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        d['_source'] = 'measured'
+        return d
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, _source='fallback')
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop = index, [], threading.Event()
+        self.t = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}',
+                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([c.strip() for c in out.strip().split(',')])
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.t.join(timeout=6)
+
+    def summary(self):
+        sm = sorted(int(float(r[0])) for r in self.rows if len(r) >= 6 and r[0].replace('.', '').isdigit())
+        mx = [int(float(r[1])) for r in self.rows if len(r) >= 6 and r[1].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for k, n in enumerate(names) if any(len(r) >= 6 and r[2 + k].lower().startswith('active') for r in self.rows)]
+        return dict(sm_mhz=(sm[len(sm) // 2] if sm else None), sm_max_mhz=(max(mx) if mx else None),
+                    reasons=reasons, samples=len(sm))
+
+
+# --------------------------------------------------------------------------------------------
+class FlameWorkload:
+    """configs[1]: standalone FLAME lbs decode, 8192 frames x 5023 verts, 300 shape + 100 expr, fp32."""
+    name = 'flame'
+    metric = 'flame_vertex_frames_per_sec'
+    unit = 'frames/s'
+    dtype = 'f32'
+    kernel = 'flame_fused'
+
+    def __init__(self, frames=8192):
+        self.frames = frames
+
+    def config(self, world):
+        return dict(workload='flame_decode_8192x5023_300+100_fp32 (BASELINE configs[1])', frames_per_gpu=self.frames,
+                    verts=5023, n_shape=300, n_exp=100, parallelism=f'frames sharded x{world}, no collective',
+                    l2_policy='per-step output 494 MB > 126 MB L2 (no reuse between steps)')
+
+    def setup(self, device, rank):
+        from types import SimpleNamespace
+        from msmd_b200.utils.flame import FLAME
+        from oracle import synth
+        raw = synth.flame_raw(0, synth.FLAME_V, 400)
+        self.model = FLAME(SimpleNamespace(n_shape=300, n_exp=100, flame_lmk_embedding_path=None), raw=raw).to(device)
+        host = synth.flame_inputs(self.frames, 300, 100, seed=rank)
+        self.host = [t.pin_memory() for t in host]
+        self.dev = [t.to(device) for t in host]
+        self.host_out = torch.empty((self.frames, synth.FLAME_V, 3), dtype=torch.float32).pin_memory()
+        self.device = device
+
+    def units(self):
+        return self.frames
+
+    def launches_per_step(self):
+        return 2  # flame_pose_kernel + fused blendshape/LBS kernel
+
+    def step(self):
+        sh, ex, po, ey = self.dev
+        v, _, _ = self.model(sh, ex, po, ey, return_lm2d=False, return_lm3d=False)
+        return v
+
+    def step_e2e(self):
+        sh, ex, po, ey = [h.to(self.device, non_blocking=True) for h in self.host]
+        v, _, _ = self.model(sh, ex, po, ey, return_lm2d=False, return_lm3d=False)
+        self.host_out.copy_(v, non_blocking=True)
+        return v
+
+    def e2e_bytes(self):
+        return sum(h.numel() * 4 for h in self.host), self.host_out.numel() * 4
+
+    def roofline(self, peaks, kernel_ms):
+        # fused minimal bytes = betas + pose + bases (once) + verts out
+        B = self.frames
+        alg = B * 400 * 4 + B * 15 * 4 + 15069 * 436 * 4 + B * 15069 * 4
+        ach = alg / (kernel_ms * 1e-3) / 1e9
+        flops = 2.0 * B * 15069 * 436
+        return dict(bound='hbm', kernel=self.kernel, achieved=ach, peak=peaks['hbm_gbs'], unit='GB/s',
+                    frac=ach / peaks['hbm_gbs'], traffic=None, peak_source=peaks['_source'] + ' (burst copy)',
+                    algorithmic_bytes=alg, kernel_ms=kernel_ms,
+                    gemm_fp32_equiv_tflops=flops / (kernel_ms * 1e-3) / 1e12)
+
+    def cpu_reference(self, seconds=10.0):
+        """oracle port (oracle/flame_lbs.py) on the host cores, 512-frame batches like common.py:176-196."""
+        from oracle import flame_lbs, synth
+        torch.set_num_threads(os.cpu_count())
+        assets = synth.flame_assets(0, synth.FLAME_V, 300, 100)
+        sh, ex, po, ey = synth.flame_inputs(512, 300, 100, seed=0)
+        flame_lbs.flame_forward(assets, sh, ex, po, ey)
+        n, t0 = 0, time.perf_counter()
+        while time.perf_counter() - t0 < seconds or n == 0:
+            flame_lbs.flame_forward(assets, sh, ex, po, ey)
+            n += 512
+        dt = time.perf_counter() - t0
+        return dict(value=n / dt, unit=self.unit, cores=torch.get_num_threads(), kind='port',
+                    sample=f'{n} frames in 512-frame batches, {dt:.1f} s, oracle/flame_lbs.py (torch CPU fp32)')
+
+
+WORKLOADS = {'flame': FlameWorkload}
+DEFAULT_WORKLOAD = 'flame'
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    a = ap.parse_args()
+    rank = int(os.environ.get('RANK', 0))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    wl = WORKLOADS[a.workload]()
+
+    if a.impl == 'reference':
+        if rank != 0:
+            return 0
+        t0 = time.perf_counter()
+        per = max(2.0, min(20.0, 60.0 / max(1, a.steps + a.warmup)))
+        for _ in range(a.warmup):
+            wl.cpu_reference(per)
+        vals = [wl.cpu_reference(per) for _ in range(a.steps)]
+        v = sum(x['value'] for x in vals) / len(vals)
+        cb = dict(vals[-1], value=v)
+        print(json.dumps(dict(impl='reference', metric=wl.metric, value=v, unit=wl.unit, n_gpus=a.gpus, steps=a.steps,
+                              warmup=a.warmup, ms_per_step=1e3 * (time.perf_counter() - t0) / max(1, a.steps + a.warmup),
+                              higher_is_better=True, scaling='weak', vs_baseline=None, dtype=wl.dtype, data='synthetic',
+                              config=wl.config(a.gpus), cpu_baseline=cb,
+                              e2e=dict(value=v, unit=wl.unit, h2d_bytes_per_step=0, d2h_bytes_per_step=0))))
+        return 0
+
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device (no CPU fallback)'
+    torch.cuda.set_device(local)
+    device = torch.device('cuda', local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=device)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if dist is None:
+            return ms
+        t = torch.tensor([ms], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    from msmd_b200 import _lib
+    wl.setup(device, rank)
+    peaks = load_peaks()
+    W = max(3, a.warmup)
+
+    def timed(fn, steps, profile=False):
+        for _ in range(W):
+            fn()
+        barrier()
+        if profile:
+            _lib.lib().msmd_profile_reset()
+            _lib.lib().msmd_profile_enable(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        if profile:
+            _lib.lib().msmd_profile_enable(0)
+        return max_over_ranks(e0.elapsed_time(e1))
+
+    with ClockSampler(local) as cs:
+        ms = timed(wl.step, a.steps)
+    clocks = cs.summary()
+    # dominant-kernel duration, measured live with CUDA events on the launching stream
+    timed(wl.step, min(a.steps, 10), profile=True)
+    kms, kn = _lib.profile_query(wl.kernel)
+    kernel_ms = kms / max(1, kn)
+    ms_e2e = timed(wl.step_e2e, a.steps)
+    h2d, d2h = wl.e2e_bytes()
+
+    out = dict(metric=wl.metric, value=wl.units() * world * a.steps / (ms * 1e-3), unit=wl.unit, n_gpus=world,
+               steps=a.steps, warmup=W, ms_per_step=ms / a.steps, higher_is_better=True, scaling='weak',
+               vs_baseline=None, dtype=wl.dtype, data='synthetic', config=wl.config(world), clocks=clocks,
+               e2e=dict(value=wl.units() * world * a.steps / (ms_e2e * 1e-3), unit=wl.unit, h2d_bytes_per_step=h2d,
+                        d2h_bytes_per_step=d2h),
+               gpu_launches=wl.launches_per_step() * a.steps,
+               roofline=wl.roofline(peaks, kernel_ms))
+    if rank == 0:
+        if world == 1 and not a.no_cpu_baseline:
+            out['cpu_baseline'] = wl.cpu_reference(10.0)
+        print(json.dumps(out))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == '__main__':
+    sys.exit(main())

@@ -1,0 +1,120 @@
+/*
+ * msmd_b200 — C ABI of the B200-native MSMD speech-to-face hot path.
+ *
+ * The reference (ubisoft/ubisoft-laforge-msmd) is pure Python/PyTorch and has no
+ * FFI of its own; the drop-in boundary is its Python call surface.
+ * Each entry point below names the reference interface it replaces (file:line in
+ * /root/reference).  The Python host modules in ubisoft-laforge-msmd_b200/ keep the
+ * reference signatures and bind these symbols with ctypes.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative msmd_status otherwise;
+ *     msmd_last_error() gives a thread-local message.  Nothing throws.
+ *   - tensor arguments are contiguous row-major DEVICE pointers owned by the
+ *     caller (PyTorch), fp32 unless stated.  Handles own only their packed
+ *     weights and workspaces.  `stream` is a cudaStream_t passed as void*.
+ *   - calls are stream-ordered; no hidden synchronisation after *_create.
+ *   - a handle is bound to one device and is not thread-safe.
+ */
+#ifndef MSMD_B200_H
+#define MSMD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  MSMD_OK = 0,
+  MSMD_ERR_INVALID = -1,   /* bad argument (mirrors the reference's assert / ValueError) */
+  MSMD_ERR_CUDA = -2,      /* CUDA runtime / driver failure */
+  MSMD_ERR_STATE = -3,     /* call order (weights not loaded, window not prepared, ...) */
+  MSMD_ERR_UNSUPPORTED = -4
+} msmd_status;
+
+const char* msmd_last_error(void);
+/* Library/build identification: "msmd_b200 <ver> sm_100a". */
+const char* msmd_version(void);
+
+/* Optional per-kernel-class CUDA-event timing (off by default).  When enabled, instrumented
+ * launches record an event pair on their own stream; msmd_profile_query synchronises those
+ * events and returns the accumulated milliseconds and launch count of one kernel class
+ * ("flame_fused", "gemm_bf16", ...).  Launches inside a CUDA-graph capture are not timed. */
+int msmd_profile_enable(int on);
+int msmd_profile_reset(void);
+int msmd_profile_query(const char* name, double* total_ms, int64_t* launches);
+
+/* ------------------------------------------------------------------------- *
+ * Rotation conversions — utils/rotation_conversions.py:38-569
+ * One fused elementwise kernel per conversion; `n` rotations; in/out packed
+ * [n, k] fp32 with k = 3 (axis-angle, euler), 4 (quaternion wxyz), 6, or 9
+ * (row-major 3x3).  `convention` encodes an Euler convention "ABC" as
+ * a*9 + b*3 + c with X=0,Y=1,Z=2 (ignored by non-Euler kinds).
+ * ------------------------------------------------------------------------- */
+typedef enum {
+  MSMD_ROT_QUAT_TO_MATRIX = 0,        /* quaternion_to_matrix        :38  */
+  MSMD_ROT_MATRIX_TO_QUAT = 1,        /* matrix_to_quaternion        :100 */
+  MSMD_ROT_EULER_TO_MATRIX = 2,       /* euler_angles_to_matrix      :151 */
+  MSMD_ROT_MATRIX_TO_EULER = 3,       /* matrix_to_euler_angles      :219 */
+  MSMD_ROT_AA_TO_QUAT = 4,            /* axis_angle_to_quaternion    :450 */
+  MSMD_ROT_QUAT_TO_AA = 5,            /* quaternion_to_axis_angle    :481 */
+  MSMD_ROT_AA_TO_MATRIX = 6,          /* axis_angle_to_matrix        :418 */
+  MSMD_ROT_MATRIX_TO_AA = 7,          /* matrix_to_axis_angle        :434 */
+  MSMD_ROT_6D_TO_MATRIX = 8,          /* rotation_6d_to_matrix       :513 */
+  MSMD_ROT_MATRIX_TO_6D = 9,          /* matrix_to_rotation_6d       :538 */
+  MSMD_ROT_AA_TO_6D = 10,             /* axis_angle_to_rotation_6d   :555 */
+  MSMD_ROT_STANDARDIZE_QUAT = 11,     /* standardize_quaternion      :326 */
+  MSMD_ROT_QUAT_INVERT = 12,          /* quaternion_invert           :380 */
+  MSMD_ROT_EULER_TO_AA = 13,          /* fused euler->matrix->axis-angle (decode adapter) */
+  MSMD_ROT_RODRIGUES = 14             /* utils/lbs.py:270 batch_rodrigues (||r+1e-8|| quirk) */
+} msmd_rot_kind;
+
+int msmd_rot_convert(int kind, const float* in, float* out, int64_t n, int convention, void* stream);
+
+/* Binary quaternion ops — quaternion_raw_multiply :341, quaternion_multiply :362,
+ * quaternion_apply :396.  a,b already broadcast to [n,4] / [n,3] by the host. */
+typedef enum {
+  MSMD_QUAT_RAW_MULTIPLY = 0,
+  MSMD_QUAT_MULTIPLY = 1,
+  MSMD_QUAT_APPLY = 2
+} msmd_quat_binop;
+
+int msmd_quat_binary(int op, const float* a, const float* b, float* out, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * FLAME decode — utils/flame.py:180-244 (FLAME.forward) -> utils/lbs.py:141-223 (lbs)
+ *
+ * msmd_flame_create packs the static bases once:
+ *   v_template [V,3], shapedirs [V,3,NB], posedirs [(NJ-1)*9, V*3],
+ *   J_regressor [NJ,V], parents [NJ] (int64, parents[0] = -1), lbs_weights [V,NJ].
+ *   Pointers may be host or device (copied with cudaMemcpyDefault).
+ * msmd_flame_decode runs F1-F6 of SURVEY 2.4 fused:
+ *   betas [B,NB]; pose [B,NJ*3] axis-angle if pose2rot else [B,NJ*9] matrices;
+ *   verts_out [B,V,3]; joints_out [B,NJ,3] or NULL.
+ * `impl`: 0 = default (tensor-core path), 1 = CUDA-core reference path (debug).
+ * ------------------------------------------------------------------------- */
+typedef struct msmd_flame msmd_flame;
+
+int msmd_flame_create(const float* v_template, const float* shapedirs, const float* posedirs,
+                      const float* J_regressor, const int64_t* parents, const float* lbs_weights,
+                      int V, int NB, int NJ, int device, msmd_flame** out);
+int msmd_flame_decode(msmd_flame* fh, const float* betas, const float* pose, int pose2rot,
+                      int64_t B, float* verts_out, float* joints_out, int impl, void* stream);
+void msmd_flame_destroy(msmd_flame* fh);
+
+/* Barycentric landmarks — utils/lbs.py:102-138 (vertices2landmarks).
+ * verts [B,V,3]; faces [F,3] int64; lmk_faces_idx [B,L] int64; bary [B,L,3]; out [B,L,3]. */
+int msmd_vertices2landmarks(const float* verts, const int64_t* faces, const int64_t* lmk_faces_idx,
+                            const float* bary, int64_t B, int V, int L, float* out, void* stream);
+
+/* Dynamic face-contour row per frame — utils/flame.py:126-172 (_find_dynamic_lmk_idx_and_bcoords)
+ * with utils/lbs.py:26-32 (rot_mat_to_euler).  full_pose [B,NJ*3] (or [B,NJ*9] if !pose2rot);
+ * neck_chain [n_chain] int64 joint ids (device); out_idx [B] int64 in [0,78]. */
+int msmd_flame_contour_index(const float* full_pose, int pose2rot, int NJ, const int64_t* neck_chain,
+                             int n_chain, int64_t B, int64_t* out_idx, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSMD_B200_H */

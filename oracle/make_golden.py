@@ -1,0 +1,108 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz from the UNMODIFIED reference (build container only).
+
+    python -m oracle.make_golden [rot flame denoiser sampler style audio infer]
+
+Each section seeds its inputs through oracle.synth (so tests can rebuild them without
+the file), runs the reference modules imported from /root/reference via
+oracle.ref_shims, and stores the reference outputs.  The GPU box has no reference:
+tests there compare the CUDA path against these vectors and against the oracle.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+from . import ref_shims, synth
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden')
+
+
+def rot_inputs(n=256, seed=11):
+    """Shared by the generator and the tests: random + edge-case rotations."""
+    g = torch.Generator().manual_seed(seed)
+    aa = torch.randn(n, 3, generator=g) * 1.3
+    aa[:4] = 0.0                     # exact zero angle (series branch)
+    aa[4:8] *= 1e-7                  # tiny angle
+    aa[8] = torch.tensor([np.pi, 0, 0])
+    aa[9] = torch.tensor([0, 3.1, 0])
+    quat = torch.randn(n, 4, generator=g)
+    quat[:4] = torch.tensor([1.0, 0, 0, 0])
+    quat[4] = torch.tensor([-1.0, 0, 0, 0])
+    quat2 = torch.randn(n, 4, generator=g)
+    euler = (torch.rand(n, 3, generator=g) * 2 - 1) * 3.0
+    euler[:2] = 0
+    d6 = torch.randn(n, 6, generator=g)
+    pts = torch.randn(n, 3, generator=g)
+    return dict(aa=aa, quat=quat, quat2=quat2, euler=euler, d6=d6, pts=pts)
+
+
+ROT_CONVENTIONS = ['XYZ', 'YXZ', 'ZYX', 'XZY', 'XYX', 'ZXZ', 'YZY']
+
+
+def gen_rot():
+    rc = ref_shims.ref_modules().rc
+    lbs = ref_shims.ref_modules().lbs
+    i = rot_inputs()
+    o = {}
+    mats = rc.euler_angles_to_matrix(i['euler'], 'YXZ')
+    o['mats'] = mats
+    o['quaternion_to_matrix'] = rc.quaternion_to_matrix(i['quat'])
+    o['matrix_to_quaternion'] = rc.matrix_to_quaternion(mats)
+    for c in ROT_CONVENTIONS:
+        o[f'euler_angles_to_matrix_{c}'] = rc.euler_angles_to_matrix(i['euler'], c)
+        o[f'matrix_to_euler_angles_{c}'] = rc.matrix_to_euler_angles(mats, c)
+    o['axis_angle_to_quaternion'] = rc.axis_angle_to_quaternion(i['aa'])
+    o['quaternion_to_axis_angle'] = rc.quaternion_to_axis_angle(rc.axis_angle_to_quaternion(i['aa']))
+    o['axis_angle_to_matrix'] = rc.axis_angle_to_matrix(i['aa'])
+    o['matrix_to_axis_angle'] = rc.matrix_to_axis_angle(mats)
+    o['rotation_6d_to_matrix'] = rc.rotation_6d_to_matrix(i['d6'])
+    o['matrix_to_rotation_6d'] = rc.matrix_to_rotation_6d(mats)
+    o['axis_angle_to_rotation_6d'] = rc.axis_angle_to_rotation_6d(i['aa'])
+    o['standardize_quaternion'] = rc.standardize_quaternion(i['quat'])
+    o['quaternion_raw_multiply'] = rc.quaternion_raw_multiply(i['quat'], i['quat2'])
+    o['quaternion_multiply'] = rc.quaternion_multiply(i['quat'], i['quat2'])
+    o['quaternion_invert'] = rc.quaternion_invert(i['quat'])
+    o['quaternion_apply'] = rc.quaternion_apply(i['quat'], i['pts'])
+    o['batch_rodrigues'] = lbs.batch_rodrigues(i['aa'])
+    o['euler_to_axis_angle_YXZ'] = rc.matrix_to_axis_angle(rc.euler_angles_to_matrix(i['euler'], 'YXZ'))
+    np.savez_compressed(os.path.join(OUT, 'rot.npz'), **{k: v.numpy() for k, v in o.items()})
+    print('rot.npz', len(o))
+
+
+FLAME_GOLD = dict(B=6, n_shape=300, n_exp=100, seed=3)
+
+
+def gen_flame():
+    cfg = FLAME_GOLD
+    raw = synth.flame_raw(0, synth.FLAME_V, 400)
+    fl = ref_shims.ref_flame(raw, cfg['n_shape'], cfg['n_exp'])
+    sh, ex, po, ey = synth.flame_inputs(cfg['B'], cfg['n_shape'], cfg['n_exp'], cfg['seed'])
+    with torch.no_grad():
+        v, lm2d, lm3d = fl(sh, ex, po, ey)
+        v_nopose, _, _ = fl(sh, ex, None, None, return_lm2d=False, return_lm3d=False)
+        v_noglob, _, _ = fl(sh, ex, po, ey, ignore_global_rot=True, return_lm2d=False, return_lm3d=False)
+        # 100/50 reference default (flame.py:49-50)
+        fl2 = ref_shims.ref_flame(raw, 100, 50)
+        sh2, ex2, po2, ey2 = synth.flame_inputs(cfg['B'], 100, 50, cfg['seed'] + 1)
+        v2, _, _ = fl2(sh2, ex2, po2, ey2, return_lm2d=False, return_lm3d=False)
+    np.savez_compressed(os.path.join(OUT, 'flame.npz'), verts=v.numpy(), lm2d=lm2d.numpy(), lm3d=lm3d.numpy(),
+                        verts_nopose=v_nopose.numpy(), verts_noglob=v_noglob.numpy(), verts_100_50=v2.numpy())
+    print('flame.npz', v.shape)
+
+
+SECTIONS = dict(rot=gen_rot, flame=gen_flame)
+
+
+def main(argv):
+    assert ref_shims.available(), 'needs /root/reference'
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_grad_enabled(False)
+    names = argv or list(SECTIONS)
+    for n in names:
+        SECTIONS[n]()
+
+
+if __name__ == '__main__':
+    main(sys.argv[1:])

@@ -1,0 +1,98 @@
+"""GPU parity: every rotation conversion through the C ABI vs the oracle and the golden vectors."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from oracle import rotations as R
+from oracle.make_golden import ROT_CONVENTIONS, rot_inputs
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def rc(built_lib):
+    from msmd_b200.utils import rotation_conversions
+    return rotation_conversions
+
+
+def _cases(rc, i, mats):
+    from msmd_b200.utils import lbs
+    c = {'quaternion_to_matrix': lambda: rc.quaternion_to_matrix(i['quat']),
+         'matrix_to_quaternion': lambda: rc.matrix_to_quaternion(mats),
+         'axis_angle_to_quaternion': lambda: rc.axis_angle_to_quaternion(i['aa']),
+         'axis_angle_to_matrix': lambda: rc.axis_angle_to_matrix(i['aa']),
+         'matrix_to_axis_angle': lambda: rc.matrix_to_axis_angle(mats),
+         'rotation_6d_to_matrix': lambda: rc.rotation_6d_to_matrix(i['d6']),
+         'matrix_to_rotation_6d': lambda: rc.matrix_to_rotation_6d(mats),
+         'axis_angle_to_rotation_6d': lambda: rc.axis_angle_to_rotation_6d(i['aa']),
+         'standardize_quaternion': lambda: rc.standardize_quaternion(i['quat']),
+         'quaternion_raw_multiply': lambda: rc.quaternion_raw_multiply(i['quat'], i['quat2']),
+         'quaternion_multiply': lambda: rc.quaternion_multiply(i['quat'], i['quat2']),
+         'quaternion_invert': lambda: rc.quaternion_invert(i['quat']),
+         'quaternion_apply': lambda: rc.quaternion_apply(i['quat'], i['pts']),
+         'batch_rodrigues': lambda: lbs.batch_rodrigues(i['aa']),
+         'euler_to_axis_angle_YXZ': lambda: rc.euler_angles_to_axis_angle(i['euler'], 'YXZ')}
+    for cv in ROT_CONVENTIONS:
+        c[f'euler_angles_to_matrix_{cv}'] = (lambda cv=cv: rc.euler_angles_to_matrix(i['euler'], cv))
+        c[f'matrix_to_euler_angles_{cv}'] = (lambda cv=cv: rc.matrix_to_euler_angles(mats, cv))
+    return c
+
+
+def _tol(k):
+    # fp32 device libm vs host libm; matrix->axis-angle near pi is ill-conditioned in the reference formula itself
+    return 3e-5 if k in ('matrix_to_axis_angle', 'euler_to_axis_angle_YXZ', 'quaternion_to_axis_angle') else 4e-6
+
+
+def test_rotations_match_golden_and_oracle(rc):
+    gold = np.load(os.path.join(GOLDEN, 'rot.npz'))
+    i = {k: v.cuda() for k, v in rot_inputs().items()}
+    mats = torch.from_numpy(gold['mats']).cuda()
+    cases = _cases(rc, i, mats)
+    cases['quaternion_to_axis_angle'] = lambda: rc.quaternion_to_axis_angle(
+        torch.from_numpy(gold['axis_angle_to_quaternion']).cuda())
+    assert set(cases) | {'mats'} == set(gold.files)
+    for k, fn in cases.items():
+        got = fn().cpu().numpy()
+        assert got.shape == gold[k].shape, k
+        assert np.abs(got - gold[k]).max() <= _tol(k), (k, np.abs(got - gold[k]).max())
+
+
+def test_rotations_large_ragged_and_empty(rc):
+    """Sizes that exercise the grid-stride loop, the unaligned tail block and n=0; leading dims broadcast."""
+    g = torch.Generator().manual_seed(5)
+    for n in (1, 255, 257, 100_003):
+        aa = torch.randn(n, 3, generator=g)
+        got = rc.axis_angle_to_matrix(aa.cuda()).cpu().numpy()
+        assert np.abs(got - R.axis_angle_to_matrix(aa.numpy())).max() < 4e-6
+        e = torch.randn(n, 3, generator=g)
+        got = rc.euler_angles_to_axis_angle(e.cuda(), 'YXZ').cpu().numpy()
+        want = R.matrix_to_axis_angle(R.euler_angles_to_matrix(e.numpy(), 'YXZ'))
+        close = np.abs(got - want).max(-1) < 5e-5
+        assert close.mean() > 0.999  # the lossy sqrt/copysign formula flips sign exactly at pi
+    assert rc.axis_angle_to_matrix(torch.zeros(0, 3).cuda()).shape == (0, 3, 3)
+    x = torch.randn(4, 5, 3, generator=g)
+    assert rc.axis_angle_to_matrix(x.cuda()).shape == (4, 5, 3, 3)
+    sl = torch.randn(64, 6, generator=g).cuda()[:, 1:4]     # non-contiguous input
+    assert np.abs(rc.axis_angle_to_quaternion(sl).cpu().numpy() -
+                  R.axis_angle_to_quaternion(sl.cpu().numpy())).max() < 4e-6
+    q = torch.randn(7, 1, 4, generator=g)
+    p = torch.randn(1, 9, 3, generator=g)
+    got = rc.quaternion_apply(q.cuda(), p.cuda()).cpu().numpy()
+    assert got.shape == (7, 9, 3)
+    assert np.abs(got - R.quaternion_apply(q.numpy(), p.numpy())).max() < 1e-5
+
+
+def test_rotation_round_trips_at_scale(rc):
+    """Size-independent properties at 4M rotations: R R^T = I, euler round trip, quaternion norm."""
+    n = 4_000_000
+    e = (torch.rand(n, 3, device='cuda') * 2 - 1) * 1.2
+    m = rc.euler_angles_to_matrix(e, 'YXZ')
+    eye = torch.eye(3, device='cuda')
+    assert (m @ m.transpose(1, 2) - eye).abs().max() < 2e-6
+    assert (rc.matrix_to_euler_angles(m, 'YXZ') - e).abs().max() < 2e-5
+    q = rc.axis_angle_to_quaternion(e)
+    assert (q.norm(dim=-1) - 1).abs().max() < 2e-6
+    assert (rc.quaternion_to_axis_angle(q) - e).abs().max() < 2e-5

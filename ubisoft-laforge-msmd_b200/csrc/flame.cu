@@ -1,0 +1,417 @@
+// FLAME decode: pack + per-frame pose/chain kernel + CUDA-core fused blendshape/LBS kernel.
+//
+// Replaces utils/flame.py:180-244 (FLAME.forward) and utils/lbs.py:141-371 (lbs, blend_shapes,
+// vertices2joints, batch_rodrigues, batch_rigid_transform).  The reference materialises
+// v_shaped, pose_offsets, the per-vertex 4x4 T ([B,V,16] = 2.6 GB at B=8192) and v_homo; here
+// one GEMM over K = NB + 36 produces v_posed - template tile by tile and the skinning is its
+// epilogue, so HBM sees only betas/pose in and vertices out.
+#include "flame.cuh"
+#include "rot_math.cuh"
+#include "profile.cuh"
+#include <vector>
+#include <cstring>
+
+namespace msmd {
+
+// ---------------------------------------------------------------------------------------
+// Per-frame kernel: one warp per frame.
+//   A[b] = betas[b] | vec(R[1:] - I) | 0          (lbs.py:200-201 pose_feature)
+//   J[b] = Jt + Jb @ betas[b]                     (lbs.py:189 with the regressor folded)
+//   chain (lbs.py:317-371) -> xf[b][j] = G_j (9) | t_j - G_j J_j (3)
+// ---------------------------------------------------------------------------------------
+template <int NJ>
+__global__ void __launch_bounds__(256) flame_pose_kernel(const float* __restrict__ betas, const float* __restrict__ pose,
+                                                         int pose2rot, int64_t B, int NB, int Kpad,
+                                                         const float* __restrict__ Jt, const float* __restrict__ Jb,
+                                                         const int* __restrict__ parents_g, float* __restrict__ A,
+                                                         float* __restrict__ A_hi, float* __restrict__ A_lo,
+                                                         float* __restrict__ xf, float* __restrict__ joints_out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const float* be = betas + b * NB;
+  float* Arow = A + b * Kpad;
+  float acc[NJ * 3];
+#pragma unroll
+  for (int i = 0; i < NJ * 3; ++i) acc[i] = 0.f;
+  for (int k = lane; k < NB; k += 32) {
+    const float v = be[k];
+    Arow[k] = v;
+    if (A_hi) {
+      const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+      A_hi[b * Kpad + k] = hi;
+      A_lo[b * Kpad + k] = v - hi;
+    }
+#pragma unroll
+    for (int i = 0; i < NJ * 3; ++i) acc[i] = fmaf(Jb[i * NB + k], v, acc[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < NJ * 3; ++i) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+  }
+  const int K = NB + (NJ - 1) * 9;
+  for (int k = K + lane; k < Kpad; k += 32) {
+    Arow[k] = 0.f;
+    if (A_hi) { A_hi[b * Kpad + k] = 0.f; A_lo[b * Kpad + k] = 0.f; }
+  }
+  if (lane != 0) return;
+
+  float J[NJ][3];
+#pragma unroll
+  for (int j = 0; j < NJ; ++j)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) J[j][c] = Jt[j * 3 + c] + acc[j * 3 + c];
+
+  Mat3 R[NJ];
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    if (pose2rot) {
+      const float* p = pose + b * NJ * 3 + j * 3;
+      R[j] = rodrigues(p[0], p[1], p[2]);
+    } else {
+      const float* p = pose + b * NJ * 9 + j * 9;
+#pragma unroll
+      for (int i = 0; i < 9; ++i) R[j].m[i] = p[i];
+    }
+  }
+#pragma unroll
+  for (int j = 1; j < NJ; ++j)
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+      const float v = R[j].m[i] - ((i % 4 == 0) ? 1.0f : 0.0f);
+      const int k = NB + (j - 1) * 9 + i;
+      Arow[k] = v;
+      if (A_hi) {
+        const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+        A_hi[b * Kpad + k] = hi;
+        A_lo[b * Kpad + k] = v - hi;
+      }
+    }
+
+  Mat3 G[NJ];
+  float t[NJ][3];
+  G[0] = R[0];
+  t[0][0] = J[0][0]; t[0][1] = J[0][1]; t[0][2] = J[0][2];
+#pragma unroll
+  for (int j = 1; j < NJ; ++j) {
+    const int p = parents_g[j];
+    float rel[3] = {J[j][0] - J[p][0], J[j][1] - J[p][1], J[j][2] - J[p][2]};
+    G[j] = mat3_mul(G[p], R[j]);
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+      t[j][i] = G[p].m[i * 3 + 0] * rel[0] + G[p].m[i * 3 + 1] * rel[1] + G[p].m[i * 3 + 2] * rel[2] + t[p][i];
+  }
+  float* x = xf + b * NJ * 12;
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) x[j * 12 + i] = G[j].m[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+      x[j * 12 + 9 + i] =
+          t[j][i] - (G[j].m[i * 3 + 0] * J[j][0] + G[j].m[i * 3 + 1] * J[j][1] + G[j].m[i * 3 + 2] * J[j][2]);
+    if (joints_out) {
+      joints_out[b * NJ * 3 + j * 3 + 0] = t[j][0];
+      joints_out[b * NJ * 3 + j * 3 + 1] = t[j][1];
+      joints_out[b * NJ * 3 + j * 3 + 2] = t[j][2];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// CUDA-core fused kernel (impl=1; also the cross-check of the tensor-core path).
+// Tile: 64 frames x 96 columns (32 vertices), BK=16, 256 threads, 4x6 register tile.
+// ---------------------------------------------------------------------------------------
+constexpr int FBM = 64, FBN = 96, FBK = 16;
+
+template <int NJ>
+__global__ void __launch_bounds__(256) flame_simt_kernel(const float* __restrict__ A, const float* __restrict__ basis,
+                                                         const float* __restrict__ tmpl, const float* __restrict__ W,
+                                                         const float* __restrict__ xf, int64_t B, int V, int Kpad,
+                                                         float* __restrict__ out) {
+  __shared__ float As[FBK][FBM + 4];
+  __shared__ float Bs[FBK][FBN + 4];
+  __shared__ float sXf[FBM][NJ * 12 + 1];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;  // tx: vertex pair, ty: frame quad
+  const int64_t row0 = (int64_t)blockIdx.y * FBM;
+  const int col0 = blockIdx.x * FBN;
+  const int N3 = 3 * V;
+
+  for (int i = tid; i < FBM * NJ * 12; i += 256) {
+    const int r = i / (NJ * 12), c = i % (NJ * 12);
+    const int64_t rr = min(row0 + r, B - 1);
+    sXf[r][c] = xf[rr * NJ * 12 + c];
+  }
+
+  float acc[4][6];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 6; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < Kpad; k0 += FBK) {
+    {  // A tile: 64 rows x 16 k = 256 float4
+      const int r = tid >> 2, q = tid & 3;
+      const int64_t rr = min(row0 + r, B - 1);
+      const float4 v = *reinterpret_cast<const float4*>(A + rr * Kpad + k0 + q * 4);
+      As[q * 4 + 0][r] = v.x; As[q * 4 + 1][r] = v.y; As[q * 4 + 2][r] = v.z; As[q * 4 + 3][r] = v.w;
+    }
+    for (int i = tid; i < FBN * 4; i += 256) {  // basis tile: 96 rows x 16 k = 384 float4 (rows padded to N3pad)
+      const int r = i >> 2, q = i & 3;
+      const float4 v = *reinterpret_cast<const float4*>(basis + (int64_t)(col0 + r) * Kpad + k0 + q * 4);
+      Bs[q * 4 + 0][r] = v.x; Bs[q * 4 + 1][r] = v.y; Bs[q * 4 + 2][r] = v.z; Bs[q * 4 + 3][r] = v.w;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < FBK; ++k) {
+      float a[4], bb[6];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[k][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 6; ++j) bb[j] = Bs[k][tx * 6 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 6; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+  // Epilogue: v_posed = acc + template; blend the NJ affines with W[v]; apply (lbs.py:210-221).
+#pragma unroll
+  for (int vv = 0; vv < 2; ++vv) {
+    const int n0 = col0 + tx * 6 + vv * 3;
+    const int v = n0 / 3;
+    if (n0 >= N3) continue;
+    float w[NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) w[j] = W[v * NJ + j];
+    const float t0 = tmpl[n0], t1 = tmpl[n0 + 1], t2 = tmpl[n0 + 2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = ty * 4 + i;
+      if (row0 + r >= B) continue;
+      float T[12];
+#pragma unroll
+      for (int e = 0; e < 12; ++e) {
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) s = fmaf(w[j], sXf[r][j * 12 + e], s);
+        T[e] = s;
+      }
+      const float px = acc[i][vv * 3 + 0] + t0, py = acc[i][vv * 3 + 1] + t1, pz = acc[i][vv * 3 + 2] + t2;
+      float* o = out + (row0 + r) * N3 + n0;
+      o[0] = T[0] * px + T[1] * py + T[2] * pz + T[9];
+      o[1] = T[3] * px + T[4] * py + T[5] * pz + T[10];
+      o[2] = T[6] * px + T[7] * py + T[8] * pz + T[11];
+    }
+  }
+}
+
+// utils/lbs.py:102-138 vertices2landmarks: one thread per (b, l, xyz)
+__global__ void landmarks_kernel(const float* __restrict__ verts, const int64_t* __restrict__ faces,
+                                 const int64_t* __restrict__ idx, const float* __restrict__ bary, int64_t B, int V,
+                                 int L, float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * L * 3) return;
+  const int c = (int)(i % 3);
+  const int64_t bl = i / 3;
+  const int64_t b = bl / L;
+  const int64_t f = idx[bl];
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) s += verts[(b * V + faces[f * 3 + k]) * 3 + c] * bary[bl * 3 + k];
+  out[i] = s;
+}
+
+// utils/flame.py:126-172 (_find_dynamic_lmk_idx_and_bcoords) + utils/lbs.py:26-32 (rot_mat_to_euler):
+// compose the neck kinematic chain, take the yaw in whole degrees (round-half-even, clamp 39) and map
+// it to a row of the 79-entry contour table.
+__global__ void contour_index_kernel(const float* __restrict__ pose, int pose2rot, int NJ,
+                                     const int64_t* __restrict__ chain, int n_chain, int64_t B,
+                                     int64_t* __restrict__ out) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  Mat3 rel = {{1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f}};
+  for (int i = 0; i < n_chain; ++i) {
+    const int j = (int)chain[i];
+    Mat3 R;
+    if (pose2rot) {
+      const float* p = pose + (b * NJ + j) * 3;
+      R = rodrigues(p[0], p[1], p[2]);
+    } else {
+      const float* p = pose + (b * NJ + j) * 9;
+      for (int k = 0; k < 9; ++k) R.m[k] = p[k];
+    }
+    rel = mat3_mul(R, rel);
+  }
+  const float sy = sqrtf(rel.m[0] * rel.m[0] + rel.m[3] * rel.m[3]);
+  const float ang = atan2f(-rel.m[6], sy) * 180.0f / 3.14159265358979323846f;
+  long long y = (long long)rintf(fminf(ang, 39.0f));
+  if (y < 0) y = (y < -39) ? 78 : (39 - y);
+  out[b] = y;
+}
+
+static int ensure_workspace(msmd_flame* fh, int64_t B) {
+  if (B <= fh->cap_B) return MSMD_OK;
+  cudaFree(fh->A); cudaFree(fh->A_hi); cudaFree(fh->A_lo); cudaFree(fh->xf);
+  fh->A = fh->A_hi = fh->A_lo = fh->xf = nullptr;
+  fh->cap_B = 0;
+  const int64_t cap = ((B + 127) / 128) * 128;  // whole 128-frame tiles for the TMA path
+  MSMD_CHECK_CUDA(cudaMalloc(&fh->A, cap * fh->Kpad * sizeof(float)));
+  MSMD_CHECK_CUDA(cudaMalloc(&fh->A_hi, cap * fh->Kpad * sizeof(float)));
+  MSMD_CHECK_CUDA(cudaMalloc(&fh->A_lo, cap * fh->Kpad * sizeof(float)));
+  MSMD_CHECK_CUDA(cudaMalloc(&fh->xf, cap * fh->NJ * 12 * sizeof(float)));
+  MSMD_CHECK_CUDA(cudaMemset(fh->A, 0, cap * fh->Kpad * sizeof(float)));
+  MSMD_CHECK_CUDA(cudaMemset(fh->A_hi, 0, cap * fh->Kpad * sizeof(float)));
+  MSMD_CHECK_CUDA(cudaMemset(fh->A_lo, 0, cap * fh->Kpad * sizeof(float)));
+  MSMD_CHECK_CUDA(cudaMemset(fh->xf, 0, cap * fh->NJ * 12 * sizeof(float)));
+  fh->cap_B = cap;
+  return MSMD_OK;
+}
+
+}  // namespace msmd
+
+using namespace msmd;
+
+extern "C" int msmd_flame_create(const float* v_template, const float* shapedirs, const float* posedirs,
+                                 const float* J_regressor, const int64_t* parents, const float* lbs_weights, int V,
+                                 int NB, int NJ, int device, msmd_flame** out) {
+  MSMD_REQUIRE(out, "msmd_flame_create: null out");
+  MSMD_REQUIRE(v_template && shapedirs && posedirs && J_regressor && parents && lbs_weights,
+               "msmd_flame_create: null asset pointer");
+  MSMD_REQUIRE(V > 0 && NB > 0, "msmd_flame_create: bad sizes V=%d NB=%d", V, NB);
+  if (NJ != 5) {
+    set_error("msmd_flame_create: only the 5-joint FLAME kinematic tree is supported (got %d)", NJ);
+    return MSMD_ERR_UNSUPPORTED;
+  }
+  MSMD_CHECK_CUDA(cudaSetDevice(device));
+  const int P = (NJ - 1) * 9;
+  const int N3 = 3 * V, K = NB + P;
+  const int Kpad = (K + 31) / 32 * 32;
+  const int N3pad = (N3 + 383) / 384 * 384;
+  // Stage the assets on the host (they may live on either side); packing is a one-off.
+  std::vector<float> h_t(N3), h_s((size_t)N3 * NB), h_p((size_t)P * N3), h_j((size_t)NJ * V), h_w((size_t)V * NJ);
+  std::vector<int64_t> h_par(NJ);
+  MSMD_CHECK_CUDA(cudaMemcpy(h_t.data(), v_template, h_t.size() * 4, cudaMemcpyDefault));
+  MSMD_CHECK_CUDA(cudaMemcpy(h_s.data(), shapedirs, h_s.size() * 4, cudaMemcpyDefault));
+  MSMD_CHECK_CUDA(cudaMemcpy(h_p.data(), posedirs, h_p.size() * 4, cudaMemcpyDefault));
+  MSMD_CHECK_CUDA(cudaMemcpy(h_j.data(), J_regressor, h_j.size() * 4, cudaMemcpyDefault));
+  MSMD_CHECK_CUDA(cudaMemcpy(h_w.data(), lbs_weights, h_w.size() * 4, cudaMemcpyDefault));
+  MSMD_CHECK_CUDA(cudaMemcpy(h_par.data(), parents, NJ * 8, cudaMemcpyDefault));
+  for (int j = 1; j < NJ; ++j)
+    MSMD_REQUIRE(h_par[j] >= 0 && h_par[j] < j, "msmd_flame_create: parents[%d]=%lld is not an earlier joint", j,
+                 (long long)h_par[j]);
+
+  msmd_flame* fh = new msmd_flame();
+  fh->device = device; fh->V = V; fh->NB = NB; fh->NJ = NJ; fh->N3 = N3; fh->K = K; fh->Kpad = Kpad; fh->N3pad = N3pad;
+  fh->parents[0] = -1;
+  for (int j = 1; j < NJ; ++j) fh->parents[j] = (int)h_par[j];
+
+  std::vector<float> basis((size_t)N3pad * Kpad, 0.f), hi(basis.size(), 0.f), lo(basis.size(), 0.f);
+  for (int n = 0; n < N3; ++n) {
+    float* row = basis.data() + (size_t)n * Kpad;
+    memcpy(row, h_s.data() + (size_t)n * NB, NB * sizeof(float));
+    for (int p = 0; p < P; ++p) row[NB + p] = h_p[(size_t)p * N3 + n];
+  }
+  for (size_t i = 0; i < basis.size(); ++i) {
+    uint32_t u;
+    memcpy(&u, &basis[i], 4);
+    u &= 0xffffe000u;
+    memcpy(&hi[i], &u, 4);
+    lo[i] = basis[i] - hi[i];
+  }
+  // Joint regression folded through the blendshapes (double accumulation on the host).
+  std::vector<float> Jt(NJ * 3), Jb((size_t)NJ * 3 * NB);
+  for (int j = 0; j < NJ; ++j)
+    for (int c = 0; c < 3; ++c) {
+      double s = 0;
+      for (int v = 0; v < V; ++v) s += (double)h_j[(size_t)j * V + v] * h_t[(size_t)v * 3 + c];
+      Jt[j * 3 + c] = (float)s;
+      for (int l = 0; l < NB; ++l) {
+        double a = 0;
+        for (int v = 0; v < V; ++v) a += (double)h_j[(size_t)j * V + v] * h_s[((size_t)v * 3 + c) * NB + l];
+        Jb[(size_t)(j * 3 + c) * NB + l] = (float)a;
+      }
+    }
+  auto up = [&](float** d, const std::vector<float>& h) -> int {
+    MSMD_CHECK_CUDA(cudaMalloc(d, h.size() * sizeof(float)));
+    MSMD_CHECK_CUDA(cudaMemcpy(*d, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
+    return MSMD_OK;
+  };
+  int rc = MSMD_OK;
+  if ((rc = up(&fh->basis, basis)) || (rc = up(&fh->basis_hi, hi)) || (rc = up(&fh->basis_lo, lo)) ||
+      (rc = up(&fh->v_template, h_t)) || (rc = up(&fh->weights, h_w)) || (rc = up(&fh->Jt, Jt)) ||
+      (rc = up(&fh->Jb, Jb))) {
+    msmd_flame_destroy(fh);
+    return rc;
+  }
+  if (cudaMalloc(&fh->d_parents, 8 * sizeof(int)) != cudaSuccess ||
+      cudaMemcpy(fh->d_parents, fh->parents, 8 * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) {
+    msmd_flame_destroy(fh);
+    set_error("msmd_flame_create: parents upload failed");
+    return MSMD_ERR_CUDA;
+  }
+  *out = fh;
+  return MSMD_OK;
+}
+
+extern "C" void msmd_flame_destroy(msmd_flame* fh) {
+  if (!fh) return;
+  flame_tc_destroy(fh);
+  cudaFree(fh->basis); cudaFree(fh->basis_hi); cudaFree(fh->basis_lo); cudaFree(fh->v_template);
+  cudaFree(fh->weights); cudaFree(fh->Jt); cudaFree(fh->Jb); cudaFree(fh->d_parents);
+  cudaFree(fh->A); cudaFree(fh->A_hi); cudaFree(fh->A_lo); cudaFree(fh->xf);
+  delete fh;
+}
+
+extern "C" int msmd_flame_decode(msmd_flame* fh, const float* betas, const float* pose, int pose2rot, int64_t B,
+                                 float* verts_out, float* joints_out, int impl, void* stream) {
+  MSMD_REQUIRE(fh, "msmd_flame_decode: null handle");
+  MSMD_REQUIRE(B >= 0, "msmd_flame_decode: negative batch");
+  if (B == 0) return MSMD_OK;
+  MSMD_REQUIRE(betas && pose && verts_out, "msmd_flame_decode: null tensor pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = ensure_workspace(fh, B);
+  if (rc) return rc;
+  flame_pose_kernel<5><<<cdiv(B, 8), 256, 0, st>>>(betas, pose, pose2rot, B, fh->NB, fh->Kpad, fh->Jt, fh->Jb,
+                                                  fh->d_parents, fh->A, impl == 0 ? fh->A_hi : nullptr,
+                                                  impl == 0 ? fh->A_lo : nullptr, fh->xf, joints_out);
+  MSMD_CHECK_LAUNCH();
+  MSMD_REQUIRE(impl == 0 || impl == 1, "msmd_flame_decode: unknown impl %d", impl);
+  if (impl == 0) {
+    rc = flame_decode_tc(fh, B, verts_out, st);
+    if (rc != MSMD_ERR_UNSUPPORTED) return rc;  // TEMPORARY until flame_tc.cu lands: run the CUDA-core kernel
+  }
+  ProfileScope prof("flame_fused", st);
+  dim3 grid(cdiv(fh->N3, FBN), cdiv(B, FBM));
+  flame_simt_kernel<5><<<grid, 256, 0, st>>>(fh->A, fh->basis, fh->v_template, fh->weights, fh->xf, B, fh->V,
+                                            fh->Kpad, verts_out);
+  MSMD_CHECK_LAUNCH();
+  return MSMD_OK;
+}
+
+extern "C" int msmd_vertices2landmarks(const float* verts, const int64_t* faces, const int64_t* lmk_faces_idx,
+                                       const float* bary, int64_t B, int V, int L, float* out, void* stream) {
+  MSMD_REQUIRE(B >= 0 && L >= 0 && V > 0, "msmd_vertices2landmarks: bad sizes");
+  if (B == 0 || L == 0) return MSMD_OK;
+  MSMD_REQUIRE(verts && faces && lmk_faces_idx && bary && out, "msmd_vertices2landmarks: null pointer");
+  const int64_t n = B * L * 3;
+  landmarks_kernel<<<cdiv(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(verts, faces, lmk_faces_idx, bary, B,
+                                                                              V, L, out);
+  MSMD_CHECK_LAUNCH();
+  return MSMD_OK;
+}
+
+extern "C" int msmd_flame_contour_index(const float* full_pose, int pose2rot, int NJ, const int64_t* neck_chain,
+                                        int n_chain, int64_t B, int64_t* out_idx, void* stream) {
+  MSMD_REQUIRE(B >= 0 && NJ > 0 && n_chain >= 0, "msmd_flame_contour_index: bad sizes");
+  if (B == 0) return MSMD_OK;
+  MSMD_REQUIRE(full_pose && neck_chain && out_idx, "msmd_flame_contour_index: null pointer");
+  contour_index_kernel<<<cdiv(B, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(full_pose, pose2rot, NJ,
+                                                                                  neck_chain, n_chain, B, out_idx);
+  MSMD_CHECK_LAUNCH();
+  return MSMD_OK;
+}

@@ -1,0 +1,35 @@
+// FLAME decode handle shared by flame.cu (pack, pose kernel, CUDA-core path) and
+// flame_tc.cu (tcgen05 path).  Replaces utils/flame.py:180-244 + utils/lbs.py:141-371.
+#pragma once
+#include "common.cuh"
+
+struct msmd_flame {
+  int device = 0;
+  int V = 0, NB = 0, NJ = 5;
+  int N3 = 0;      // 3*V output columns (vertex-major, xyz inner)
+  int K = 0;       // NB + 9*(NJ-1): blendshape + pose-corrective depth
+  int Kpad = 0;    // K rounded up to 32 (tf32 k-block)
+  int N3pad = 0;   // N3 rounded up to 384 rows so every tile load is in-bounds
+  int parents[8] = {-1, 0, 1, 1, 1, 0, 0, 0};
+  // static device buffers
+  float* basis = nullptr;     // [N3pad, Kpad] K-major: row n=(v,c): shapedirs[v,c,:] | posedirs[:,n] | 0
+  float* basis_hi = nullptr;  // tf32-truncated copy, and the exact remainder (3-pass split, flame_tc.cu)
+  float* basis_lo = nullptr;
+  float* v_template = nullptr;  // [N3]
+  float* weights = nullptr;     // [V, NJ]
+  float* Jt = nullptr;          // [NJ*3]      J_regressor @ v_template
+  float* Jb = nullptr;          // [NJ*3, NB]  J_regressor @ shapedirs (joint regression folded)
+  int* d_parents = nullptr;     // [8]
+  // per-call workspaces (grown on demand)
+  int64_t cap_B = 0;
+  float* A = nullptr;     // [cap_B, Kpad]  betas | pose_feature | 0
+  float* A_hi = nullptr;  // tf32 split of A
+  float* A_lo = nullptr;
+  float* xf = nullptr;    // [cap_B, NJ, 12] skinning affines: G (9) | t - G j (3)
+  void* tc_state = nullptr;  // tensor maps etc. owned by flame_tc.cu
+};
+
+namespace msmd {
+int flame_decode_tc(msmd_flame* fh, int64_t B, float* verts_out, cudaStream_t st);  // flame_tc.cu
+void flame_tc_destroy(msmd_flame* fh);
+}  // namespace msmd
