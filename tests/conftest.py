@@ -18,6 +18,9 @@ def pytest_configure(config):
 def built_lib():
     """Make sure the in-tree library exists (built by __graft_entry__.build / build.py)."""
     import build
+    import torch
+    if torch.cuda.is_available() and os.path.exists(build.OUT):
+        return build.OUT          # GPU box: use the prebuilt library that travelled with the snapshot
     return build.build(quiet=True)
 
 

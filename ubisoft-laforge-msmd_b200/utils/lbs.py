@@ -41,7 +41,7 @@ class FlameHandle:
     def decode(self, betas, pose, pose2rot=True, want_joints=True, impl=0):
         B = max(betas.shape[0], pose.shape[0])
         betas = _lib.as_f32c(betas.expand(B, -1))
-        pose = _lib.as_f32c(pose.reshape(pose.shape[0], -1).expand(B, -1))
+        pose = _lib.as_f32c(pose.reshape(pose.shape[0], self.NJ * (3 if pose2rot else 9)).expand(B, -1))
         if betas.shape[1] != self.NB:
             raise ValueError(f'betas has {betas.shape[1]} coefficients, model has {self.NB}')
         if pose.shape[1] != self.NJ * (3 if pose2rot else 9):
