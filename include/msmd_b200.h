@@ -83,6 +83,21 @@ typedef enum {
 int msmd_quat_binary(int op, const float* a, const float* b, float* out, int64_t n, void* stream);
 
 /* ------------------------------------------------------------------------- *
+ * Linear layer on the tensor cores — every nn.Linear on the path (model.py:931-961,
+ * nn.TransformerDecoderLayer / nn.MultiheadAttention projections, style_encoder.py:137-175,
+ * HF encoder projections):   out[M,N] = act(x[M,K] . w[N,K]^T + bias[N]) (+ aux[M,N])
+ *   mode 0: x, w bf16; one tcgen05 kind::f16 pass, fp32 accumulation in TMEM.
+ *   mode 1: fp32-grade: x/x_lo and w/w_lo are tf32 hi/lo splits (msmd_split_tf32); three
+ *           kind::tf32 passes (hi*hi + hi*lo + lo*hi).  out/aux fp32.
+ *   ld* are row strides in elements (rows must be 16-byte multiples apart); act 0 none, 1 GELU(erf);
+ *   out_f32 / aux_f32 select fp32 (1) or bf16 (0) for out / aux.
+ * ------------------------------------------------------------------------- */
+int msmd_linear(int mode, const void* x, const void* x_lo, const void* w, const void* w_lo,
+                const float* bias, const void* aux, void* out, int M, int N, int K, int64_t ldx,
+                int64_t ldw, int64_t ldo, int64_t ld_aux, int out_f32, int aux_f32, int act, void* stream);
+int msmd_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------- *
  * FLAME decode — utils/flame.py:180-244 (FLAME.forward) -> utils/lbs.py:141-223 (lbs)
  *
  * msmd_flame_create packs the static bases once:

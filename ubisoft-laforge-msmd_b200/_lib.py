@@ -22,6 +22,8 @@ SIGNATURES = {
     'msmd_profile_query': (_i, [C.c_char_p, C.POINTER(C.c_double), C.POINTER(_i64)]),
     'msmd_rot_convert': (_i, [_i, _vp, _vp, _i64, _i, _vp]),
     'msmd_quat_binary': (_i, [_i, _vp, _vp, _vp, _i64, _vp]),
+    'msmd_linear': (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i64, _i64, _i64, _i, _i, _i, _vp]),
+    'msmd_split_tf32': (_i, [_vp, _vp, _vp, _i64, _vp]),
     'msmd_flame_create': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, C.POINTER(_vp)]),
     'msmd_flame_decode': (_i, [_vp, _vp, _vp, _i, _i64, _vp, _vp, _i, _vp]),
     'msmd_flame_destroy': (None, [_vp]),

@@ -1,0 +1,184 @@
+// Host side of the tcgen05 GEMM core: tensor-map construction, config dispatch, C-ABI test entry.
+#include "gemm_tc.cuh"
+#include "profile.cuh"
+#include <cudaTypedefs.h>
+#include <mutex>
+
+namespace msmd {
+
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  });
+  return fn;
+}
+
+int make_tmap(CUtensorMap* out, const void* base, CUtensorMapDataType dt, int rank, const uint64_t* dims,
+              const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz) {
+  auto enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled entry point unavailable (driver too old?)");
+    return MSMD_ERR_CUDA;
+  }
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) {
+    set_error("tensor map: base address %p is not 16-byte aligned", base);
+    return MSMD_ERR_INVALID;
+  }
+  for (int i = 0; i + 1 < rank; ++i)
+    if (gstr[i] % 16 != 0) {
+      set_error("tensor map: stride %llu bytes is not a multiple of 16", (unsigned long long)gstr[i]);
+      return MSMD_ERR_INVALID;
+    }
+  CUresult r = enc(out, dt, rank, const_cast<void*>(base), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu,%llu box %u,%u)", (int)r, rank,
+              (unsigned long long)gdim[0], (unsigned long long)(rank > 1 ? gdim[1] : 0), bx[0], rank > 1 ? bx[1] : 0);
+    return MSMD_ERR_CUDA;
+  }
+  return MSMD_OK;
+}
+
+int make_tmap_2d(CUtensorMap* out, const void* base, CUtensorMapDataType dt, uint64_t inner, uint64_t outer,
+                 uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer, CUtensorMapSwizzle swz) {
+  uint64_t dims[2] = {inner, outer};
+  uint64_t str[1] = {row_stride_bytes};
+  uint32_t box[2] = {box_inner, box_outer};
+  return make_tmap(out, base, dt, 2, dims, str, box, swz);
+}
+
+static int make_tmap_23(CUtensorMap* out, const void* base, CUtensorMapDataType dt, int esz, uint64_t inner,
+                        uint64_t outer, int64_t row_stride, int batch, int64_t batch_stride, uint32_t box_inner,
+                        uint32_t box_outer) {
+  if (batch <= 1)
+    return make_tmap_2d(out, base, dt, inner, outer, (uint64_t)row_stride * esz, box_inner, box_outer,
+                        CU_TENSOR_MAP_SWIZZLE_128B);
+  uint64_t dims[3] = {inner, outer, (uint64_t)batch};
+  uint64_t str[2] = {(uint64_t)row_stride * esz, (uint64_t)batch_stride * esz};
+  uint32_t box[3] = {box_inner, box_outer, 1};
+  return make_tmap(out, base, dt, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+template <class Cfg, int MODE>
+static int launch_cfg(const GemmDesc& d, cudaStream_t st) {
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  const auto in_dt = MODE == 0 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  const int esz = Cfg::ELT;
+  int rc;
+  if ((rc = make_tmap_23(&p.a_map, d.A, in_dt, esz, d.K, d.M, d.lda, d.batch, d.sA, Cfg::BK, Cfg::BM))) return rc;
+  if ((rc = make_tmap_23(&p.b_map, d.W, in_dt, esz, d.K, d.N, d.ldw, d.batch, d.sW, Cfg::BK, Cfg::BN))) return rc;
+  if (MODE == 1) {
+    MSMD_REQUIRE(d.A_lo && d.W_lo, "gemm: tf32x3 mode needs the lo operands");
+    MSMD_REQUIRE(d.batch <= 1, "gemm: batched tf32x3 is not implemented");
+    if ((rc = make_tmap_23(&p.a_lo_map, d.A_lo, in_dt, esz, d.K, d.M, d.lda, 1, 0, Cfg::BK, Cfg::BM))) return rc;
+    if ((rc = make_tmap_23(&p.b_lo_map, d.W_lo, in_dt, esz, d.K, d.N, d.ldw, 1, 0, Cfg::BK, Cfg::BN))) return rc;
+  }
+  using OutT = typename Cfg::OutT;
+  using AuxT = typename Cfg::AuxT;
+  const auto out_dt = sizeof(OutT) == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  if ((rc = make_tmap_23(&p.out_map, d.out, out_dt, sizeof(OutT), d.N, d.M, d.ldo, d.batch, d.sO, Cfg::OUT_COLS, 32)))
+    return rc;
+  if (Cfg::HAS_AUX) {
+    const auto aux_dt = sizeof(AuxT) == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    if ((rc = make_tmap_23(&p.aux_map, d.aux, aux_dt, sizeof(AuxT), d.N, d.M, d.ld_aux, d.batch, d.sAux,
+                           Cfg::AUX_COLS, 32)))
+      return rc;
+  }
+  p.bias = d.bias;
+  p.M = d.M; p.N = d.N; p.K = d.K;
+  p.act = d.act;
+  p.batch = d.batch < 1 ? 1 : d.batch;
+  p.tiles_m = cdiv(d.M, Cfg::BM);
+  p.tiles_n = cdiv(d.N, Cfg::BN);
+  const int tiles = p.tiles_m * p.tiles_n * p.batch;
+  auto kern = gemm_tc_kernel<Cfg, MODE>;
+  static bool attr_set = false;  // per template instantiation
+  if (!attr_set) {
+    MSMD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int grid = tiles < kNumSMs ? tiles : kNumSMs;
+  ProfileScope prof(MODE == 0 ? "gemm_bf16" : "gemm_tf32x3", st);
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(p);
+  MSMD_CHECK_LAUNCH();
+  return MSMD_OK;
+}
+
+int gemm_tc_launch(const GemmDesc& d, cudaStream_t st) {
+  MSMD_REQUIRE(d.M > 0 && d.N > 0 && d.K > 0, "gemm: empty problem %dx%dx%d", d.M, d.N, d.K);
+  MSMD_REQUIRE(d.A && d.W && d.out, "gemm: null operand");
+  using bf = __nv_bfloat16;
+  const bool aux = d.aux != nullptr;
+  if (d.mode == 0) {
+    // narrow outputs (N <= 128) use the 128-wide tile so small problems still spread over SMs
+    const bool narrow = d.N <= 128;
+    if (!aux) {
+      if (d.out_f32) {
+        return narrow ? launch_cfg<GemmCfg<0, 128, 4, false, float, float>, 0>(d, st)
+                      : launch_cfg<GemmCfg<0, 256, 4, false, float, float>, 0>(d, st);
+      }
+      if (d.gelu_heavy && !narrow) return launch_cfg<GemmCfg<0, 256, 8, false, bf, bf>, 0>(d, st);
+      return narrow ? launch_cfg<GemmCfg<0, 128, 4, false, bf, bf>, 0>(d, st)
+                    : launch_cfg<GemmCfg<0, 256, 4, false, bf, bf>, 0>(d, st);
+    }
+    if (d.out_f32 && !d.aux_f32) return launch_cfg<GemmCfg<0, 256, 4, true, float, bf>, 0>(d, st);
+    if (d.out_f32 && d.aux_f32) return launch_cfg<GemmCfg<0, 256, 4, true, float, float>, 0>(d, st);
+    if (!d.out_f32 && !d.aux_f32) return launch_cfg<GemmCfg<0, 256, 4, true, bf, bf>, 0>(d, st);
+    set_error("gemm: bf16 output with fp32 aux is not instantiated");
+    return MSMD_ERR_UNSUPPORTED;
+  }
+  MSMD_REQUIRE(d.mode == 1, "gemm: unknown mode %d", d.mode);
+  MSMD_REQUIRE(d.out_f32 && (!aux || d.aux_f32), "gemm: tf32x3 mode is fp32 in / fp32 out");
+  if (aux) return launch_cfg<GemmCfg<1, 128, 4, true, float, float>, 1>(d, st);
+  return launch_cfg<GemmCfg<1, 128, 4, false, float, float>, 1>(d, st);
+}
+
+// tf32 hi/lo split of an fp32 array (hi = value with the low 13 mantissa bits cleared, lo = value - hi)
+__global__ void split_tf32_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+    hi[i] = h;
+    lo[i] = v - h;
+  }
+}
+
+int split_tf32(const float* x, float* hi, float* lo, int64_t n, cudaStream_t st) {
+  if (n == 0) return MSMD_OK;
+  const int blocks = (int)std::min<int64_t>((n + 255) / 256, (int64_t)kNumSMs * 8);
+  split_tf32_kernel<<<blocks, 256, 0, st>>>(x, hi, lo, n);
+  MSMD_CHECK_LAUNCH();
+  return MSMD_OK;
+}
+
+}  // namespace msmd
+
+using namespace msmd;
+
+// y = act(x W^T + b) (+ aux): the nn.Linear calls of model.py:931-961 / style_encoder.py / HF encoder.
+extern "C" int msmd_linear(int mode, const void* x, const void* x_lo, const void* w, const void* w_lo,
+                           const float* bias, const void* aux, void* out, int M, int N, int K, int64_t ldx,
+                           int64_t ldw, int64_t ldo, int64_t ld_aux, int out_f32, int aux_f32, int act, void* stream) {
+  GemmDesc d;
+  d.mode = mode; d.A = x; d.A_lo = x_lo; d.W = w; d.W_lo = w_lo; d.bias = bias; d.aux = aux; d.out = out;
+  d.M = M; d.N = N; d.K = K; d.lda = ldx; d.ldw = ldw; d.ldo = ldo; d.ld_aux = ld_aux;
+  d.out_f32 = out_f32; d.aux_f32 = aux_f32; d.act = act & 1; d.gelu_heavy = (act & 1);
+  return gemm_tc_launch(d, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int msmd_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream) {
+  MSMD_REQUIRE(n >= 0, "msmd_split_tf32: negative count");
+  MSMD_REQUIRE(n == 0 || (x && hi && lo), "msmd_split_tf32: null pointer");
+  return split_tf32(x, hi, lo, n, static_cast<cudaStream_t>(stream));
+}

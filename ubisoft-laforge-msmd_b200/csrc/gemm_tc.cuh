@@ -1,0 +1,364 @@
+// tcgen05 / TMEM / TMA GEMM core:  out[M,N] = act(A[M,K] . W[N,K]^T + bias) (+ aux)
+//
+// Both operands are K-major (nn.Linear layout), fetched by TMA into 128-byte-swizzled shared-memory
+// tiles and multiplied by tcgen05.mma with the fp32 accumulator in TMEM.  Warp roles (one CTA per SM,
+// persistent over tiles):   warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner,
+// warps 2.. = epilogue (TMEM -> registers -> swizzled smem -> TMA store), double-buffered accumulators
+// so the epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// MODE 0: bf16 operands, one pass (kind::f16).
+// MODE 1: fp32-grade "tf32x3": operands pre-split into hi (tf32-exact) + lo (remainder); three
+//         kind::tf32 MMAs per k-step (hi*hi + hi*lo + lo*hi), error ~2^-21 relative.
+#pragma once
+#include "common.cuh"
+#include "tc_common.cuh"
+#include <cuda_bf16.h>
+
+namespace msmd {
+
+struct GemmParams {
+  CUtensorMap a_map, b_map;        // MODE 0: bf16 A / W.  MODE 1: hi parts (fp32)
+  CUtensorMap a_lo_map, b_lo_map;  // MODE 1 only
+  CUtensorMap out_map;             // box {128B worth of columns, 32 rows}, SWIZZLE_128B
+  CUtensorMap aux_map;             // same box geometry in AuxT
+  const float* bias;               // [N] or nullptr
+  int M, N, K;
+  int act;                         // 0 none, 1 exact-erf GELU
+  int batch;                       // z tiles (3-D maps) or 1
+  int tiles_m, tiles_n;
+};
+
+template <int MODE, int BN_, int EPI_WARPS_, bool HAS_AUX_, typename OutT_, typename AuxT_>
+struct GemmCfg {
+  using OutT = OutT_;
+  using AuxT = AuxT_;
+  static constexpr int BN = BN_, EPI_WARPS = EPI_WARPS_;
+  static constexpr bool HAS_AUX = HAS_AUX_;
+  static constexpr int BM = 128;
+  static constexpr int ELT = MODE == 0 ? 2 : 4;
+  static constexpr int BK = 128 / ELT;  // one 128-byte swizzle atom of K per stage
+  static constexpr int UK = 32 / ELT;   // K per tcgen05.mma (32 bytes)
+  static constexpr int A_BYTES = BM * 128, B_BYTES = BN * 128;
+  static constexpr int NSPLIT = MODE == 0 ? 1 : 2;
+  static constexpr int STAGE_BYTES = NSPLIT * (A_BYTES + B_BYTES);
+  static constexpr int OUT_COLS = 128 / (int)sizeof(OutT);
+  static constexpr int AUX_COLS = 128 / (int)sizeof(AuxT);
+  static constexpr int EPI_WARP_BYTES = 4096 + (HAS_AUX ? 8192 : 0);
+  static constexpr int EPI_BYTES = EPI_WARPS * EPI_WARP_BYTES;
+  static constexpr int BAR_BYTES = 1024;
+  static constexpr int BUDGET = 227 * 1024 - 1024 /*alignment slack*/ - BAR_BYTES;
+  static constexpr int STAGES_RAW = (BUDGET - EPI_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
+  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES;
+  static constexpr int THREADS = 64 + 32 * EPI_WARPS;
+  // MODE 1 keeps the small cross terms (hi*lo + lo*hi) in their own accumulator: the tensor core adds into
+  // the accumulator with truncation, so the error grows with the number of MMAs chained on one accumulator.
+  static constexpr int ACC_COLS = NSPLIT * BN;  // TMEM columns per accumulator stage
+  static constexpr int TMEM_NEED = 2 * ACC_COLS;
+  static constexpr int TMEM_COLS = (TMEM_NEED <= 32) ? 32 : (TMEM_NEED <= 64) ? 64 : (TMEM_NEED <= 128) ? 128 : (TMEM_NEED <= 256) ? 256 : 512;
+  static constexpr int COL_SPLIT = EPI_WARPS / 4;  // column ranges handled by different epilogue warps
+  static constexpr int COLS_PER_WARP = BN / COL_SPLIT;
+  static_assert(EPI_WARPS == 4 || EPI_WARPS == 8, "epilogue warps must cover the 4 TMEM lane quarters");
+  static_assert(BN % 32 == 0 && BN <= 256 && TMEM_NEED <= 512, "BN");
+  static_assert(COLS_PER_WARP % OUT_COLS == 0 && (!HAS_AUX || COLS_PER_WARP % AUX_COLS == 0), "chunking");
+  static_assert(STAGES >= 2, "not enough shared memory for a pipeline");
+};
+
+// erf by Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7): enough for a bf16-rounded GELU, 3x cheaper than erff
+__device__ __forceinline__ float erf_fast(float x) {
+  const float ax = fabsf(x);
+  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float r = 1.0f - p * t * __expf(-ax * ax);
+  return copysignf(r, x);
+}
+template <int MODE>
+__device__ __forceinline__ float gelu_erf(float x) {
+  if constexpr (MODE == 0) return 0.5f * x * (1.0f + erf_fast(x * 0.70710678118654752f));
+  else return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+}
+
+template <class Cfg, int MODE>
+__global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
+  using namespace tc;
+  using OutT = typename Cfg::OutT;
+  using AuxT = typename Cfg::AuxT;
+  constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* stage_base = smem;
+  uint8_t* epi_base = smem + STAGES * Cfg::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_base + Cfg::EPI_BYTES);
+  uint64_t* full_bar = bars;                    // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;          // [STAGES]
+  uint64_t* tfull_bar = bars + 2 * STAGES;      // [2]
+  uint64_t* tempty_bar = bars + 2 * STAGES + 2; // [2]
+  uint64_t* aux_bar = bars + 2 * STAGES + 4;    // [EPI_WARPS][2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4 + 2 * Cfg::EPI_WARPS);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = p.tiles_m * p.tiles_n * p.batch;
+  const int num_kb = (p.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&p.a_map);
+    prefetch_tmap(&p.b_map);
+    prefetch_tmap(&p.out_map);
+    if (MODE == 1) { prefetch_tmap(&p.a_lo_map); prefetch_tmap(&p.b_lo_map); }
+    if (Cfg::HAS_AUX) prefetch_tmap(&p.aux_map);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], Cfg::EPI_WARPS); }
+    for (int i = 0; i < 2 * Cfg::EPI_WARPS; ++i) mbar_init(&aux_bar[i], 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto tile_coords = [&](int t, int& m0, int& n0, int& z) {
+    const int per_z = p.tiles_m * p.tiles_n;
+    z = t / per_z;
+    const int r = t - z * per_z;
+    m0 = (r / p.tiles_n) * BM;
+    n0 = (r % p.tiles_n) * BN;
+  };
+
+  if (warp == 0) {
+    // ------------------------------------------------ TMA producer (lane 0 issues; the warp stays converged)
+    int s = 0;
+    uint32_t ph = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      int m0, n0, z;
+      tile_coords(t, m0, n0, z);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        if (lane == 0) {
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* sa = stage_base + s * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + Cfg::NSPLIT * Cfg::A_BYTES;
+          mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+          if (p.batch > 1) {
+            tma_load_3d(sa, &p.a_map, &full_bar[s], kb * BK, m0, z);
+            tma_load_3d(sb, &p.b_map, &full_bar[s], kb * BK, n0, z);
+          } else {
+            tma_load_2d(sa, &p.a_map, &full_bar[s], kb * BK, m0);
+            tma_load_2d(sb, &p.b_map, &full_bar[s], kb * BK, n0);
+            if (MODE == 1) {
+              tma_load_2d(sa + Cfg::A_BYTES, &p.a_lo_map, &full_bar[s], kb * BK, m0);
+              tma_load_2d(sb + Cfg::B_BYTES, &p.b_lo_map, &full_bar[s], kb * BK, n0);
+            }
+          }
+        }
+        __syncwarp();
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------ MMA issuer (lane 0 issues for the whole CTA)
+    constexpr uint32_t idesc = make_idesc(MODE == 0 ? 1 : 2, BM, BN);
+    int s = 0;
+    uint32_t ph = 0;
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const int a = it & 1;
+      const uint32_t aph = (it >> 1) & 1;
+      const uint32_t d_tmem = tmem_base + a * Cfg::ACC_COLS;
+      if (lane == 0) {
+        mbar_wait(&tempty_bar[a], aph ^ 1);
+        tc_fence_after();
+      }
+      __syncwarp();
+      for (int kb = 0; kb < num_kb; ++kb) {
+        if (lane == 0) {
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(stage_base + s * Cfg::STAGE_BYTES);
+          const uint32_t sb = sa + Cfg::NSPLIT * Cfg::A_BYTES;
+          const uint64_t da = make_smem_desc_sw128(sa), db = make_smem_desc_sw128(sb);
+#pragma unroll
+          for (int k = 0; k < BK / Cfg::UK; ++k) {
+            const uint32_t acc = (kb | k) != 0;
+            if constexpr (MODE == 0) {
+              umma<0>(d_tmem, desc_advance(da, k * 32), desc_advance(db, k * 32), idesc, acc);
+            } else {
+              const uint64_t dal = make_smem_desc_sw128(sa + Cfg::A_BYTES), dbl = make_smem_desc_sw128(sb + Cfg::B_BYTES);
+              umma<1>(d_tmem + BN, desc_advance(dal, k * 32), desc_advance(db, k * 32), idesc, acc);  // lo * hi
+              umma<1>(d_tmem + BN, desc_advance(da, k * 32), desc_advance(dbl, k * 32), idesc, 1u);   // hi * lo
+              umma<1>(d_tmem, desc_advance(da, k * 32), desc_advance(db, k * 32), idesc, acc);        // hi * hi
+            }
+          }
+          umma_commit(&empty_bar[s]);  // smem slot reusable once these MMAs have read it
+        }
+        __syncwarp();
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+      if (lane == 0) umma_commit(&tfull_bar[a]);  // accumulator complete -> epilogue
+      __syncwarp();
+    }
+  } else {
+    // ------------------------------------------------ epilogue warps
+    const int e = warp - 2;
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int csplit = e / 4;               // which column range of the tile
+    uint8_t* my = epi_base + e * Cfg::EPI_WARP_BYTES;
+    uint8_t* out_stage = my;                // [32 rows][128 B], SW128
+    uint8_t* aux_stage = my + 4096;         // 2 x [32 rows][128 B]
+    uint64_t* my_aux_bar = aux_bar + 2 * e;
+    constexpr int CPW = Cfg::COLS_PER_WARP;
+    constexpr int AUX_PER_TILE = Cfg::HAS_AUX ? CPW / Cfg::AUX_COLS : 1;
+    const int swz = lane & 7;
+
+    auto issue_aux = [&](int f) {  // flat aux-chunk index over this CTA's tiles
+      if constexpr (Cfg::HAS_AUX) {
+        const int lt = f / AUX_PER_TILE, ck = f % AUX_PER_TILE;
+        const int t = blockIdx.x + lt * gridDim.x;
+        if (t < num_tiles && lane == 0) {
+          int m0, n0, z;
+          tile_coords(t, m0, n0, z);
+          const int b = f & 1;
+          mbar_expect_tx(&my_aux_bar[b], 4096);
+          const int c0 = n0 + csplit * CPW + ck * Cfg::AUX_COLS;
+          if (p.batch > 1) tma_load_3d(aux_stage + b * 4096, &p.aux_map, &my_aux_bar[b], c0, m0 + q * 32, z);
+          else tma_load_2d(aux_stage + b * 4096, &p.aux_map, &my_aux_bar[b], c0, m0 + q * 32);
+        }
+      }
+    };
+    int af = 0;  // next aux chunk to consume
+    issue_aux(0);
+
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      int m0, n0, z;
+      tile_coords(t, m0, n0, z);
+      const int a = it & 1;
+      const uint32_t aph = (it >> 1) & 1;
+      mbar_wait(&tfull_bar[a], aph);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + a * Cfg::ACC_COLS + csplit * CPW;
+#pragma unroll 1
+      for (int c = 0; c < CPW; c += 32) {
+        uint32_t raw[32];
+        tmem_ld32(t_addr + c, raw);
+        uint32_t raw2[MODE == 1 ? 32 : 1];
+        if constexpr (MODE == 1) tmem_ld32(t_addr + BN + c, raw2);
+        const uint8_t* aux_buf = nullptr;
+        int aux_off = 0;
+        if constexpr (Cfg::HAS_AUX) {
+          if (c % Cfg::AUX_COLS == 0) {
+            __syncwarp();               // every lane is done with the buffer the prefetch will overwrite
+            issue_aux(af + 1);
+            mbar_wait(&my_aux_bar[af & 1], (af >> 1) & 1);
+          }
+          aux_buf = aux_stage + (af & 1) * 4096 + lane * 128;
+          aux_off = (c % Cfg::AUX_COLS) * (int)sizeof(AuxT) / 16;  // first 16-byte chunk of this 32-col slice
+        }
+        tmem_ld_wait();
+        float v[32];
+        const int colg = n0 + csplit * CPW + c;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float x = __uint_as_float(raw[j]);
+          if constexpr (MODE == 1) x += __uint_as_float(raw2[j]);
+          if (p.bias != nullptr) x += (colg + j < p.N) ? __ldg(p.bias + colg + j) : 0.f;
+          if (p.act == 1) x = gelu_erf<MODE>(x);
+          v[j] = x;
+        }
+        if constexpr (Cfg::HAS_AUX) {
+          if constexpr (sizeof(AuxT) == 4) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 r4 = *reinterpret_cast<const float4*>(aux_buf + (((aux_off + j) ^ swz) << 4));
+              v[4 * j + 0] += r4.x; v[4 * j + 1] += r4.y; v[4 * j + 2] += r4.z; v[4 * j + 3] += r4.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 r4 = *reinterpret_cast<const uint4*>(aux_buf + (((aux_off + j) ^ swz) << 4));
+              const uint32_t w[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                v[8 * j + 2 * u + 0] += __uint_as_float(w[u] << 16);
+                v[8 * j + 2 * u + 1] += __uint_as_float(w[u] & 0xffff0000u);
+              }
+            }
+          }
+          if ((c + 32) % Cfg::AUX_COLS == 0) ++af;
+        }
+        // ---- registers -> swizzled staging -> TMA store
+        const int o_off = (c % Cfg::OUT_COLS) * (int)sizeof(OutT) / 16;
+        if (c % Cfg::OUT_COLS == 0) {
+          if (lane == 0) tma_store_wait_read<0>();  // previous store has finished reading the staging tile
+          __syncwarp();
+        }
+        uint8_t* orow = out_stage + lane * 128;
+        if constexpr (sizeof(OutT) == 4) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(orow + (((o_off + j) ^ swz) << 4)) =
+                make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint32_t w[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              __nv_bfloat162 h = __floats2bfloat162_rn(v[8 * j + 2 * u], v[8 * j + 2 * u + 1]);
+              w[u] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            *reinterpret_cast<uint4*>(orow + (((o_off + j) ^ swz) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+        }
+        if ((c + 32) % Cfg::OUT_COLS == 0) {
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            const int c0 = n0 + csplit * CPW + (c / Cfg::OUT_COLS) * Cfg::OUT_COLS;
+            if (p.batch > 1) tma_store_3d(&p.out_map, out_stage, c0, m0 + q * 32, z);
+            else tma_store_2d(&p.out_map, out_stage, c0, m0 + q * 32);
+            tma_store_commit();
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[a]);
+    }
+    if (lane == 0) tma_store_wait<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host-side description of one GEMM call.  Element strides; row-major [rows, K] operands.
+struct GemmDesc {
+  int mode = 0;                 // 0 bf16, 1 tf32x3
+  const void* A = nullptr;      // [M,K] bf16 (mode 0) / fp32 hi (mode 1)
+  const void* A_lo = nullptr;   // mode 1
+  const void* W = nullptr;      // [N,K]
+  const void* W_lo = nullptr;   // mode 1
+  const float* bias = nullptr;  // [N]
+  const void* aux = nullptr;    // [M,N] residual added after bias/activation
+  void* out = nullptr;          // [M,N]
+  int M = 0, N = 0, K = 0;
+  int64_t lda = 0, ldw = 0, ldo = 0, ld_aux = 0;  // row strides (elements)
+  int out_f32 = 0, aux_f32 = 0;
+  int act = 0;
+  // optional batch (z) dimension: strides in elements; batch<=1 means plain 2-D
+  int batch = 1;
+  int64_t sA = 0, sW = 0, sO = 0, sAux = 0;
+  int gelu_heavy = 0;           // use 8 epilogue warps
+};
+
+int gemm_tc_launch(const GemmDesc& d, cudaStream_t st);
+
+}  // namespace msmd
