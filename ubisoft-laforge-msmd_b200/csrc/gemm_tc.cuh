@@ -81,7 +81,7 @@ __device__ __forceinline__ float gelu_erf(float x) {
   else return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
 }
 
-template <class Cfg, int MODE>
+template <class Cfg, int MODE, bool GELU>
 __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   using namespace tc;
   using OutT = typename Cfg::OutT;
@@ -261,11 +261,26 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_tc_kernel(const __grid_c
         const int colg = n0 + csplit * CPW + c;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          float x = __uint_as_float(raw[j]);
-          if constexpr (MODE == 1) x += __uint_as_float(raw2[j]);
-          if (p.bias != nullptr) x += (colg + j < p.N) ? __ldg(p.bias + colg + j) : 0.f;
-          if (p.act == 1) x = gelu_erf<MODE>(x);
-          v[j] = x;
+          v[j] = __uint_as_float(raw[j]);
+          if constexpr (MODE == 1) v[j] += __uint_as_float(raw2[j]);
+        }
+        if (p.bias != nullptr) {  // warp-uniform
+          if (colg + 32 <= p.N) {
+            const float4* b4 = reinterpret_cast<const float4*>(p.bias + colg);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 b = __ldg(b4 + j);
+              v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (colg + j < p.N) v[j] += __ldg(p.bias + colg + j);
+          }
+        }
+        if constexpr (GELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = gelu_erf<MODE>(v[j]);
         }
         if constexpr (Cfg::HAS_AUX) {
           if constexpr (sizeof(AuxT) == 4) {
