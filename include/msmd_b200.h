@@ -98,6 +98,69 @@ int msmd_linear(int mode, const void* x, const void* x_lo, const void* w, const 
 int msmd_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream);
 
 /* ------------------------------------------------------------------------- *
+ * Denoiser + sampler — model.py:820-996 (DenoisingNetwork_MSMD), :282-440 (MSMD.sample),
+ * :20-71 (DiffusionSchedule).
+ *
+ * A "sequence" is one row of the reference's concatenated CFG batch (model.py:368-374):
+ * S = E * NX sequences for NX clips and E classifier-free-guidance entries, sequence
+ * s = e * NX + n.  All sequences of a window share the step index.
+ * ------------------------------------------------------------------------- */
+typedef struct {
+  int n_motions;        /* L   = 100 */
+  int n_prev_motions;   /* Lp  = 10  */
+  int d_model;          /* 512 */
+  int n_heads;          /* 8   */
+  int n_layers;         /* 8   */
+  int d_ff;             /* mlp_ratio * d_model = 2048 */
+  int d_style;          /* 256 */
+  int d_shape;          /* 100 */
+  int motion_dim;       /* 67  */
+  int n_basis;          /* 4   */
+  int n_diff_steps;     /* 500 */
+  int use_indicator;    /* 1   */
+  int align_mask_width; /* 1 (the only width with step-invariant cross attention; others unsupported) */
+  int target_noise;     /* 0: network predicts the sample (args.target == 'sample'), 1: the noise */
+  int max_seqs;         /* capacity in sequences (E * clips); workspaces are sized for it at create */
+  int precision;        /* 0: bf16 tensor-core GEMMs (fp32 accumulate, fp32 LayerNorm/softmax statistics) */
+} msmd_config;
+
+typedef struct msmd_model msmd_model;
+
+int msmd_create(const msmd_config* cfg, int device, msmd_model** out);
+void msmd_destroy(msmd_model* m);
+
+/* Weights by state_dict key: "denoising_net.*" and "diffusion_sched.*" entries of
+ * MSMD.state_dict() (model.py:115-137, :855-906).  fp32 data, host or device pointers; copied and
+ * re-packed (bf16 casts, transposes, the 501-row timestep-embedding table) — the caller keeps its tensors. */
+int msmd_load_weights(msmd_model* m, const char* const* names, const void* const* data,
+                      const int64_t* numel, int n);
+
+/* Per-window, step-invariant work: memory K/V projections of every layer, the
+ * cross-attention output of motion rows (== out_proj(v_proj(audio[i-1])) under the width-1 alignment
+ * mask), person_proj, previous-motion projection, static-basis MLPs.
+ * Arguments are exactly the conditioning tensors of DenoisingNetwork_MSMD.forward (model.py:914):
+ *   audio [S,L,d], person [S,d_shape+d_style], style [S,d_style], prev_motion [S,Lp,dm],
+ *   prev_audio [S,Lp,d], indicator [S,L] or NULL.  S = E*NX.  `indicator` must stay valid until the
+ * window's last msmd_denoise / msmd_sample_window call. */
+int msmd_window_begin(msmd_model* m, const float* audio, const float* person, const float* style,
+                      const float* prev_motion, const float* prev_audio, const float* indicator,
+                      int S, int NX, int E, void* stream);
+
+/* One forward of the denoising network (model.py:914-996) for module-level parity.
+ * Needs msmd_window_begin(..., S, NX=S, E=1).  motion [S,L,dm]; steps [S] int64; out [S,Lp+L,dm]. */
+int msmd_denoise(msmd_model* m, const float* motion, const int64_t* steps, float* out, void* stream);
+
+/* Ancestral sampling loop of MSMD.sample (model.py:377-435) for the current window, steps
+ * t = t_start .. t_start-n_steps+1, captured once as a CUDA graph and replayed per step.
+ *   x_T [NX,L,dm] start state (state at t_start);  z [T+1,NX,L,dm] noise indexed by t or NULL
+ *   (-> in-kernel Philox keyed by `seed`); cfg_independent selects 'independent' vs 'incremental';
+ *   scale0/scale1 = guidance scales of entries 1 and 2; x_out [NX,L,dm];
+ *   traj [T+1,NX,L,dm] or NULL receives x_{t-1} at index t-1 for every executed step. */
+int msmd_sample_window(msmd_model* m, const float* x_T, const float* z, uint64_t seed, int cfg_independent,
+                       float scale0, float scale1, float flexibility, int t_start, int n_steps,
+                       float* x_out, float* traj, void* stream);
+
+/* ------------------------------------------------------------------------- *
  * FLAME decode — utils/flame.py:180-244 (FLAME.forward) -> utils/lbs.py:141-223 (lbs)
  *
  * msmd_flame_create packs the static bases once:

@@ -92,7 +92,48 @@ def gen_flame():
     print('flame.npz', v.shape)
 
 
-SECTIONS = dict(rot=gen_rot, flame=gen_flame)
+DEN_GOLD = dict(N=3, seed=21, weight_seed=1234)
+SAMP_GOLD = dict(N=2, T=12, seed=22, weight_seed=1234, scales=[1.4, 1.7])
+
+
+def ref_msmd(weight_seed, **over):
+    """Reference MSMD (model.py:73) with deterministic weights from synth.fill_state_dict."""
+    m = ref_shims.ref_modules()
+    args = ref_shims.pinned_args(**over)
+    model = m.model.get_diffusion_model(args, 'cpu').eval()
+    fill = synth.fill_state_dict(synth.param_spec(model), weight_seed)
+    missing, unexpected = model.load_state_dict(fill, strict=False)
+    assert not unexpected and all(k.startswith(('audio_encoder.', 'diffusion_sched.')) or k.endswith(('TE.pe', 'alignment_mask'))
+                                  for k in missing), (missing[:5], unexpected[:5])
+    return model, args
+
+
+def gen_denoiser():
+    c = DEN_GOLD
+    model, args = ref_msmd(c['weight_seed'])
+    i = synth.denoiser_inputs(c['N'], c['seed'])
+    out = model.denoising_net(i['motion'], i['audio'], i['person'], i['style'], i['prev_motion'], i['prev_audio'],
+                              i['step'], i['indicator'])
+    np.savez_compressed(os.path.join(OUT, 'denoiser.npz'), out=out.numpy())
+    print('denoiser.npz', out.shape)
+
+
+def gen_sampler():
+    c = SAMP_GOLD
+    model, args = ref_msmd(c['weight_seed'], n_diff_steps=c['T'])
+    i = synth.sampler_inputs(c['N'], c['T'], c['seed'])
+    res = {}
+    for mode in ('incremental', 'independent'):
+        with ref_shims.inject_randn_like([i['z'][t] for t in range(c['T'], 1, -1)]):
+            traj, _, _ = model.sample(i['audio_feat'], i['shape'], i['style'], motion_at_T=i['x_T'],
+                                      indicator=i['indicator'], cfg_mode=mode, cfg_scale=list(c['scales']),
+                                      ret_traj=True)
+        res[mode] = torch.stack([traj[t] for t in range(c['T'] + 1)]).numpy()
+    np.savez_compressed(os.path.join(OUT, 'sampler.npz'), **res)
+    print('sampler.npz', res['incremental'].shape)
+
+
+SECTIONS = dict(rot=gen_rot, flame=gen_flame, denoiser=gen_denoiser, sampler=gen_sampler)
 
 
 def main(argv):

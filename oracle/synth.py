@@ -135,3 +135,32 @@ def clip_step_noise(clip_id, window, n_steps, L=100, d=67):
     z[0] = 0
     z[1] = 0
     return z
+
+
+def param_spec(module, skip=('audio_encoder.',)):
+    """{name: shape} of a module's trainable parameters (buffers are rebuilt by the modules)."""
+    return {k: tuple(v.shape) for k, v in module.named_parameters() if not k.startswith(skip)}
+
+
+def denoiser_inputs(N, seed=0, L=100, Lp=10, d=512, dm=67, d_style=256, T=500):
+    """Seeded inputs of one DenoisingNetwork_MSMD.forward call (model.py:914)."""
+    g = torch.Generator().manual_seed(seed)
+    r = lambda *s: torch.randn(*s, generator=g)
+    ind = torch.ones(N, L)
+    if N > 1:
+        ind[1, -30:] = 0
+    step = torch.randint(1, T + 1, (N,), generator=g)
+    return dict(motion=r(N, L, dm), audio=r(N, L, d), person=r(N, 1, 100 + d_style), style=r(N, 1, d_style),
+                prev_motion=r(N, Lp, dm), prev_audio=r(N, Lp, d), step=step, indicator=ind)
+
+
+def sampler_inputs(N, T, seed=0, L=100, d=512, dm=67, d_style=256):
+    g = torch.Generator().manual_seed(seed)
+    r = lambda *s: torch.randn(*s, generator=g)
+    z = r(T + 1, N, L, dm)
+    z[0] = 0
+    z[1] = 0
+    ind = torch.ones(N, L)
+    ind[-1, -17:] = 0
+    return dict(audio_feat=r(N, L, d), shape=torch.zeros(N, 1, 100), style=r(N, d_style), x_T=r(N, L, dm), z=z,
+                indicator=ind)

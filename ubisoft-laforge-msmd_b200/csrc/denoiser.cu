@@ -1,0 +1,416 @@
+// Denoiser + sampler engine behind msmd_create / msmd_load_weights / msmd_window_begin / msmd_denoise /
+// msmd_sample_window (include/msmd_b200.h).  Replaces model.py:820-996 and the loop at model.py:377-435.
+//
+// Data layout in HBM (S sequences, T = 1+Lp+L tokens, M = S*T rows, d = 512):
+//   x     [M, d]     bf16   residual stream = A operand of every GEMM (token-major, features contiguous)
+//   y     [M, d]     fp32   pre-LayerNorm sums written by the out-proj / FF2 GEMM epilogues
+//   qkv   [M, 3d]    bf16   packed q|k|v
+//   ctx   [M, d]     bf16   attention output
+//   h     [M, d_ff]  bf16   GELU(FF1)
+//   kv[l] [S*(T-1), 2d] bf16 and ca[l] [S, T-1, d] bf16: per-window cross-attention caches
+//   dec   [M, 80]    fp32   motion_dec output (67 dynamic + 4 alphas, row stride padded to 80)
+#include "denoiser_kernels.cuh"
+#include "gemm_tc.cuh"
+#include "profile.cuh"
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+using namespace msmd;
+
+namespace {
+
+struct LayerW {
+  bf16 *Wqkv = nullptr, *Wo = nullptr, *Wq0 = nullptr, *Wkv = nullptr, *Wco = nullptr, *W1 = nullptr, *W2 = nullptr;
+  float *bqkv = nullptr, *bo = nullptr, *bq0 = nullptr, *bkv = nullptr, *bco = nullptr, *b1 = nullptr, *b2 = nullptr;
+  float *g1 = nullptr, *be1 = nullptr, *g2 = nullptr, *be2 = nullptr, *g3 = nullptr, *be3 = nullptr;
+  bf16 *kv = nullptr, *ca = nullptr;  // per-window caches
+};
+
+uint16_t f2bf(float f) {  // round-to-nearest-even
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+
+}  // namespace
+
+struct msmd_model {
+  msmd_config c{};
+  int device = 0;
+  bool loaded = false, window = false;
+  int T = 0, dp = 0, ldd = 80;
+  std::vector<LayerW> L;
+  std::vector<void*> owned;  // every device allocation, freed in destroy
+  // fp32 parameters
+  float *PE = nullptr, *temb = nullptr, *Wp = nullptr, *bp = nullptr, *Wf = nullptr, *WfT = nullptr, *bf_ = nullptr;
+  std::vector<float*> Ws0, bs0, Ws2, bs2;
+  bf16 *Wd1 = nullptr, *Wd2 = nullptr;
+  float *bd1 = nullptr, *bd2 = nullptr;
+  float *alphas = nullptr, *alpha_bars = nullptr, *sig_flex = nullptr, *sig_inflex = nullptr;
+  // workspaces
+  bf16 *x = nullptr, *qkv = nullptr, *ctx = nullptr, *h = nullptr, *dec1 = nullptr, *mem = nullptr, *x0c = nullptr,
+       *q0 = nullptr, *ctx0 = nullptr;
+  float *y = nullptr, *y0 = nullptr, *dec2 = nullptr, *pp = nullptr, *pmproj = nullptr, *stat = nullptr,
+        *hid = nullptr, *xbuf = nullptr, *mixed = nullptr;
+  int* steps = nullptr;
+  // window state
+  int S = 0, NX = 0, E = 0;
+  const float* indicator = nullptr;
+};
+
+namespace {
+
+template <class Tp>
+int dalloc(msmd_model* m, Tp** p, size_t n) {
+  void* q = nullptr;
+  MSMD_CHECK_CUDA(cudaMalloc(&q, n * sizeof(Tp)));
+  m->owned.push_back(q);
+  *p = static_cast<Tp*>(q);
+  return MSMD_OK;
+}
+
+int up_f32(msmd_model* m, float** dst, const std::vector<float>& h) {
+  int rc = dalloc(m, dst, h.size());
+  if (rc) return rc;
+  MSMD_CHECK_CUDA(cudaMemcpy(*dst, h.data(), h.size() * 4, cudaMemcpyHostToDevice));
+  return MSMD_OK;
+}
+int up_bf16(msmd_model* m, bf16** dst, const float* h, size_t n) {
+  std::vector<uint16_t> t(n);
+  for (size_t i = 0; i < n; ++i) t[i] = f2bf(h[i]);
+  int rc = dalloc(m, dst, n);
+  if (rc) return rc;
+  MSMD_CHECK_CUDA(cudaMemcpy(*dst, t.data(), n * 2, cudaMemcpyHostToDevice));
+  return MSMD_OK;
+}
+
+int gemm(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const float* bias, const bf16* aux, int64_t ld_aux,
+         void* out, int64_t ldo, int out_f32, int M, int N, int K, int act, cudaStream_t st) {
+  GemmDesc d;
+  d.mode = 0; d.A = A; d.W = W; d.bias = bias; d.aux = aux; d.out = out;
+  d.M = M; d.N = N; d.K = K; d.lda = lda; d.ldw = ldw; d.ldo = ldo; d.ld_aux = ld_aux;
+  d.out_f32 = out_f32; d.aux_f32 = 0; d.act = act; d.gelu_heavy = act;
+  return gemm_tc_launch(d, st);
+}
+
+// One forward of the network on the current window context: x rows [NX,L,dm] -> dec2 [M, ldd]
+int run_forward(msmd_model* m, const float* xrows, cudaStream_t st) {
+  const msmd_config& c = m->c;
+  const int S = m->S, T = m->T, d = c.d_model, M = S * T;
+  int rc;
+  EmbedParams ep;
+  ep.pp = m->pp; ep.temb = m->temb; ep.pmproj = m->pmproj; ep.PE = m->PE; ep.steps = m->steps;
+  ep.x = xrows; ep.indicator = c.use_indicator ? m->indicator : nullptr; ep.WfT = m->WfT; ep.bf = m->bf_;
+  ep.out = m->x; ep.S = S; ep.NX = m->NX; ep.E = m->E; ep.Lp = c.n_prev_motions; ep.L = c.n_motions; ep.d = d;
+  ep.dm = c.motion_dim;
+  if ((rc = embed_launch(ep, st))) return rc;
+  for (int l = 0; l < c.n_layers; ++l) {
+    LayerW& w = m->L[l];
+    // self-attention block (nn.TransformerDecoderLayer._sa_block) + norm1, then the cached cross-attention
+    // rows + norm2 for motion tokens
+    if ((rc = gemm(m->x, d, w.Wqkv, d, w.bqkv, nullptr, 0, m->qkv, 3 * d, 0, M, 3 * d, d, 0, st))) return rc;
+    if ((rc = self_attn_launch(m->qkv, m->ctx, S, T, c.n_heads, st))) return rc;
+    if ((rc = gemm(m->ctx, d, w.Wo, d, w.bo, m->x, d, m->y, d, 1, M, d, d, 0, st))) return rc;
+    LnParams lp;
+    lp.y = m->y; lp.g1 = w.g1; lp.b1 = w.be1; lp.add = w.ca; lp.g2 = w.g2; lp.b2 = w.be2; lp.out = m->x;
+    lp.x0 = m->x0c; lp.M = M; lp.T = T; lp.d = d;
+    if ((rc = ln_launch(lp, st))) return rc;
+    // person token (row 0): real cross attention over the memory (_mha_block) + norm2
+    if ((rc = gemm(m->x0c, d, w.Wq0, d, w.bq0, nullptr, 0, m->q0, d, 0, S, d, d, 0, st))) return rc;
+    if ((rc = cross_attn_row0_launch(m->q0, w.kv, m->ctx0, S, T - 1, c.n_heads, st))) return rc;
+    if ((rc = gemm(m->ctx0, d, w.Wco, d, w.bco, m->x0c, d, m->y0, d, 1, S, d, d, 0, st))) return rc;
+    if ((rc = ln_row0_launch(m->y0, w.g2, w.be2, m->x, S, T, d, st))) return rc;
+    // feed-forward block (_ff_block) + norm3
+    if ((rc = gemm(m->x, d, w.W1, d, w.b1, nullptr, 0, m->h, c.d_ff, 0, M, c.d_ff, d, 1, st))) return rc;
+    if ((rc = gemm(m->h, c.d_ff, w.W2, c.d_ff, w.b2, m->x, d, m->y, d, 1, M, d, c.d_ff, 0, st))) return rc;
+    LnParams l3;
+    l3.y = m->y; l3.g1 = w.g3; l3.b1 = w.be3; l3.add = nullptr; l3.g2 = nullptr; l3.b2 = nullptr; l3.out = m->x;
+    l3.x0 = nullptr; l3.M = M; l3.T = T; l3.d = d;
+    if ((rc = ln_launch(l3, st))) return rc;
+  }
+  // motion_dec (model.py:961): Linear(d, d/2) + GELU + Linear(d/2, dm + n_basis)
+  if ((rc = gemm(m->x, d, m->Wd1, d, m->bd1, nullptr, 0, m->dec1, d / 2, 0, M, d / 2, d, 1, st))) return rc;
+  if ((rc = gemm(m->dec1, d / 2, m->Wd2, d / 2, m->bd2, nullptr, 0, m->dec2, m->ldd, 1, M, c.motion_dim + c.n_basis,
+                 d / 2, 0, st)))
+    return rc;
+  return MSMD_OK;
+}
+
+}  // namespace
+
+extern "C" int msmd_create(const msmd_config* cfg, int device, msmd_model** out) {
+  MSMD_REQUIRE(cfg && out, "msmd_create: null argument");
+  const msmd_config& c = *cfg;
+  MSMD_REQUIRE(c.d_model == 512 && c.n_heads * 64 == c.d_model, "msmd_create: only d_model=512 / 8 heads x 64 is built (got %d / %d)",
+               c.d_model, c.n_heads);
+  MSMD_REQUIRE(1 + c.n_prev_motions + c.n_motions <= 112, "msmd_create: sequence %d exceeds the 112-token attention tile",
+               1 + c.n_prev_motions + c.n_motions);
+  MSMD_REQUIRE(c.n_layers > 0 && c.d_ff % 8 == 0 && c.max_seqs > 0 && c.n_diff_steps > 0, "msmd_create: bad sizes");
+  MSMD_REQUIRE(c.motion_dim + c.n_basis <= 80, "msmd_create: motion_dim + n_basis > 80");
+  if (c.align_mask_width != 1) {
+    set_error("msmd_create: align_mask_width=%d: only width 1 (step-invariant cross attention) is implemented", c.align_mask_width);
+    return MSMD_ERR_UNSUPPORTED;
+  }
+  if (c.precision != 0) {
+    set_error("msmd_create: precision %d not implemented (0 = bf16)", c.precision);
+    return MSMD_ERR_UNSUPPORTED;
+  }
+  MSMD_CHECK_CUDA(cudaSetDevice(device));
+  msmd_model* m = new msmd_model();
+  m->c = c;
+  m->device = device;
+  m->T = 1 + c.n_prev_motions + c.n_motions;
+  m->dp = c.d_shape + c.d_style;
+  m->L.resize(c.n_layers);
+  const size_t S = c.max_seqs, T = m->T, M = S * T, d = c.d_model;
+  int rc = MSMD_OK;
+  auto A = [&](auto** p, size_t n) { if (!rc) rc = dalloc(m, p, n); };
+  A(&m->x, M * d); A(&m->qkv, M * 3 * d); A(&m->ctx, M * d); A(&m->h, M * c.d_ff); A(&m->dec1, M * d / 2);
+  A(&m->mem, S * (T - 1) * d); A(&m->x0c, S * d); A(&m->q0, S * d); A(&m->ctx0, S * d);
+  A(&m->y, M * d); A(&m->y0, S * d); A(&m->dec2, M * m->ldd); A(&m->pp, S * d);
+  A(&m->pmproj, S * c.n_prev_motions * d); A(&m->stat, S * c.n_basis * c.motion_dim); A(&m->hid, S * d);
+  A(&m->xbuf, S * c.n_motions * c.motion_dim); A(&m->mixed, S * (T - 1) * c.motion_dim); A(&m->steps, S);
+  for (auto& w : m->L) { A(&w.kv, S * (T - 1) * 2 * d); A(&w.ca, S * (T - 1) * d); }
+  if (rc) { msmd_destroy(m); return rc; }
+  cudaMemset(m->dec2, 0, M * m->ldd * sizeof(float));
+  *out = m;
+  return MSMD_OK;
+}
+
+extern "C" void msmd_destroy(msmd_model* m) {
+  if (!m) return;
+  for (void* p : m->owned) cudaFree(p);
+  delete m;
+}
+
+extern "C" int msmd_load_weights(msmd_model* m, const char* const* names, const void* const* data,
+                                 const int64_t* numel, int n) {
+  MSMD_REQUIRE(m && names && data && numel, "msmd_load_weights: null argument");
+  const msmd_config& c = m->c;
+  MSMD_CHECK_CUDA(cudaSetDevice(m->device));
+  std::map<std::string, int> idx;
+  for (int i = 0; i < n; ++i) idx[names[i]] = i;
+  std::string missing;
+  int rc = MSMD_OK;
+  auto fetch = [&](const std::string& key, size_t expect, std::vector<float>& h) -> bool {
+    auto it = idx.find(key);
+    if (it == idx.end()) { missing += key + " "; return false; }
+    if ((size_t)numel[it->second] != expect) {
+      set_error("msmd_load_weights: %s has %lld elements, expected %zu", key.c_str(), (long long)numel[it->second], expect);
+      rc = MSMD_ERR_INVALID;
+      return false;
+    }
+    h.resize(expect);
+    if (cudaMemcpy(h.data(), data[it->second], expect * 4, cudaMemcpyDefault) != cudaSuccess) {
+      set_error("msmd_load_weights: copy of %s failed", key.c_str());
+      rc = MSMD_ERR_CUDA;
+      return false;
+    }
+    return true;
+  };
+  const size_t d = c.d_model, ff = c.d_ff, dm = c.motion_dim, fin = dm + (c.use_indicator ? 1 : 0);
+  const std::string P = "denoising_net.";
+  std::vector<float> h, h2;
+  auto F32 = [&](const std::string& key, size_t n_, float** dst) { if (!rc && fetch(key, n_, h)) rc = up_f32(m, dst, h); };
+  auto BF = [&](const std::string& key, size_t n_, bf16** dst) { if (!rc && fetch(key, n_, h)) rc = up_bf16(m, dst, h.data(), n_); };
+
+  for (int l = 0; l < c.n_layers && !rc; ++l) {
+    LayerW& w = m->L[l];
+    const std::string q = P + "transformer.layers." + std::to_string(l) + ".";
+    BF(q + "self_attn.in_proj_weight", 3 * d * d, &w.Wqkv);
+    F32(q + "self_attn.in_proj_bias", 3 * d, &w.bqkv);
+    BF(q + "self_attn.out_proj.weight", d * d, &w.Wo);
+    F32(q + "self_attn.out_proj.bias", d, &w.bo);
+    if (!rc && fetch(q + "multihead_attn.in_proj_weight", 3 * d * d, h)) {  // packed q|k|v (model.py:874 / App. E)
+      rc = up_bf16(m, &w.Wq0, h.data(), d * d);
+      if (!rc) rc = up_bf16(m, &w.Wkv, h.data() + d * d, 2 * d * d);
+    }
+    if (!rc && fetch(q + "multihead_attn.in_proj_bias", 3 * d, h)) {
+      rc = up_f32(m, &w.bq0, std::vector<float>(h.begin(), h.begin() + d));
+      if (!rc) rc = up_f32(m, &w.bkv, std::vector<float>(h.begin() + d, h.end()));
+    }
+    BF(q + "multihead_attn.out_proj.weight", d * d, &w.Wco);
+    F32(q + "multihead_attn.out_proj.bias", d, &w.bco);
+    BF(q + "linear1.weight", ff * d, &w.W1);
+    F32(q + "linear1.bias", ff, &w.b1);
+    BF(q + "linear2.weight", d * ff, &w.W2);
+    F32(q + "linear2.bias", d, &w.b2);
+    F32(q + "norm1.weight", d, &w.g1); F32(q + "norm1.bias", d, &w.be1);
+    F32(q + "norm2.weight", d, &w.g2); F32(q + "norm2.bias", d, &w.be2);
+    F32(q + "norm3.weight", d, &w.g3); F32(q + "norm3.bias", d, &w.be3);
+  }
+  F32(P + "PE", (size_t)m->T * d, &m->PE);
+  F32(P + "person_proj.weight", d * m->dp, &m->Wp);
+  F32(P + "person_proj.bias", d, &m->bp);
+  if (!rc && fetch(P + "feature_proj.weight", d * fin, h)) {
+    rc = up_f32(m, &m->Wf, h);
+    std::vector<float> t((dm + 1) * d, 0.f);  // k-major copy; row dm = indicator column (zero if unused)
+    for (size_t cc = 0; cc < d; ++cc)
+      for (size_t k = 0; k < fin; ++k) t[k * d + cc] = h[cc * fin + k];
+    if (!rc) rc = up_f32(m, &m->WfT, t);
+  }
+  F32(P + "feature_proj.bias", d, &m->bf_);
+  m->Ws0.assign(c.n_basis, nullptr); m->bs0 = m->Ws2 = m->bs2 = m->Ws0;
+  for (int b = 0; b < c.n_basis && !rc; ++b) {
+    const std::string q = P + "static_feature_mapping." + std::to_string(b) + ".";
+    F32(q + "0.weight", d * c.d_style, &m->Ws0[b]); F32(q + "0.bias", d, &m->bs0[b]);
+    F32(q + "2.weight", dm * d, &m->Ws2[b]); F32(q + "2.bias", dm, &m->bs2[b]);
+  }
+  BF(P + "motion_dec.0.weight", (d / 2) * d, &m->Wd1);
+  F32(P + "motion_dec.0.bias", d / 2, &m->bd1);
+  BF(P + "motion_dec.2.weight", (dm + c.n_basis) * (d / 2), &m->Wd2);
+  if (!rc && fetch(P + "motion_dec.2.bias", dm + c.n_basis, h)) {
+    h.resize(m->ldd, 0.f);
+    rc = up_f32(m, &m->bd2, h);
+  }
+  // timestep-embedding table: diff_step_map(TE.pe[0, t]) for t = 0..T (model.py:931) — weights only
+  const size_t nt = c.n_diff_steps + 1;
+  float *te = nullptr, *w0 = nullptr, *b0 = nullptr, *w2 = nullptr, *b2 = nullptr, *hid = nullptr;
+  F32(P + "TE.pe", nt * d, &te);
+  F32(P + "diff_step_map.0.weight", d * d, &w0); F32(P + "diff_step_map.0.bias", d, &b0);
+  F32(P + "diff_step_map.2.weight", d * d, &w2); F32(P + "diff_step_map.2.bias", d, &b2);
+  // schedule (model.py:20-71): copied, not recomputed
+  F32("diffusion_sched.alphas", nt, &m->alphas);
+  F32("diffusion_sched.alpha_bars", nt, &m->alpha_bars);
+  F32("diffusion_sched.sigmas_flex", nt, &m->sig_flex);
+  F32("diffusion_sched.sigmas_inflex", nt, &m->sig_inflex);
+  if (rc) return rc;
+  if (!missing.empty()) {
+    set_error("msmd_load_weights: missing state_dict keys: %s", missing.c_str());
+    return MSMD_ERR_INVALID;
+  }
+  if ((rc = dalloc(m, &hid, nt * d)) || (rc = dalloc(m, &m->temb, nt * d))) return rc;
+  if ((rc = linear_simt(te, d, w0, d, b0, hid, d, (int)nt, (int)d, (int)d, 1, 0))) return rc;
+  if ((rc = linear_simt(hid, d, w2, d, b2, m->temb, d, (int)nt, (int)d, (int)d, 0, 0))) return rc;
+  MSMD_CHECK_CUDA(cudaDeviceSynchronize());
+  m->loaded = true;
+  return MSMD_OK;
+}
+
+extern "C" int msmd_window_begin(msmd_model* m, const float* audio, const float* person, const float* style,
+                                 const float* prev_motion, const float* prev_audio, const float* indicator, int S,
+                                 int NX, int E, void* stream) {
+  MSMD_REQUIRE(m, "msmd_window_begin: null model");
+  if (!m->loaded) { set_error("msmd_window_begin: weights not loaded"); return MSMD_ERR_STATE; }
+  const msmd_config& c = m->c;
+  MSMD_REQUIRE(S > 0 && NX > 0 && E > 0 && S == NX * E, "msmd_window_begin: S=%d must equal NX*E=%d*%d", S, NX, E);
+  MSMD_REQUIRE(S <= c.max_seqs, "msmd_window_begin: %d sequences exceed the capacity %d given at create", S, c.max_seqs);
+  MSMD_REQUIRE(E <= 3, "msmd_window_begin: at most 2 guidance conditions (3 entries)");
+  MSMD_REQUIRE(audio && person && style && prev_motion && prev_audio, "msmd_window_begin: null conditioning tensor");
+  MSMD_REQUIRE(!c.use_indicator || indicator, "Missing indicator: the model was built with use_indicator");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int d = c.d_model, Tk = m->T - 1, Lp = c.n_prev_motions, dm = c.motion_dim;
+  int rc;
+  if ((rc = build_memory_bf16(prev_audio, audio, m->mem, S, Lp, c.n_motions, d, st))) return rc;
+  for (auto& w : m->L) {
+    // memory K|V projection, then the motion rows' cross-attention output out_proj(v_proj(mem)) (softmax over
+    // a single visible key is 1, so the query drops out: SURVEY section 0)
+    if ((rc = gemm(m->mem, d, w.Wkv, d, w.bkv, nullptr, 0, w.kv, 2 * d, 0, S * Tk, 2 * d, d, 0, st))) return rc;
+    if ((rc = gemm(w.kv + d, 2 * d, w.Wco, d, w.bco, nullptr, 0, w.ca, d, 0, S * Tk, d, d, 0, st))) return rc;
+  }
+  if ((rc = linear_simt(person, m->dp, m->Wp, m->dp, m->bp, m->pp, d, S, d, m->dp, 0, st))) return rc;
+  const int fin = dm + (c.use_indicator ? 1 : 0);
+  if ((rc = linear_simt(prev_motion, dm, m->Wf, fin, m->bf_, m->pmproj, d, S * Lp, d, dm, 0, st))) return rc;
+  for (int b = 0; b < c.n_basis; ++b) {
+    if ((rc = linear_simt(style, c.d_style, m->Ws0[b], c.d_style, m->bs0[b], m->hid, d, S, d, c.d_style, 1, st))) return rc;
+    if ((rc = linear_simt(m->hid, d, m->Ws2[b], d, m->bs2[b], m->stat + b * dm, (int64_t)c.n_basis * dm, S, dm, d, 0, st)))
+      return rc;
+  }
+  m->S = S; m->NX = NX; m->E = E;
+  m->indicator = indicator;
+  m->window = true;
+  return MSMD_OK;
+}
+
+__global__ void steps_from_i64_kernel(const int64_t* in, int* out, int S) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < S) out[i] = (int)in[i];
+}
+
+extern "C" int msmd_denoise(msmd_model* m, const float* motion, const int64_t* steps, float* out, void* stream) {
+  MSMD_REQUIRE(m && motion && steps && out, "msmd_denoise: null argument");
+  if (!m->window) { set_error("msmd_denoise: call msmd_window_begin first"); return MSMD_ERR_STATE; }
+  MSMD_REQUIRE(m->E == 1 && m->NX == m->S, "msmd_denoise: window must be opened with NX == S, E == 1");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  steps_from_i64_kernel<<<cdiv(m->S, 256), 256, 0, st>>>(steps, m->steps, m->S);
+  MSMD_CHECK_LAUNCH();
+  int rc = run_forward(m, motion, st);
+  if (rc) return rc;
+  return mix_static_launch(m->dec2, m->stat, out, m->S, m->T, m->c.motion_dim, m->c.n_basis, m->ldd, st);
+}
+
+extern "C" int msmd_sample_window(msmd_model* m, const float* x_T, const float* z, uint64_t seed, int cfg_independent,
+                                  float scale0, float scale1, float flexibility, int t_start, int n_steps,
+                                  float* x_out, float* traj, void* stream) {
+  MSMD_REQUIRE(m && x_T && x_out, "msmd_sample_window: null argument");
+  if (!m->window) { set_error("msmd_sample_window: call msmd_window_begin first"); return MSMD_ERR_STATE; }
+  const msmd_config& c = m->c;
+  MSMD_REQUIRE(t_start >= 1 && t_start <= c.n_diff_steps && n_steps >= 1 && n_steps <= t_start,
+               "msmd_sample_window: steps %d..%d outside 1..%d", t_start, t_start - n_steps + 1, c.n_diff_steps);
+  MSMD_REQUIRE(flexibility >= 0.f && flexibility <= 1.f, "msmd_sample_window: flexibility outside [0,1]");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t n_el = (size_t)m->NX * c.n_motions * c.motion_dim;
+  MSMD_CHECK_CUDA(cudaMemcpyAsync(m->xbuf, x_T, n_el * 4, cudaMemcpyDeviceToDevice, st));
+  int rc;
+  if ((rc = steps_set(m->steps, m->S, t_start, st))) return rc;
+
+  UpdateParams up;
+  up.dec = m->dec2; up.stat = m->stat; up.x = m->xbuf; up.z = z; up.traj = traj; up.steps = m->steps;
+  up.alphas = m->alphas; up.alpha_bars = m->alpha_bars; up.sig_flex = m->sig_flex; up.sig_inflex = m->sig_inflex;
+  up.scale0 = scale0; up.scale1 = scale1; up.flexibility = flexibility; up.seed = seed;
+  up.NX = m->NX; up.E = m->E; up.T = m->T; up.L = c.n_motions; up.Lp = c.n_prev_motions; up.dm = c.motion_dim;
+  up.nb = c.n_basis; up.ldd = m->ldd; up.cfg_independent = cfg_independent; up.target_noise = c.target_noise;
+
+  auto one_step = [&](cudaStream_t s) -> int {
+    int r;
+    if ((r = run_forward(m, m->xbuf, s))) return r;
+    if ((r = update_launch(up, s))) return r;
+    return steps_advance(m->steps, m->S, s);
+  };
+
+  if (profiling_on() || n_steps < 3) {  // event timing cannot live inside a graph: plain launches
+    for (int i = 0; i < n_steps; ++i)
+      if ((rc = one_step(st))) return rc;
+  } else {
+    // first step eagerly (one-time function attributes, launch validation), the rest as graph replays
+    if ((rc = one_step(st))) return rc;
+    n_steps -= 1;
+    // capture ONE step (the step index lives in device memory) and replay it
+    cudaStream_t cs;
+    MSMD_CHECK_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    MSMD_CHECK_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+    rc = one_step(cs);
+    cudaError_t ce = cudaStreamEndCapture(cs, &graph);
+    if (rc || ce != cudaSuccess) {
+      if (graph) cudaGraphDestroy(graph);
+      cudaStreamDestroy(cs);
+      if (!rc) { set_error("msmd_sample_window: graph capture failed: %s", cudaGetErrorString(ce)); rc = MSMD_ERR_CUDA; }
+      return rc;
+    }
+    ce = cudaGraphInstantiate(&exec, graph, 0);
+    if (ce != cudaSuccess) {
+      cudaGraphDestroy(graph);
+      cudaStreamDestroy(cs);
+      set_error("msmd_sample_window: cudaGraphInstantiate failed: %s", cudaGetErrorString(ce));
+      return MSMD_ERR_CUDA;
+    }
+    for (int i = 0; i < n_steps && ce == cudaSuccess; ++i) ce = cudaGraphLaunch(exec, st);
+    // the exec must outlive its launches: destroy after the stream has drained them
+    cudaError_t se = cudaStreamSynchronize(st);
+    cudaGraphExecDestroy(exec);
+    cudaGraphDestroy(graph);
+    cudaStreamDestroy(cs);
+    if (ce != cudaSuccess || se != cudaSuccess) {
+      set_error("msmd_sample_window: graph launch failed: %s", cudaGetErrorString(ce != cudaSuccess ? ce : se));
+      return MSMD_ERR_CUDA;
+    }
+  }
+  MSMD_CHECK_CUDA(cudaMemcpyAsync(x_out, m->xbuf, n_el * 4, cudaMemcpyDeviceToDevice, st));
+  return MSMD_OK;
+}

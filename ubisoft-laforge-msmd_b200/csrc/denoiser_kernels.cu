@@ -1,0 +1,539 @@
+// Non-GEMM kernels of the denoiser / sampler: embeddings (model.py:931-949), LayerNorm chains of the
+// post-LN decoder layers, self-attention over the 111-token sequence, the person-token (row 0) cross
+// attention, and the fused CFG-combine + static-basis mix + DDPM posterior step (model.py:404-430,
+// :964-995).  All HBM-bound elementwise / small-tile work: coalesced float4 / bf16x4 accesses,
+// warp-shuffle reductions, fp32 statistics.
+#include "denoiser_kernels.cuh"
+#include "profile.cuh"
+
+namespace msmd {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+// ------------------------------------------------------------------------------------------- small fp32 linear
+__global__ void __launch_bounds__(256) linear_simt_kernel(const float* __restrict__ x, int64_t ldx,
+                                                          const float* __restrict__ W, int64_t ldw,
+                                                          const float* __restrict__ b, float* __restrict__ out,
+                                                          int64_t ldo, int R, int C, int K, int act) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (w >= (int64_t)R * C) return;
+  const int r = (int)(w / C), c = (int)(w % C);
+  const float* xr = x + r * ldx;
+  const float* wr = W + (int64_t)c * ldw;
+  float s = 0.f;
+  for (int k = lane; k < K; k += 32) s = fmaf(xr[k], wr[k], s);
+  s = warp_sum(s);
+  if (lane == 0) {
+    s += b ? b[c] : 0.f;
+    if (act == 1) s = gelu_exact(s);
+    out[r * ldo + c] = s;
+  }
+}
+int linear_simt(const float* x, int64_t ldx, const float* W, int64_t ldw, const float* b, float* out, int64_t ldo, int R,
+                int C, int K, int act, cudaStream_t st) {
+  if (R <= 0 || C <= 0) return MSMD_OK;
+  const int64_t warps = (int64_t)R * C;
+  linear_simt_kernel<<<cdiv(warps * 32, 256), 256, 0, st>>>(x, ldx, W, ldw, b, out, ldo, R, C, K, act);
+  MSMD_CHECK_LAUNCH();
+  return MSMD_OK;
+}
+
+__global__ void cast_rows_bf16_kernel(const float* __restrict__ src, int64_t lds, bf16* __restrict__ dst, int64_t ldd,
+                                      int64_t rows, int cols) {
+  const int64_t n = rows * cols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cols;
+    const int c = (int)(i % cols);
+    dst[r * ldd + c] = __float2bfloat16_rn(src[r * lds + c]);
+  }
+}
+int cast_rows_bf16(const float* src, int64_t lds, bf16* dst, int64_t ldd, int64_t rows, int cols, cudaStream_t st) {
+  if (rows * cols == 0) return MSMD_OK;
+  cast_rows_bf16_kernel<<<(int)std::min<int64_t>(cdiv(rows * cols, 256), kNumSMs * 16), 256, 0, st>>>(src, lds, dst, ldd,
+                                                                                                   rows, cols);
+  MSMD_CHECK_LAUNCH();
+  return MSMD_OK;
+}
+
+__global__ void build_memory_kernel(const float* __restrict__ prev_audio, const float* __restrict__ audio,
+                                    bf16* __restrict__ mem, int S, int Lp, int L, int d) {
+  const int64_t n = (int64_t)S * (Lp + L) * d;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % d);
+    const int64_t row = i / d;
+    const int tok = (int)(row % (Lp + L));
+    const int64_t s = row / (Lp + L);
+    const float v = tok < Lp ? prev_audio[(s * Lp + tok) * d + c] : audio[(s * L + tok - Lp) * d + c];
+    mem[i] = __float2bfloat16_rn(v);
+  }
+}
+int build_memory_bf16(const float* prev_audio, const float* audio, bf16* mem, int S, int Lp, int L, int d,
+                      cudaStream_t st) {
+  const int64_t n = (int64_t)S * (Lp + L) * d;
+  build_memory_kernel<<<(int)std::min<int64_t>(cdiv(n, 256), kNumSMs * 16), 256, 0, st>>>(prev_audio, audio, mem, S, Lp, L, d);
+  MSMD_CHECK_LAUNCH();
+  return MSMD_OK;
+}
+
+// ------------------------------------------------------------------------------------------- embeddings
+// rows 0..Lp: person token (+ timestep embedding) and the projected previous-motion context
+__global__ void embed_ctx_kernel(EmbedParams p) {
+  const int T = 1 + p.Lp + p.L;
+  const int row = blockIdx.x;  // s * (Lp+1) + i
+  const int s = row / (p.Lp + 1), i = row % (p.Lp + 1);
+  const int t = p.steps[s];
+  for (int c = threadIdx.x; c < p.d; c += blockDim.x) {
+    float v = p.PE[i * p.d + c];
+    v += (i == 0) ? (p.pp[(int64_t)s * p.d + c] + p.temb[(int64_t)t * p.d + c])
+                  : p.pmproj[((int64_t)s * p.Lp + (i - 1)) * p.d + c];
+    p.out[((int64_t)s * T + i) * p.d + c] = __float2bfloat16_rn(v);
+  }
+}
+// rows Lp+1..: feature_proj([x_t, indicator]) + PE, computed once per x row and written to its E sequences
+constexpr int kEmbedRows = 20;
+__global__ void __launch_bounds__(512) embed_x_kernel(EmbedParams p) {
+  extern __shared__ float xs[];  // [kEmbedRows][dm]
+  const int T = 1 + p.Lp + p.L;
+  const int blocks_per_x = (p.L + kEmbedRows - 1) / kEmbedRows;
+  const int n = blockIdx.x / blocks_per_x;
+  const int l0 = (blockIdx.x % blocks_per_x) * kEmbedRows;
+  const int nr = min(kEmbedRows, p.L - l0);
+  for (int i = threadIdx.x; i < nr * p.dm; i += blockDim.x) xs[i] = p.x[((int64_t)n * p.L + l0) * p.dm + i];
+  __syncthreads();
+  for (int c = threadIdx.x; c < p.d; c += blockDim.x) {
+    float acc[kEmbedRows];
+#pragma unroll
+    for (int r = 0; r < kEmbedRows; ++r) acc[r] = 0.f;
+    for (int k = 0; k < p.dm; ++k) {
+      const float w = p.WfT[(int64_t)k * p.d + c];
+#pragma unroll
+      for (int r = 0; r < kEmbedRows; ++r)
+        if (r < nr) acc[r] = fmaf(xs[r * p.dm + k], w, acc[r]);
+    }
+    const float wi = p.indicator ? p.WfT[(int64_t)p.dm * p.d + c] : 0.f;
+    const float bc = p.bf[c];
+    for (int e = 0; e < p.E; ++e) {
+      const int s = e * p.NX + n;
+#pragma unroll
+      for (int r = 0; r < kEmbedRows; ++r) {
+        if (r < nr) {
+          const int l = l0 + r;
+          const float ind = p.indicator ? p.indicator[(int64_t)s * p.L + l] : 0.f;
+          const float v = acc[r] + bc + ind * wi + p.PE[(1 + p.Lp + l) * p.d + c];
+          p.out[((int64_t)s * T + 1 + p.Lp + l) * p.d + c] = __float2bfloat16_rn(v);
+        }
+      }
+    }
+  }
+}
+int embed_launch(const EmbedParams& p, cudaStream_t st) {
+  embed_ctx_kernel<<<p.S * (p.Lp + 1), 128, 0, st>>>(p);
+  MSMD_CHECK_LAUNCH();
+  const int blocks = p.NX * ((p.L + kEmbedRows - 1) / kEmbedRows);
+  embed_x_kernel<<<blocks, 512, kEmbedRows * p.dm * sizeof(float), st>>>(p);
+  MSMD_CHECK_LAUNCH();
+  return MSMD_OK;
+}
+
+// ------------------------------------------------------------------------------------------- LayerNorm chain
+// one warp per 512-wide row; two-pass statistics in registers
+template <int D>
+__device__ __forceinline__ void ln_row(float (&v)[D / 32], const float* __restrict__ g, const float* __restrict__ b,
+                                       int lane) {
+  constexpr int NV = D / 32;
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) s += v[i];
+  const float mean = warp_sum(s) * (1.0f / D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) { const float dlt = v[i] - mean; q = fmaf(dlt, dlt, q); }
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + 1e-5f);
+#pragma unroll
+  for (int i = 0; i < NV / 4; ++i) {
+    const float4 gg = *reinterpret_cast<const float4*>(g + i * 128 + lane * 4);
+    const float4 bb = *reinterpret_cast<const float4*>(b + i * 128 + lane * 4);
+    v[4 * i + 0] = (v[4 * i + 0] - mean) * rstd * gg.x + bb.x;
+    v[4 * i + 1] = (v[4 * i + 1] - mean) * rstd * gg.y + bb.y;
+    v[4 * i + 2] = (v[4 * i + 2] - mean) * rstd * gg.z + bb.z;
+    v[4 * i + 3] = (v[4 * i + 3] - mean) * rstd * gg.w + bb.w;
+  }
+}
+__device__ __forceinline__ void store_bf16x4(bf16* dst, float a, float b, float c, float d) {
+  __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&lo);
+  u.y = *reinterpret_cast<uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(dst) = u;
+}
+
+template <int D>
+__global__ void __launch_bounds__(256) ln_kernel(LnParams p) {
+  constexpr int NV = D / 32;
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= p.M) return;
+  const int s = row / p.T, tok = row % p.T;
+  float v[NV];
+  const float* y = p.y + (int64_t)row * D;
+#pragma unroll
+  for (int i = 0; i < NV / 4; ++i) {
+    const float4 t4 = *reinterpret_cast<const float4*>(y + i * 128 + lane * 4);
+    v[4 * i] = t4.x; v[4 * i + 1] = t4.y; v[4 * i + 2] = t4.z; v[4 * i + 3] = t4.w;
+  }
+  ln_row<D>(v, p.g1, p.b1, lane);
+  if (tok == 0 && p.x0 != nullptr) {
+#pragma unroll
+    for (int i = 0; i < NV / 4; ++i)
+      store_bf16x4(p.x0 + (int64_t)s * D + i * 128 + lane * 4, v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    return;
+  }
+  if (p.add != nullptr && tok > 0) {
+    // x1 is rounded to bf16 where the reference's next sub-layer reads it; keep the same rounding point
+    const bf16* a = p.add + ((int64_t)s * (p.T - 1) + (tok - 1)) * D;
+#pragma unroll
+    for (int i = 0; i < NV / 4; ++i) {
+      const uint2 u = *reinterpret_cast<const uint2*>(a + i * 128 + lane * 4);
+      v[4 * i + 0] += __uint_as_float(u.x << 16);
+      v[4 * i + 1] += __uint_as_float(u.x & 0xffff0000u);
+      v[4 * i + 2] += __uint_as_float(u.y << 16);
+      v[4 * i + 3] += __uint_as_float(u.y & 0xffff0000u);
+    }
+    ln_row<D>(v, p.g2, p.b2, lane);
+  }
+  bf16* o = p.out + (int64_t)row * D;
+#pragma unroll
+  for (int i = 0; i < NV / 4; ++i) store_bf16x4(o + i * 128 + lane * 4, v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+}
+int ln_launch(const LnParams& p, cudaStream_t st) {
+  MSMD_REQUIRE(p.d == 512, "ln: only d_model = 512 is instantiated (got %d)", p.d);
+  ln_kernel<512><<<cdiv(p.M, 8), 256, 0, st>>>(p);
+  MSMD_CHECK_LAUNCH();
+  return MSMD_OK;
+}
+
+template <int D>
+__global__ void __launch_bounds__(256) ln_row0_kernel(const float* __restrict__ y0, const float* __restrict__ g,
+                                                      const float* __restrict__ b, bf16* __restrict__ out, int S, int T) {
+  constexpr int NV = D / 32;
+  const int lane = threadIdx.x & 31;
+  const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (s >= S) return;
+  float v[NV];
+#pragma unroll
+  for (int i = 0; i < NV / 4; ++i) {
+    const float4 t4 = *reinterpret_cast<const float4*>(y0 + (int64_t)s * D + i * 128 + lane * 4);
+    v[4 * i] = t4.x; v[4 * i + 1] = t4.y; v[4 * i + 2] = t4.z; v[4 * i + 3] = t4.w;
+  }
+  ln_row<D>(v, g, b, lane);
+  bf16* o = out + (int64_t)s * T * D;
+#pragma unroll
+  for (int i = 0; i < NV / 4; ++i) store_bf16x4(o + i * 128 + lane * 4, v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+}
+int ln_row0_launch(const float* y0, const float* g, const float* b, bf16* out, int S, int T, int d, cudaStream_t st) {
+  MSMD_REQUIRE(d == 512, "ln_row0: only d_model = 512 is instantiated");
+  ln_row0_kernel<512><<<cdiv(S, 8), 256, 0, st>>>(y0, g, b, out, S, T);
+  MSMD_CHECK_LAUNCH();
+  return MSMD_OK;
+}
+
+// ------------------------------------------------------------------------------------------- self attention
+// One CTA per (sequence, head): T <= 112 tokens, head dim 64.  S = Q K^T and O = P V on mma.sync
+// m16n8k16 bf16 (the whole problem is one 112x112x64 tile, 3% of the layer's FLOPs); softmax in fp32.
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+constexpr int kAttT = 112, kAttDh = 64, kQKStride = 72, kVtStride = 120;
+
+__global__ void __launch_bounds__(224) self_attn_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ ctx, int T,
+                                                        int H) {
+  __shared__ __align__(16) bf16 sQ[kAttT * kQKStride];
+  __shared__ __align__(16) bf16 sK[kAttT * kQKStride];
+  __shared__ __align__(16) bf16 sVt[kAttDh * kVtStride];
+  const int h = blockIdx.x, s = blockIdx.y;
+  const int d = H * kAttDh;
+  const int tid = threadIdx.x;
+  const bf16* base = qkv + (int64_t)s * T * 3 * d + h * kAttDh;
+  for (int idx = tid; idx < kAttT * 8; idx += blockDim.x) {
+    const int row = idx >> 3, ch = idx & 7;
+    uint4 q = make_uint4(0, 0, 0, 0), k = q, v = q;
+    if (row < T) {
+      const bf16* r = base + (int64_t)row * 3 * d + ch * 8;
+      q = *reinterpret_cast<const uint4*>(r);
+      k = *reinterpret_cast<const uint4*>(r + d);
+      v = *reinterpret_cast<const uint4*>(r + 2 * d);
+    }
+    *reinterpret_cast<uint4*>(&sQ[row * kQKStride + ch * 8]) = q;
+    *reinterpret_cast<uint4*>(&sK[row * kQKStride + ch * 8]) = k;
+    const bf16* vv = reinterpret_cast<const bf16*>(&v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sVt[(ch * 8 + j) * kVtStride + row] = vv[j];
+  }
+  __syncthreads();
+
+  const int warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int r0 = warp * 16;
+  uint32_t aq[4][4];
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    aq[ks][0] = *reinterpret_cast<const uint32_t*>(&sQ[(r0 + g) * kQKStride + ks * 16 + 2 * t]);
+    aq[ks][1] = *reinterpret_cast<const uint32_t*>(&sQ[(r0 + g + 8) * kQKStride + ks * 16 + 2 * t]);
+    aq[ks][2] = *reinterpret_cast<const uint32_t*>(&sQ[(r0 + g) * kQKStride + ks * 16 + 8 + 2 * t]);
+    aq[ks][3] = *reinterpret_cast<const uint32_t*>(&sQ[(r0 + g + 8) * kQKStride + ks * 16 + 8 + 2 * t]);
+  }
+  float sc[14][4];
+#pragma unroll
+  for (int j = 0; j < 14; ++j) {
+    sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&sK[(j * 8 + g) * kQKStride + ks * 16 + 2 * t]);
+      const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&sK[(j * 8 + g) * kQKStride + ks * 16 + 8 + 2 * t]);
+      mma_bf16_16816(sc[j], aq[ks], b0, b1);
+    }
+  }
+  // softmax over keys (columns): thread holds cols j*8+2t, +1 of rows g (regs 0,1) and g+8 (regs 2,3)
+  const float kScale = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
+  float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < 14; ++j) {
+    const int c = j * 8 + 2 * t;
+    if (c >= T) { sc[j][0] = -INFINITY; sc[j][2] = -INFINITY; }
+    if (c + 1 >= T) { sc[j][1] = -INFINITY; sc[j][3] = -INFINITY; }
+    m0 = fmaxf(m0, fmaxf(sc[j][0], sc[j][1]));
+    m1 = fmaxf(m1, fmaxf(sc[j][2], sc[j][3]));
+  }
+  m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+  m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+  float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+  for (int j = 0; j < 14; ++j) {
+    sc[j][0] = exp2f((sc[j][0] - m0) * kScale); sc[j][1] = exp2f((sc[j][1] - m0) * kScale);
+    sc[j][2] = exp2f((sc[j][2] - m1) * kScale); sc[j][3] = exp2f((sc[j][3] - m1) * kScale);
+    l0 += sc[j][0] + sc[j][1];
+    l1 += sc[j][2] + sc[j][3];
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+
+  float o[8][4];
+#pragma unroll
+  for (int n = 0; n < 8; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+#pragma unroll
+  for (int kb = 0; kb < 7; ++kb) {
+    uint32_t ap[4];
+    ap[0] = pack_bf16(sc[2 * kb][0], sc[2 * kb][1]);
+    ap[1] = pack_bf16(sc[2 * kb][2], sc[2 * kb][3]);
+    ap[2] = pack_bf16(sc[2 * kb + 1][0], sc[2 * kb + 1][1]);
+    ap[3] = pack_bf16(sc[2 * kb + 1][2], sc[2 * kb + 1][3]);
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&sVt[(n * 8 + g) * kVtStride + kb * 16 + 2 * t]);
+      const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&sVt[(n * 8 + g) * kVtStride + kb * 16 + 8 + 2 * t]);
+      mma_bf16_16816(o[n], ap, b0, b1);
+    }
+  }
+  const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+  const int row_a = r0 + g, row_b = r0 + g + 8;
+#pragma unroll
+  for (int n = 0; n < 8; ++n) {
+    const int col = h * kAttDh + n * 8 + 2 * t;
+    if (row_a < T)
+      *reinterpret_cast<uint32_t*>(ctx + ((int64_t)s * T + row_a) * d + col) = pack_bf16(o[n][0] * i0, o[n][1] * i0);
+    if (row_b < T)
+      *reinterpret_cast<uint32_t*>(ctx + ((int64_t)s * T + row_b) * d + col) = pack_bf16(o[n][2] * i1, o[n][3] * i1);
+  }
+}
+int self_attn_launch(const bf16* qkv, bf16* ctx, int S, int T, int H, cudaStream_t st) {
+  MSMD_REQUIRE(T <= kAttT, "self_attn: sequence length %d exceeds the %d-token tile", T, kAttT);
+  ProfileScope prof("self_attn", st);
+  self_attn_kernel<<<dim3(H, S), 224, 0, st>>>(qkv, ctx, T, H);
+  MSMD_CHECK_LAUNCH();
+  return MSMD_OK;
+}
+
+// ------------------------------------------------------------------------------------------- row-0 cross attention
+// The alignment mask (model.py:879-883) lets only the person token attend to all memory; one warp per (s, head).
+__global__ void __launch_bounds__(256) cross_attn_row0_kernel(const bf16* __restrict__ q0, const bf16* __restrict__ kv,
+                                                              bf16* __restrict__ ctx0, int S, int Tk, int H) {
+  const int lane = threadIdx.x & 31;
+  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= S * H) return;
+  const int s = w / H, h = w % H;
+  const int d = H * 64;
+  // q: lane holds dims 2*lane, 2*lane+1
+  const uint32_t qu = *reinterpret_cast<const uint32_t*>(q0 + (int64_t)s * d + h * 64 + 2 * lane);
+  const float qa = __uint_as_float(qu << 16), qb = __uint_as_float(qu & 0xffff0000u);
+  float sc[4];  // scores of keys lane, lane+32, lane+64, lane+96
+#pragma unroll
+  for (int grp = 0; grp < 4; ++grp) {
+    float mine = -INFINITY;
+    for (int j0 = 0; j0 < 32; ++j0) {
+      const int j = grp * 32 + j0;
+      if (j >= Tk) break;
+      const uint32_t ku = *reinterpret_cast<const uint32_t*>(kv + ((int64_t)s * Tk + j) * 2 * d + h * 64 + 2 * lane);
+      float p = qa * __uint_as_float(ku << 16) + qb * __uint_as_float(ku & 0xffff0000u);
+      p = warp_sum(p);
+      if (j0 == lane) mine = p * 0.125f;
+    }
+    sc[grp] = mine;
+  }
+  const float m = warp_max(fmaxf(fmaxf(sc[0], sc[1]), fmaxf(sc[2], sc[3])));
+  float l = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { sc[i] = (sc[i] == -INFINITY) ? 0.f : __expf(sc[i] - m); l += sc[i]; }
+  l = warp_sum(l);
+  float oa = 0.f, ob = 0.f;
+#pragma unroll
+  for (int grp = 0; grp < 4; ++grp) {
+    for (int j0 = 0; j0 < 32; ++j0) {
+      const int j = grp * 32 + j0;
+      if (j >= Tk) break;
+      const float p = __shfl_sync(0xffffffffu, sc[grp], j0);
+      const uint32_t vu = *reinterpret_cast<const uint32_t*>(kv + ((int64_t)s * Tk + j) * 2 * d + d + h * 64 + 2 * lane);
+      oa = fmaf(p, __uint_as_float(vu << 16), oa);
+      ob = fmaf(p, __uint_as_float(vu & 0xffff0000u), ob);
+    }
+  }
+  const float inv = 1.0f / l;
+  *reinterpret_cast<uint32_t*>(ctx0 + (int64_t)s * d + h * 64 + 2 * lane) = pack_bf16(oa * inv, ob * inv);
+}
+int cross_attn_row0_launch(const bf16* q0, const bf16* kv, bf16* ctx0, int S, int Tk, int H, cudaStream_t st) {
+  MSMD_REQUIRE(Tk <= 128, "cross_attn_row0: memory length %d > 128", Tk);
+  cross_attn_row0_kernel<<<cdiv(S * H, 8), 256, 0, st>>>(q0, kv, ctx0, S, Tk, H);
+  MSMD_CHECK_LAUNCH();
+  return MSMD_OK;
+}
+
+// ------------------------------------------------------------------------------------------- sampler update
+// Philox4x32-10 + Box-Muller for the in-kernel noise path (z == null); keyed by (seed, t, element)
+__device__ __forceinline__ float philox_normal(unsigned long long seed, uint32_t t, uint32_t idx) {
+  uint32_t c0 = idx, c1 = t, c2 = 0x9E3779B9u, c3 = 0xBB67AE85u;
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  const float u1 = ((c0 >> 8) + 1) * (1.0f / 16777216.0f);
+  const float u2 = (c1 >> 8) * (1.0f / 16777216.0f);
+  return sqrtf(-2.0f * __logf(u1)) * __cosf(6.283185307179586f * u2);
+}
+
+__device__ __forceinline__ float mixed_target(const UpdateParams& p, int s, int l, int c) {
+  // model.py:964-995: dynamic + sum_b alpha_b * static_b (face dims) / sum_b static_b (last 3 dims, unweighted)
+  const float* row = p.dec + ((int64_t)s * p.T + 1 + p.Lp + l) * p.ldd;
+  const float* st = p.stat + (int64_t)s * p.nb * p.dm;
+  float v = row[c];
+  const bool face = c < p.dm - 3;
+  for (int b = 0; b < p.nb; ++b) v += (face ? row[p.dm + b] : 1.0f) * st[b * p.dm + c];
+  return v;
+}
+
+__global__ void __launch_bounds__(256) update_kernel(UpdateParams p) {
+  const int64_t n_el = (int64_t)p.NX * p.L * p.dm;
+  const int t = p.steps[0];
+  // model.py:383-386, :421-428 — 0-dim fp32 tensor arithmetic, same operation order
+  const float alpha = p.alphas[t], ab = p.alpha_bars[t], abp = p.alpha_bars[t - 1];
+  const float sigma = p.sig_flex[t] * p.flexibility + p.sig_inflex[t] * (1.0f - p.flexibility);
+  float c0, c1;
+  if (p.target_noise) {
+    c0 = 1.0f / sqrtf(alpha);
+    c1 = (1.0f - alpha) / sqrtf(1.0f - ab);
+  } else {
+    c0 = (1.0f - abp) * sqrtf(alpha) / (1.0f - ab);
+    c1 = (1.0f - alpha) * sqrtf(abp) / (1.0f - ab);
+  }
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_el; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % p.dm);
+    const int l = (int)((i / p.dm) % p.L);
+    const int n = (int)(i / ((int64_t)p.dm * p.L));
+    // CFG combine (model.py:404-417); results[0] is updated in place through a view, so 'independent'
+    // subtracts the running target
+    float tgt = mixed_target(p, n, l, c);
+    float prev = tgt;
+    for (int e = 1; e < p.E; ++e) {
+      const float r = mixed_target(p, e * p.NX + n, l, c);
+      const float ref = (p.cfg_independent || e == 1) ? tgt : prev;
+      tgt = tgt + (e == 1 ? p.scale0 : p.scale1) * (r - ref);
+      prev = r;
+    }
+    float zt = 0.f;
+    if (t > 1) zt = p.z ? p.z[(int64_t)t * n_el + i] : philox_normal(p.seed, (uint32_t)t, (uint32_t)i);
+    const float xo = p.x[i];
+    const float xn = p.target_noise ? (c0 * (xo - c1 * tgt) + sigma * zt) : (c0 * xo + c1 * tgt + sigma * zt);
+    p.x[i] = xn;
+    if (p.traj) p.traj[(int64_t)(t - 1) * n_el + i] = xn;
+  }
+}
+int update_launch(const UpdateParams& p, cudaStream_t st) {
+  const int64_t n = (int64_t)p.NX * p.L * p.dm;
+  update_kernel<<<(int)std::min<int64_t>(cdiv(n, 256), kNumSMs * 8), 256, 0, st>>>(p);
+  MSMD_CHECK_LAUNCH();
+  return MSMD_OK;
+}
+
+__global__ void steps_set_kernel(int* steps, int S, int v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < S) steps[i] = v;
+}
+__global__ void steps_advance_kernel(int* steps, int S) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < S) steps[i] -= 1;
+}
+int steps_set(int* steps, int S, int value, cudaStream_t st) {
+  steps_set_kernel<<<cdiv(S, 256), 256, 0, st>>>(steps, S, value);
+  MSMD_CHECK_LAUNCH();
+  return MSMD_OK;
+}
+int steps_advance(int* steps, int S, cudaStream_t st) {
+  steps_advance_kernel<<<cdiv(S, 256), 256, 0, st>>>(steps, S);
+  MSMD_CHECK_LAUNCH();
+  return MSMD_OK;
+}
+
+__global__ void mix_static_kernel(const float* __restrict__ dec, const float* __restrict__ stat, float* __restrict__ out,
+                                  int S, int T, int dm, int nb, int ldd) {
+  const int64_t n_el = (int64_t)S * (T - 1) * dm;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_el; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % dm);
+    const int tok = (int)((i / dm) % (T - 1));
+    const int s = (int)(i / ((int64_t)dm * (T - 1)));
+    const float* row = dec + ((int64_t)s * T + 1 + tok) * ldd;
+    float v = row[c];
+    const bool face = c < dm - 3;
+    for (int b = 0; b < nb; ++b) v += (face ? row[dm + b] : 1.0f) * stat[((int64_t)s * nb + b) * dm + c];
+    out[i] = v;
+  }
+}
+int mix_static_launch(const float* dec, const float* stat, float* out, int S, int T, int dm, int nb, int ldd,
+                      cudaStream_t st) {
+  const int64_t n = (int64_t)S * (T - 1) * dm;
+  mix_static_kernel<<<(int)std::min<int64_t>(cdiv(n, 256), kNumSMs * 8), 256, 0, st>>>(dec, stat, out, S, T, dm, nb, ldd);
+  MSMD_CHECK_LAUNCH();
+  return MSMD_OK;
+}
+
+}  // namespace msmd

@@ -1,0 +1,77 @@
+// Non-GEMM kernels of the denoiser / sampler (model.py:914-996, :377-435): declarations.
+#pragma once
+#include "common.cuh"
+#include <cuda_bf16.h>
+
+namespace msmd {
+
+using bf16 = __nv_bfloat16;
+
+// out[r,c] = act(b[c] + sum_k x[r,k] W[c,k])  — small fp32 linears (step-invariant precompute only)
+int linear_simt(const float* x, int64_t ldx, const float* W, int64_t ldw, const float* b, float* out, int64_t ldo, int R,
+                int C, int K, int act, cudaStream_t st);
+
+// fp32 -> bf16 cast of a [rows, cols] block into a strided destination
+int cast_rows_bf16(const float* src, int64_t lds, bf16* dst, int64_t ldd, int64_t rows, int cols, cudaStream_t st);
+
+// memory = cat(prev_audio [S,Lp,d], audio [S,L,d]) -> bf16 [S, Lp+L, d]
+int build_memory_bf16(const float* prev_audio, const float* audio, bf16* mem, int S, int Lp, int L, int d, cudaStream_t st);
+
+struct EmbedParams {
+  // rows 0..Lp of every sequence (step-dependent only through the timestep embedding)
+  const float* pp;        // [S, d]   person_proj(person) (per window)
+  const float* temb;      // [T+1, d] diff_step_map(TE.pe) table
+  const float* pmproj;    // [S, Lp, d] feature_proj([prev_motion, 0]) (per window)
+  const float* PE;        // [1+Lp+L, d]
+  const int* steps;       // [S]
+  // rows Lp+1.. : feature_proj([x_t, indicator]) + PE
+  const float* x;         // [NX, L, dm]
+  const float* indicator; // [S, L] or null (-> no indicator column)
+  const float* WfT;       // [dm+1, d] feature_proj weight transposed (k-major), fp32
+  const float* bf;        // [d]
+  bf16* out;              // [S, 1+Lp+L, d]
+  int S, NX, E, Lp, L, d, dm;
+};
+int embed_launch(const EmbedParams& p, cudaStream_t st);
+
+// y [M,512] fp32 -> LayerNorm(g1,b1); rows with (token != 0): + add[(seq, token-1)] then LayerNorm(g2,b2) (optional)
+// -> out bf16 [M,512]; token-0 rows: LN1 only, written to x0 [S,512] (and NOT to out) when x0 != null.
+struct LnParams {
+  const float* y;           // [M, d]
+  const float* g1; const float* b1;
+  const bf16* add;          // [S, T-1, d] or null
+  const float* g2; const float* b2;   // used iff add != null
+  bf16* out;                // [M, d]
+  bf16* x0;                 // [S, d] or null
+  int M, T, d;
+};
+int ln_launch(const LnParams& p, cudaStream_t st);
+// row-0 finish: LayerNorm(y0 [S,d]; g,b) -> out[s*T + 0]
+int ln_row0_launch(const float* y0, const float* g, const float* b, bf16* out, int S, int T, int d, cudaStream_t st);
+
+// self-attention over T <= 112 tokens, head dim 64: qkv [S*T, 3*d] bf16 (q|k|v) -> ctx [S*T, d] bf16
+int self_attn_launch(const bf16* qkv, bf16* ctx, int S, int T, int H, cudaStream_t st);
+// row-0 cross attention: q0 [S,d]; kv [S*Tk, 2d] (k|v) -> ctx0 [S,d]
+int cross_attn_row0_launch(const bf16* q0, const bf16* kv, bf16* ctx0, int S, int Tk, int H, cudaStream_t st);
+
+struct UpdateParams {
+  const float* dec;       // [S, T, ldd] fp32: motion_dec output (dm dynamic + nb alphas)
+  const float* stat;      // [S, nb, dm]
+  float* x;               // [NX, L, dm]  in/out
+  const float* z;         // [Tsteps+1, NX, L, dm] or null
+  float* traj;            // [Tsteps+1, NX, L, dm] or null (writes index t-1)
+  const int* steps;       // [S] (all equal in sampling mode)
+  const float* alphas; const float* alpha_bars; const float* sig_flex; const float* sig_inflex;  // [Tsteps+1]
+  float scale0, scale1, flexibility;
+  unsigned long long seed;
+  int NX, E, T, L, Lp, dm, nb, ldd;
+  int cfg_independent, target_noise;
+};
+int update_launch(const UpdateParams& p, cudaStream_t st);
+int steps_set(int* steps, int S, int value, cudaStream_t st);
+int steps_advance(int* steps, int S, cudaStream_t st);
+
+// out[S, T-1... ] : x̂0 per sequence (module-level parity): dyn + static mix for ALL Lp+L rows -> [S, T-1, dm]
+int mix_static_launch(const float* dec, const float* stat, float* out, int S, int T, int dm, int nb, int ldd, cudaStream_t st);
+
+}  // namespace msmd

@@ -67,7 +67,7 @@ struct GemmCfg {
 // erf by Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7): enough for a bf16-rounded GELU, 3x cheaper than erff
 __device__ __forceinline__ float erf_fast(float x) {
   const float ax = fabsf(x);
-  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
   float p = fmaf(1.061405429f, t, -1.453152027f);
   p = fmaf(p, t, 1.421413741f);
   p = fmaf(p, t, -0.284496736f);
