@@ -110,6 +110,9 @@ class FlameWorkload:
         v, _, _ = self.model(sh, ex, po, ey, return_lm2d=False, return_lm3d=False)
         return v
 
+    def profile_step(self):
+        return self.step()
+
     def step_e2e(self):
         sh, ex, po, ey = [h.to(self.device, non_blocking=True) for h in self.host]
         v, _, _ = self.model(sh, ex, po, ey, return_lm2d=False, return_lm3d=False)
@@ -146,19 +149,146 @@ class FlameWorkload:
                     sample=f'{n} frames in 512-frame batches, {dt:.1f} s, oracle/flame_lbs.py (torch CPU fp32)')
 
 
-WORKLOADS = {'flame': FlameWorkload}
-DEFAULT_WORKLOAD = 'flame'
+class SamplerWorkload:
+    """configs[2]: 64 clips x 10 s @ 25 fps, style-conditioned CFG sampling (3 entries, 3 windows x 500 steps,
+    bf16 tensor-core GEMMs) followed by the FLAME decode of the 64 x 250 generated frames."""
+    name = 'sampler'
+    metric = 'generated_animation_seconds_per_second'
+    unit = 'animation-s/s'
+    dtype = 'bf16'
+    kernel = 'gemm_bf16'
+
+    def __init__(self, clips=64, seconds=10.0):
+        self.clips, self.seconds = clips, seconds
+        self.frames = int(seconds * 25)
+        self.n_sub = -(-self.frames // 100)
+
+    def config(self, world):
+        return dict(workload=f'{self.clips} clips x {self.seconds:g} s @ 25 fps per GPU, 3 CFG entries, {self.n_sub} windows x 500 steps, '
+                             'bf16 + FLAME decode (BASELINE configs[2])',
+                    clips_per_gpu=self.clips, sequences=3 * self.clips, rows=3 * self.clips * 111,
+                    parallelism=f'clips sharded x{world}, no collective',
+                    audio='synthetic audio FEATURES [clips, 300, 512] (CUDA audio encoder not in this step yet)',
+                    noise='externally supplied z [501, clips, 100, 67], shared by the windows',
+                    l2_policy='per-layer activations (qkv 65 MB + h 87 MB + ...) exceed the 126 MB L2 every layer')
+
+    def setup(self, device, rank):
+        from types import SimpleNamespace
+        import torch.nn as nn
+        from msmd_b200 import model as M
+        from msmd_b200.utils.flame import FLAME
+        from oracle import synth
+        from oracle.ref_shims import pinned_args
+        self.args = pinned_args()
+        m = M.MSMD(self.args, 'cpu', True, use_head_alpha=False, audio_encoder=nn.Identity())
+        m.load_state_dict(synth.fill_state_dict(synth.param_spec(m), 1234), strict=False)
+        self.model = m.to(device).eval()
+        raw = synth.flame_raw(0, synth.FLAME_V, 400)
+        self.flame = FLAME(SimpleNamespace(n_shape=300, n_exp=100, flame_lmk_embedding_path=None), raw=raw).to(device)
+        g = torch.Generator().manual_seed(1000 + rank)
+        N, tot = self.clips, self.n_sub * 100
+        self.host = dict(audio_feat=torch.randn(N, tot, 512, generator=g), style=torch.randn(N, 256, generator=g),
+                         shape=torch.zeros(N, 1, 100), x_T=torch.randn(N, 100, 67, generator=g),
+                         z=torch.randn(501, N, 100, 67, generator=g))
+        self.host = {k: v.pin_memory() for k, v in self.host.items()}
+        self.dev = {k: v.to(device) for k, v in self.host.items()}
+        self.host_out = torch.empty((N, self.frames, 67)).pin_memory()
+        self.host_verts = torch.empty((N, self.frames, synth.FLAME_V, 3)).pin_memory()
+        self.device = device
+
+    def units(self):
+        return self.clips * self.frames / 25.0
+
+    def launches_per_step(self):
+        per_denoise = 2 + 8 * 11 + 2 + 2          # embed(2) + 8 layers x 11 kernels + motion_dec(2) + update/advance
+        return self.n_sub * (500 * per_denoise + 8 * 2 + 12) + 3
+
+    def _run(self, d):
+        from msmd_b200.inference import infer_coeffs_batched
+        from msmd_b200.decode import decode_vertices
+        codes = infer_coeffs_batched(self.model, self.args, d['audio_feat'], d['shape'], d['style'],
+                                     clip_len=self.frames, cfg_scale=1.4, x_T=d['x_T'], noise=d['z'])
+        verts = decode_vertices(self.flame, codes, n_exp=100)
+        return codes, verts
+
+    def step(self):
+        return self._run(self.dev)
+
+    def profile_step(self):
+        # 10 eager sampling steps of the window left open by the last step(): only the per-step GEMMs are timed
+        eng = self.model._eng
+        eng.sample_window(self.dev['x_T'], self.dev['z'], 0, False, 1.4, 1.4, 0.0, t_start=500, n_steps=10)
+
+    def step_e2e(self):
+        d = {k: v.to(self.device, non_blocking=True) for k, v in self.host.items()}
+        codes, verts = self._run(d)
+        self.host_out.copy_(codes, non_blocking=True)
+        self.host_verts.copy_(verts, non_blocking=True)
+        return codes
+
+    def e2e_bytes(self):
+        return sum(v.numel() * 4 for v in self.host.values()), (self.host_out.numel() + self.host_verts.numel()) * 4
+
+    def roofline(self, peaks, kernel_ms):
+        # dominant kernel class = the bf16 tcgen05 GEMM.  Algorithmic FLOPs per denoiser forward as executed
+        # (SURVEY App. D-1, hoisted basis): per sequence 8 x (in_proj 174.6M + out 58.2M + FFN 465.6M) + motion_dec 32.8M
+        S = 3 * self.clips
+        per_fwd = S * (8 * (174.6e6 + 58.2e6 + 465.6e6) + 32.8e6)
+        n_gemm = 8 * 4 + 2 + 8 * 2          # big GEMMs + motion_dec + the row-0 q/out projections
+        flops_per_launch = per_fwd / n_gemm
+        ach = flops_per_launch / (kernel_ms * 1e-3) / 1e12
+        pk = peaks.get('bf16_tflops_sustained', peaks['bf16_tflops'])
+        return dict(bound='tensor', kernel=self.kernel, achieved=ach, peak=pk, unit='TFLOP/s', frac=ach / pk,
+                    traffic=None, peak_source=peaks['_source'] + ' (sustained cuBLAS bf16)',
+                    algorithmic_flops_per_launch=flops_per_launch, launches_per_forward=n_gemm, kernel_ms=kernel_ms)
+
+    def cpu_reference(self, seconds=15.0):
+        """oracle port of the sampler (oracle/denoiser.py) on the host cores: a bounded number of sampling
+        steps of ONE clip (3 CFG entries), extrapolated to the clip's 3 x 500 steps."""
+        from oracle import denoiser as D
+        from oracle import synth
+        from oracle.ref_shims import pinned_args
+        import torch.nn as nn
+        from msmd_b200 import model as M
+        torch.set_num_threads(os.cpu_count())
+        args = pinned_args()
+        m = M.MSMD(args, 'cpu', True, use_head_alpha=False, audio_encoder=nn.Identity())
+        m.load_state_dict(synth.fill_state_dict(synth.param_spec(m), 1234), strict=False)
+        sd = {k: v.detach() for k, v in m.state_dict().items()}
+        i = synth.sampler_inputs(1, 500, 0)
+        with torch.no_grad():
+            D.sample(sd, args, i['audio_feat'], i['shape'], i['style'], x_T=i['x_T'], z=i['z'], indicator=i['indicator'],
+                     cfg_scale=1.4, n_steps=1)
+            n, t0 = 0, time.perf_counter()
+            while time.perf_counter() - t0 < seconds or n == 0:
+                D.sample(sd, args, i['audio_feat'], i['shape'], i['style'], x_T=i['x_T'], z=i['z'],
+                         indicator=i['indicator'], cfg_scale=1.4, n_steps=4)
+                n += 4
+        dt = time.perf_counter() - t0
+        per_clip = dt / n * 500 * self.n_sub
+        return dict(value=self.seconds / per_clip, unit=self.unit, cores=torch.get_num_threads(), kind='port',
+                    sample=f'{n} sampling steps of 1 clip (3 CFG entries) in {dt:.1f} s, extrapolated to {self.n_sub} windows x 500 '
+                           'steps; oracle/denoiser.py (torch CPU fp32); FLAME decode and encoders excluded (<1% of the work)')
+
+
+WORKLOADS = {'flame': FlameWorkload, 'sampler': SamplerWorkload}
+DEFAULT_WORKLOAD = 'sampler'
+DEFAULT_STEPS = {'flame': (20, 5), 'sampler': (2, 1)}
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
-    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--steps', type=int, default=None)
+    ap.add_argument('--warmup', type=int, default=None)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument('--no-cpu-baseline', action='store_true')
     a = ap.parse_args()
+    if a.steps is None:
+        a.steps = DEFAULT_STEPS[a.workload][0]
+    if a.warmup is None:
+        a.warmup = DEFAULT_STEPS[a.workload][1]
     rank = int(os.environ.get('RANK', 0))
     local = int(os.environ.get('LOCAL_RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
@@ -204,10 +334,10 @@ def main():
     from msmd_b200 import _lib
     wl.setup(device, rank)
     peaks = load_peaks()
-    W = max(3, a.warmup)
+    W = max(3, a.warmup) if a.workload == 'flame' else max(1, a.warmup)
 
-    def timed(fn, steps, profile=False):
-        for _ in range(W):
+    def timed(fn, steps, profile=False, warm=None):
+        for _ in range(W if warm is None else warm):
             fn()
         barrier()
         if profile:
@@ -227,10 +357,10 @@ def main():
         ms = timed(wl.step, a.steps)
     clocks = cs.summary()
     # dominant-kernel duration, measured live with CUDA events on the launching stream
-    timed(wl.step, min(a.steps, 10), profile=True)
+    timed(wl.profile_step, 1, profile=True, warm=1)
     kms, kn = _lib.profile_query(wl.kernel)
     kernel_ms = kms / max(1, kn)
-    ms_e2e = timed(wl.step_e2e, a.steps)
+    ms_e2e = timed(wl.step_e2e, a.steps, warm=1)
     h2d, d2h = wl.e2e_bytes()
 
     out = dict(metric=wl.metric, value=wl.units() * world * a.steps / (ms * 1e-3), unit=wl.unit, n_gpus=world,

@@ -1,0 +1,68 @@
+"""Drop-in for the hot-path driver of /root/reference/inference.py: ``infer_coeffs`` (inference.py:34-75).
+
+Same signature and windowing semantics: the audio encoder sees the whole zero-padded clip once, windows
+of ``n_motions`` frames are sampled sequentially, each conditioned on the previous window's last
+``n_prev_motions`` frames of motion and of INPUT audio features, every window re-uses window 0's x_T
+(inference.py:57-69), and the padded tail is trimmed.
+
+``infer_coeffs_batched`` is the same loop over a batch of independent clips (the reference handles one
+clip per call; clips never interact, so they are simply stacked along the batch dimension).
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+
+@torch.no_grad()
+def infer_coeffs_batched(model, args, audio_feat, shape_coef, style_feats=None, clip_len=None, cfg_mode=None,
+                         cfg_cond=None, cfg_scale=1.15, dynamic_threshold=None, x_T=None, noise=None):
+    """audio_feat [N, n_sub*n_motions, d] (already extracted); shape_coef [N,1,100] or [N,100];
+    style_feats [N,d_style] (or a list per window); clip_len = frames to keep (<= n_sub*n_motions).
+    x_T [N,n_motions,67] / noise ([T+1,N,L,67] or a list per window) are optional fixed inputs.
+    Returns [N, clip_len, 67]."""
+    N, total = audio_feat.shape[:2]
+    L = args.n_motions
+    assert total % L == 0, f'audio feature length {total} is not a multiple of n_motions={L}'
+    n_sub = total // L
+    clip_len = total if clip_len is None else clip_len
+    n_padding_frames = total - clip_len
+    coef_list = []
+    prev_motion_feat = prev_audio_feat = None
+    noise_T = x_T
+    for i in range(n_sub):
+        indicator = torch.ones((N, L), device=audio_feat.device) if args.use_indicator else None
+        if indicator is not None and i == n_sub - 1 and n_padding_frames > 0:
+            indicator[:, -n_padding_frames:] = 0
+        audio_in = audio_feat[:, i * L:(i + 1) * L]
+        style_feat = style_feats[i] if isinstance(style_feats, list) else style_feats
+        z = noise[i] if isinstance(noise, list) else noise
+        motion_feat, noise_T, used_audio = model.sample(
+            audio_in, shape_coef, style_feat, prev_motion_feat, prev_audio_feat, noise_T, indicator=indicator,
+            cfg_mode=cfg_mode, cfg_cond=cfg_cond, cfg_scale=cfg_scale, dynamic_threshold=dynamic_threshold, noise=z)
+        prev_motion_feat = motion_feat[:, -args.n_prev_motions:].clone()
+        prev_audio_feat = used_audio[:, -args.n_prev_motions:]
+        if i == n_sub - 1 and n_padding_frames > 0:
+            motion_feat = motion_feat[:, :-n_padding_frames]
+        coef_list.append(motion_feat)
+    return torch.cat(coef_list, dim=1)
+
+
+@torch.no_grad()
+def infer_coeffs(model, args, audio, shape_coef, audio_unit, style_feats=None, n_repetitions: int = 1, cfg_mode=None,
+                 cfg_cond=None, cfg_scale: float = 1.15, include_shape: bool = False, dynamic_threshold=(0, 1, 4)):
+    """inference.py:34-75 (one clip, 1-D 16 kHz audio)."""
+    clip_len = int(len(audio) / 16000 * args.fps)
+    n_audio_samples = round(audio_unit * args.n_motions)
+    n_subdivision = 1 if clip_len <= args.n_motions else math.ceil(clip_len / args.n_motions)
+    n_padding_audio_samples = n_audio_samples * n_subdivision - len(audio)
+    n_padding_frames = math.ceil(n_padding_audio_samples / audio_unit)
+    if n_padding_audio_samples > 0:
+        audio = F.pad(audio, (0, n_padding_audio_samples), value=0)
+    audio_feat = model.extract_audio_feature(audio.unsqueeze(0), args.n_motions * n_subdivision)
+    total = args.n_motions * n_subdivision
+    rep = lambda t: t if t is None else t.expand(n_repetitions, *t.shape[1:])
+    style = [rep(s) for s in style_feats] if isinstance(style_feats, list) else rep(style_feats)
+    return infer_coeffs_batched(model, args, audio_feat.expand(n_repetitions, -1, -1), rep(shape_coef), style,
+                                clip_len=total - max(n_padding_frames, 0), cfg_mode=cfg_mode, cfg_cond=cfg_cond,
+                                cfg_scale=cfg_scale, dynamic_threshold=dynamic_threshold)
