@@ -18,6 +18,10 @@ __device__ __forceinline__ float warp_max(float v) {
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
 __device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 
 // ------------------------------------------------------------------------------------------- small fp32 linear
@@ -102,36 +106,46 @@ __global__ void embed_ctx_kernel(EmbedParams p) {
 }
 // rows Lp+1..: feature_proj([x_t, indicator]) + PE, computed once per x row and written to its E sequences
 constexpr int kEmbedRows = 20;
-__global__ void __launch_bounds__(512) embed_x_kernel(EmbedParams p) {
-  extern __shared__ float xs[];  // [kEmbedRows][dm]
+__global__ void __launch_bounds__(256) embed_x_kernel(EmbedParams p) {
+  extern __shared__ float xs[];  // [kEmbedRows][dm] x rows, then [E][kEmbedRows] indicators
   const int T = 1 + p.Lp + p.L;
   const int blocks_per_x = (p.L + kEmbedRows - 1) / kEmbedRows;
   const int n = blockIdx.x / blocks_per_x;
   const int l0 = (blockIdx.x % blocks_per_x) * kEmbedRows;
   const int nr = min(kEmbedRows, p.L - l0);
+  float* inds = xs + kEmbedRows * p.dm;
   for (int i = threadIdx.x; i < nr * p.dm; i += blockDim.x) xs[i] = p.x[((int64_t)n * p.L + l0) * p.dm + i];
+  for (int i = threadIdx.x; i < p.E * kEmbedRows; i += blockDim.x) {
+    const int e = i / kEmbedRows, r = i % kEmbedRows;
+    inds[i] = (p.indicator && r < nr) ? p.indicator[(int64_t)(e * p.NX + n) * p.L + l0 + r] : 0.f;
+  }
   __syncthreads();
-  for (int c = threadIdx.x; c < p.d; c += blockDim.x) {
-    float acc[kEmbedRows];
+  for (int c = 2 * threadIdx.x; c < p.d; c += 2 * blockDim.x) {
+    float a0[kEmbedRows], a1[kEmbedRows];
 #pragma unroll
-    for (int r = 0; r < kEmbedRows; ++r) acc[r] = 0.f;
+    for (int r = 0; r < kEmbedRows; ++r) a0[r] = a1[r] = 0.f;
     for (int k = 0; k < p.dm; ++k) {
-      const float w = p.WfT[(int64_t)k * p.d + c];
-#pragma unroll
-      for (int r = 0; r < kEmbedRows; ++r)
-        if (r < nr) acc[r] = fmaf(xs[r * p.dm + k], w, acc[r]);
-    }
-    const float wi = p.indicator ? p.WfT[(int64_t)p.dm * p.d + c] : 0.f;
-    const float bc = p.bf[c];
-    for (int e = 0; e < p.E; ++e) {
-      const int s = e * p.NX + n;
+      const float2 w = *reinterpret_cast<const float2*>(p.WfT + (int64_t)k * p.d + c);
 #pragma unroll
       for (int r = 0; r < kEmbedRows; ++r) {
-        if (r < nr) {
-          const int l = l0 + r;
-          const float ind = p.indicator ? p.indicator[(int64_t)s * p.L + l] : 0.f;
-          const float v = acc[r] + bc + ind * wi + p.PE[(1 + p.Lp + l) * p.d + c];
-          p.out[((int64_t)s * T + 1 + p.Lp + l) * p.d + c] = __float2bfloat16_rn(v);
+        const float xv = xs[r * p.dm + k];
+        a0[r] = fmaf(xv, w.x, a0[r]);
+        a1[r] = fmaf(xv, w.y, a1[r]);
+      }
+    }
+    const float2 wi = *reinterpret_cast<const float2*>(p.WfT + (int64_t)p.dm * p.d + c);
+    const float2 bc = *reinterpret_cast<const float2*>(p.bf + c);
+#pragma unroll
+    for (int r = 0; r < kEmbedRows; ++r) {
+      if (r < nr) {
+        const int l = l0 + r;
+        const float2 pe = *reinterpret_cast<const float2*>(p.PE + (int64_t)(1 + p.Lp + l) * p.d + c);
+        const float b0 = a0[r] + bc.x + pe.x, b1 = a1[r] + bc.y + pe.y;
+        for (int e = 0; e < p.E; ++e) {
+          const float ind = inds[e * kEmbedRows + r];
+          const int s = e * p.NX + n;
+          *reinterpret_cast<uint32_t*>(p.out + ((int64_t)s * T + 1 + p.Lp + l) * p.d + c) =
+              pack_bf16(b0 + ind * wi.x, b1 + ind * wi.y);
         }
       }
     }
@@ -141,7 +155,7 @@ int embed_launch(const EmbedParams& p, cudaStream_t st) {
   embed_ctx_kernel<<<p.S * (p.Lp + 1), 128, 0, st>>>(p);
   MSMD_CHECK_LAUNCH();
   const int blocks = p.NX * ((p.L + kEmbedRows - 1) / kEmbedRows);
-  embed_x_kernel<<<blocks, 512, kEmbedRows * p.dm * sizeof(float), st>>>(p);
+  embed_x_kernel<<<blocks, 256, (kEmbedRows * p.dm + 3 * kEmbedRows) * sizeof(float), st>>>(p);
   MSMD_CHECK_LAUNCH();
   return MSMD_OK;
 }
@@ -257,18 +271,14 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
-  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&h);
-}
 
-constexpr int kAttT = 112, kAttDh = 64, kQKStride = 72, kVtStride = 120;
+constexpr int kAttT = 112, kAttDh = 64, kQKStride = 72;
 
-__global__ void __launch_bounds__(224) self_attn_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ ctx, int T,
+__global__ void __launch_bounds__(224, 3) self_attn_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ ctx, int T,
                                                         int H) {
   __shared__ __align__(16) bf16 sQ[kAttT * kQKStride];
   __shared__ __align__(16) bf16 sK[kAttT * kQKStride];
-  __shared__ __align__(16) bf16 sVt[kAttDh * kVtStride];
+  __shared__ __align__(16) bf16 sV[kAttT * kQKStride];
   const int h = blockIdx.x, s = blockIdx.y;
   const int d = H * kAttDh;
   const int tid = threadIdx.x;
@@ -284,9 +294,7 @@ __global__ void __launch_bounds__(224) self_attn_kernel(const bf16* __restrict__
     }
     *reinterpret_cast<uint4*>(&sQ[row * kQKStride + ch * 8]) = q;
     *reinterpret_cast<uint4*>(&sK[row * kQKStride + ch * 8]) = k;
-    const bf16* vv = reinterpret_cast<const bf16*>(&v);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) sVt[(ch * 8 + j) * kVtStride + row] = vv[j];
+    *reinterpret_cast<uint4*>(&sV[row * kQKStride + ch * 8]) = v;
   }
   __syncthreads();
 
@@ -346,11 +354,17 @@ __global__ void __launch_bounds__(224) self_attn_kernel(const bf16* __restrict__
     ap[1] = pack_bf16(sc[2 * kb][2], sc[2 * kb][3]);
     ap[2] = pack_bf16(sc[2 * kb + 1][0], sc[2 * kb + 1][1]);
     ap[3] = pack_bf16(sc[2 * kb + 1][2], sc[2 * kb + 1][3]);
+    // V is [key][dh] row-major: ldmatrix.trans hands out the (k = key, n = dh) B fragments, two dh tiles per x4
 #pragma unroll
-    for (int n = 0; n < 8; ++n) {
-      const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&sVt[(n * 8 + g) * kVtStride + kb * 16 + 2 * t]);
-      const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&sVt[(n * 8 + g) * kVtStride + kb * 16 + 8 + 2 * t]);
-      mma_bf16_16816(o[n], ap, b0, b1);
+    for (int n2 = 0; n2 < 4; ++n2) {
+      const int mrow = kb * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;   // matrices 0/1: keys 0-7 / 8-15 of dh tile 2*n2
+      const int mcol = (2 * n2 + (lane >> 4)) * 8;                     // matrices 2/3: same keys, dh tile 2*n2+1
+      uint32_t b0, b1, b2, b3;
+      const uint32_t addr = (uint32_t)__cvta_generic_to_shared(&sV[mrow * kQKStride + mcol]);
+      asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                   : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3) : "r"(addr));
+      mma_bf16_16816(o[2 * n2], ap, b0, b1);
+      mma_bf16_16816(o[2 * n2 + 1], ap, b2, b3);
     }
   }
   const float i0 = 1.0f / l0, i1 = 1.0f / l1;
@@ -381,38 +395,67 @@ __global__ void __launch_bounds__(256) cross_attn_row0_kernel(const bf16* __rest
   if (w >= S * H) return;
   const int s = w / H, h = w % H;
   const int d = H * 64;
-  // q: lane holds dims 2*lane, 2*lane+1
-  const uint32_t qu = *reinterpret_cast<const uint32_t*>(q0 + (int64_t)s * d + h * 64 + 2 * lane);
-  const float qa = __uint_as_float(qu << 16), qb = __uint_as_float(qu & 0xffff0000u);
-  float sc[4];  // scores of keys lane, lane+32, lane+64, lane+96
+  // every lane keeps the whole 64-dim query (broadcast loads), and scores keys lane, lane+32, lane+64, lane+96
+  float q[64];
+  {
+    const uint4* qp = reinterpret_cast<const uint4*>(q0 + (int64_t)s * d + h * 64);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const uint4 u = __ldg(qp + i);
+      const uint32_t ww[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        q[i * 8 + 2 * k] = __uint_as_float(ww[k] << 16);
+        q[i * 8 + 2 * k + 1] = __uint_as_float(ww[k] & 0xffff0000u);
+      }
+    }
+  }
+  float sc[4];
 #pragma unroll
   for (int grp = 0; grp < 4; ++grp) {
-    float mine = -INFINITY;
-    for (int j0 = 0; j0 < 32; ++j0) {
-      const int j = grp * 32 + j0;
-      if (j >= Tk) break;
-      const uint32_t ku = *reinterpret_cast<const uint32_t*>(kv + ((int64_t)s * Tk + j) * 2 * d + h * 64 + 2 * lane);
-      float p = qa * __uint_as_float(ku << 16) + qb * __uint_as_float(ku & 0xffff0000u);
-      p = warp_sum(p);
-      if (j0 == lane) mine = p * 0.125f;
+    const int j = grp * 32 + lane;
+    float dot = -INFINITY;
+    if (j < Tk) {
+      const uint4* kp = reinterpret_cast<const uint4*>(kv + ((int64_t)s * Tk + j) * 2 * d + h * 64);
+      float acc = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint4 u = __ldg(kp + i);
+        const uint32_t ww[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          acc = fmaf(q[i * 8 + 2 * k], __uint_as_float(ww[k] << 16), acc);
+          acc = fmaf(q[i * 8 + 2 * k + 1], __uint_as_float(ww[k] & 0xffff0000u), acc);
+        }
+      }
+      dot = acc * 0.125f;
     }
-    sc[grp] = mine;
+    sc[grp] = dot;
   }
   const float m = warp_max(fmaxf(fmaxf(sc[0], sc[1]), fmaxf(sc[2], sc[3])));
   float l = 0.f;
 #pragma unroll
   for (int i = 0; i < 4; ++i) { sc[i] = (sc[i] == -INFINITY) ? 0.f : __expf(sc[i] - m); l += sc[i]; }
   l = warp_sum(l);
+  // output: lane owns dims 2*lane, 2*lane+1; V rows are read coalesced (128 B per key)
   float oa = 0.f, ob = 0.f;
+  const bf16* vbase = kv + (int64_t)s * Tk * 2 * d + d + h * 64 + 2 * lane;
 #pragma unroll
   for (int grp = 0; grp < 4; ++grp) {
-    for (int j0 = 0; j0 < 32; ++j0) {
-      const int j = grp * 32 + j0;
-      if (j >= Tk) break;
-      const float p = __shfl_sync(0xffffffffu, sc[grp], j0);
-      const uint32_t vu = *reinterpret_cast<const uint32_t*>(kv + ((int64_t)s * Tk + j) * 2 * d + d + h * 64 + 2 * lane);
-      oa = fmaf(p, __uint_as_float(vu << 16), oa);
-      ob = fmaf(p, __uint_as_float(vu & 0xffff0000u), ob);
+#pragma unroll
+    for (int j8 = 0; j8 < 32; j8 += 8) {   // 8 independent V loads in flight per batch
+      uint32_t vu[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int j = grp * 32 + j8 + u;
+        vu[u] = (j < Tk) ? __ldg(reinterpret_cast<const uint32_t*>(vbase + (int64_t)j * 2 * d)) : 0u;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float p = __shfl_sync(0xffffffffu, sc[grp], j8 + u);   // 0 for keys >= Tk
+        oa = fmaf(p, __uint_as_float(vu[u] << 16), oa);
+        ob = fmaf(p, __uint_as_float(vu[u] & 0xffff0000u), ob);
+      }
     }
   }
   const float inv = 1.0f / l;

@@ -43,13 +43,14 @@ struct GemmCfg {
   static constexpr int STAGE_BYTES = NSPLIT * (A_BYTES + B_BYTES);
   static constexpr int OUT_COLS = 128 / (int)sizeof(OutT);
   static constexpr int AUX_COLS = 128 / (int)sizeof(AuxT);
-  static constexpr int EPI_WARP_BYTES = 4096 + (HAS_AUX ? 8192 : 0);
+  static constexpr int EPI_WARP_BYTES = 8192 + (HAS_AUX ? 8192 : 0);  // 2 out staging (+ 2 aux) tiles of 4 KB
   static constexpr int EPI_BYTES = EPI_WARPS * EPI_WARP_BYTES;
-  static constexpr int BAR_BYTES = 1024;
-  static constexpr int BUDGET = 227 * 1024 - 1024 /*alignment slack*/ - BAR_BYTES;
+  static constexpr int BAR_BYTES = 256 + 2 * 256 * 4;  // mbarriers + TMEM slot, then 2 bias tiles of <= 256 floats
+  static constexpr int ALIGN_SLACK = 512;              // dynamic smem base is >= 512-byte aligned in practice; checked
+  static constexpr int BUDGET = 227 * 1024 - ALIGN_SLACK - BAR_BYTES;
   static constexpr int STAGES_RAW = (BUDGET - EPI_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
-  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES;
+  static constexpr int SMEM_BYTES = ALIGN_SLACK + STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES;
   static constexpr int THREADS = 64 + 32 * EPI_WARPS;
   // MODE 1 keeps the small cross terms (hi*lo + lo*hi) in their own accumulator: the tensor core adds into
   // the accumulator with truncation, so the error grows with the number of MMAs chained on one accumulator.
@@ -60,7 +61,8 @@ struct GemmCfg {
   static constexpr int COLS_PER_WARP = BN / COL_SPLIT;
   static_assert(EPI_WARPS == 4 || EPI_WARPS == 8, "epilogue warps must cover the 4 TMEM lane quarters");
   static_assert(BN % 32 == 0 && BN <= 256 && TMEM_NEED <= 512, "BN");
-  static_assert(COLS_PER_WARP % OUT_COLS == 0 && (!HAS_AUX || COLS_PER_WARP % AUX_COLS == 0), "chunking");
+  static_assert(COLS_PER_WARP % 64 == 0, "the epilogue processes 32-column chunks in pairs");
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
   static_assert(STAGES >= 2, "not enough shared memory for a pipeline");
 };
 
@@ -98,6 +100,9 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_tc_kernel(const __grid_c
   uint64_t* tempty_bar = bars + 2 * STAGES + 2; // [2]
   uint64_t* aux_bar = bars + 2 * STAGES + 4;    // [EPI_WARPS][2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4 + 2 * Cfg::EPI_WARPS);
+  float* bias_tile = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [2][BN]
+  static_assert((2 * Cfg::STAGES + 4 + 2 * Cfg::EPI_WARPS) * 8 + 4 <= 256, "barrier block overflows its 256 bytes");
+  if (threadIdx.x == 0 && reinterpret_cast<uint8_t*>(bias_tile) + 2 * 256 * 4 > smem_raw + Cfg::SMEM_BYTES) __trap();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = p.tiles_m * p.tiles_n * p.batch;
@@ -205,12 +210,14 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_tc_kernel(const __grid_c
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
     const int csplit = e / 4;               // which column range of the tile
     uint8_t* my = epi_base + e * Cfg::EPI_WARP_BYTES;
-    uint8_t* out_stage = my;                // [32 rows][128 B], SW128
-    uint8_t* aux_stage = my + 4096;         // 2 x [32 rows][128 B]
+    uint8_t* out_stage = my;                // 2 x [32 rows][128 B], SW128
+    uint8_t* aux_stage = my + 8192;         // 2 x [32 rows][128 B]
     uint64_t* my_aux_bar = aux_bar + 2 * e;
     constexpr int CPW = Cfg::COLS_PER_WARP;
     constexpr int AUX_PER_TILE = Cfg::HAS_AUX ? CPW / Cfg::AUX_COLS : 1;
+    constexpr int EPI_THREADS = 32 * Cfg::EPI_WARPS;
     const int swz = lane & 7;
+    const int etid = threadIdx.x - 64;
 
     auto issue_aux = [&](int f) {  // flat aux-chunk index over this CTA's tiles
       if constexpr (Cfg::HAS_AUX) {
@@ -227,7 +234,8 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_tc_kernel(const __grid_c
         }
       }
     };
-    int af = 0;  // next aux chunk to consume
+    int af = 0;        // next aux chunk to consume
+    int so = 0;        // output staging buffers written so far (alternates between the two)
     issue_aux(0);
 
     int it = 0;
@@ -236,15 +244,18 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_tc_kernel(const __grid_c
       tile_coords(t, m0, n0, z);
       const int a = it & 1;
       const uint32_t aph = (it >> 1) & 1;
+      // bias tile -> shared (double-buffered by tile parity), overlapped with the wait for the accumulator.
+      // The named barrier also keeps the epilogue warps within one tile of each other.
+      float* sb = bias_tile + a * BN;
+      for (int i = etid; i < BN; i += EPI_THREADS)
+        sb[i] = (p.bias != nullptr && n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
       mbar_wait(&tfull_bar[a], aph);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + a * Cfg::ACC_COLS + csplit * CPW;
-#pragma unroll 1
-      for (int c = 0; c < CPW; c += 32) {
-        uint32_t raw[32];
-        tmem_ld32(t_addr + c, raw);
-        uint32_t raw2[MODE == 1 ? 32 : 1];
-        if constexpr (MODE == 1) tmem_ld32(t_addr + BN + c, raw2);
+      const float* sbw = sb + csplit * CPW;
+
+      auto process = [&](uint32_t (&raw)[32], uint32_t (&raw2)[MODE == 1 ? 32 : 1], int c) {
         const uint8_t* aux_buf = nullptr;
         int aux_off = 0;
         if constexpr (Cfg::HAS_AUX) {
@@ -256,27 +267,18 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_tc_kernel(const __grid_c
           aux_buf = aux_stage + (af & 1) * 4096 + lane * 128;
           aux_off = (c % Cfg::AUX_COLS) * (int)sizeof(AuxT) / 16;  // first 16-byte chunk of this 32-col slice
         }
-        tmem_ld_wait();
         float v[32];
-        const int colg = n0 + csplit * CPW + c;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          v[j] = __uint_as_float(raw[j]);
-          if constexpr (MODE == 1) v[j] += __uint_as_float(raw2[j]);
+        for (int j = 0; j < 8; ++j) {
+          const float4 b4 = *reinterpret_cast<const float4*>(sbw + c + 4 * j);   // broadcast LDS.128
+          v[4 * j + 0] = __uint_as_float(raw[4 * j + 0]) + b4.x;
+          v[4 * j + 1] = __uint_as_float(raw[4 * j + 1]) + b4.y;
+          v[4 * j + 2] = __uint_as_float(raw[4 * j + 2]) + b4.z;
+          v[4 * j + 3] = __uint_as_float(raw[4 * j + 3]) + b4.w;
         }
-        if (p.bias != nullptr) {  // warp-uniform
-          if (colg + 32 <= p.N) {
-            const float4* b4 = reinterpret_cast<const float4*>(p.bias + colg);
+        if constexpr (MODE == 1) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 b = __ldg(b4 + j);
-              v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (colg + j < p.N) v[j] += __ldg(p.bias + colg + j);
-          }
+          for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(raw2[j]);
         }
         if constexpr (GELU) {
 #pragma unroll
@@ -303,13 +305,14 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_tc_kernel(const __grid_c
           }
           if ((c + 32) % Cfg::AUX_COLS == 0) ++af;
         }
-        // ---- registers -> swizzled staging -> TMA store
+        // ---- registers -> swizzled staging (two buffers) -> TMA store
         const int o_off = (c % Cfg::OUT_COLS) * (int)sizeof(OutT) / 16;
         if (c % Cfg::OUT_COLS == 0) {
-          if (lane == 0) tma_store_wait_read<0>();  // previous store has finished reading the staging tile
+          if (lane == 0) tma_store_wait_read<1>();  // the store issued two buffers ago has finished reading smem
           __syncwarp();
         }
-        uint8_t* orow = out_stage + lane * 128;
+        uint8_t* obuf = out_stage + (so & 1) * 4096;
+        uint8_t* orow = obuf + lane * 128;
         if constexpr (sizeof(OutT) == 4) {
 #pragma unroll
           for (int j = 0; j < 8; ++j)
@@ -332,11 +335,31 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_tc_kernel(const __grid_c
           __syncwarp();
           if (lane == 0) {
             const int c0 = n0 + csplit * CPW + (c / Cfg::OUT_COLS) * Cfg::OUT_COLS;
-            if (p.batch > 1) tma_store_3d(&p.out_map, out_stage, c0, m0 + q * 32, z);
-            else tma_store_2d(&p.out_map, out_stage, c0, m0 + q * 32);
+            if (p.batch > 1) tma_store_3d(&p.out_map, obuf, c0, m0 + q * 32, z);
+            else tma_store_2d(&p.out_map, obuf, c0, m0 + q * 32);
             tma_store_commit();
           }
+          ++so;
         }
+      };
+
+      // software-pipelined TMEM reads: chunk c+1 is in flight while chunk c is processed
+      uint32_t rA[32], rB[32];
+      uint32_t rA2[MODE == 1 ? 32 : 1], rB2[MODE == 1 ? 32 : 1];
+      tmem_ld32(t_addr, rA);
+      if constexpr (MODE == 1) tmem_ld32(t_addr + BN, rA2);
+#pragma unroll 1
+      for (int c = 0; c < CPW; c += 64) {
+        tmem_ld_wait();
+        tmem_ld32(t_addr + c + 32, rB);
+        if constexpr (MODE == 1) tmem_ld32(t_addr + BN + c + 32, rB2);
+        process(rA, rA2, c);
+        tmem_ld_wait();
+        if (c + 64 < CPW) {
+          tmem_ld32(t_addr + c + 64, rA);
+          if constexpr (MODE == 1) tmem_ld32(t_addr + BN + c + 64, rA2);
+        }
+        process(rB, rB2, c + 32);
       }
       tc_fence_before();
       __syncwarp();
