@@ -161,6 +161,21 @@ int msmd_sample_window(msmd_model* m, const float* x_T, const float* z, uint64_t
                        float* x_out, float* traj, void* stream);
 
 /* ------------------------------------------------------------------------- *
+ * Style encoder — style_encoder.py:119-213 (StyleEncoder_VAE2.forward / .sample)
+ * motion [N,L,d_in] -> mu, logvar [N,d_style]; style = mu + eps * exp(0.5 logvar) with the
+ * caller's eps [N,d_style] (NULL -> style = mu).  Any of the three outputs may be NULL.
+ * Weights by state_dict key ("StyleEncoder_VAE2").  L <= 112 frames.
+ * ------------------------------------------------------------------------- */
+typedef struct msmd_style msmd_style;
+int msmd_style_create(int d_in, int d_model, int d_style, int max_clips, int max_len, int device,
+                      msmd_style** out);
+void msmd_style_destroy(msmd_style* m);
+int msmd_style_load_weights(msmd_style* m, const char* const* names, const void* const* data,
+                            const int64_t* numel, int n);
+int msmd_style_encode(msmd_style* m, const float* motion, int N, int L, const float* eps, float* style_out,
+                      float* mu_out, float* logvar_out, void* stream);
+
+/* ------------------------------------------------------------------------- *
  * FLAME decode — utils/flame.py:180-244 (FLAME.forward) -> utils/lbs.py:141-223 (lbs)
  *
  * msmd_flame_create packs the static bases once:

@@ -133,7 +133,37 @@ def gen_sampler():
     print('sampler.npz', res['incremental'].shape)
 
 
-SECTIONS = dict(rot=gen_rot, flame=gen_flame, denoiser=gen_denoiser, sampler=gen_sampler)
+STYLE_GOLD = dict(N=5, L=100, seed=31, weight_seed=77)
+
+
+def gen_style():
+    c = STYLE_GOLD
+    m = ref_shims.ref_modules()
+    enc = m.style.get_style_encoder(ref_shims.pinned_args(), 'vae2').eval()
+    enc.load_state_dict(synth.fill_state_dict(synth.param_spec(enc), c['weight_seed']), strict=False)
+    g = torch.Generator().manual_seed(c['seed'])
+    x = torch.randn(c['N'], c['L'], 67, generator=g)
+    eps = torch.randn(c['N'], 256, generator=g)
+    with ref_shims.inject_randn_like([eps]):
+        out, mu, logvar = enc(x)
+    x2 = torch.randn(3, 41, 67, generator=g)          # a shorter style clip
+    with ref_shims.inject_randn_like([eps[:3]]):
+        out2, mu2, logvar2 = enc(x2)
+    np.savez_compressed(os.path.join(OUT, 'style.npz'), out=out.numpy(), mu=mu.numpy(), logvar=logvar.numpy(),
+                        mu_short=mu2.numpy(), logvar_short=logvar2.numpy())
+    print('style.npz', out.shape)
+
+
+def style_inputs():
+    c = STYLE_GOLD
+    g = torch.Generator().manual_seed(c['seed'])
+    x = torch.randn(c['N'], c['L'], 67, generator=g)
+    eps = torch.randn(c['N'], 256, generator=g)
+    x2 = torch.randn(3, 41, 67, generator=g)
+    return x, eps, x2
+
+
+SECTIONS = dict(rot=gen_rot, flame=gen_flame, denoiser=gen_denoiser, sampler=gen_sampler, style=gen_style)
 
 
 def main(argv):
