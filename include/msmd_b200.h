@@ -176,6 +176,23 @@ int msmd_style_encode(msmd_style* m, const float* motion, int N, int L, const fl
                       float* mu_out, float* logvar_out, void* stream);
 
 /* ------------------------------------------------------------------------- *
+ * Audio encoder — utils/hubert.py:13-51, utils/wav2vec2.py:71-119 (HF Hubert / Wav2Vec2 *base*
+ * forward with the reference's 50 fps -> output_fps resampling) and model.py:250-264
+ * (MSMD.extract_audio_feature: encode at 2L frames, 2:1 linear resample, Linear 768 -> d).
+ * wav [N, n_samples] fp32 16 kHz (un-padded: pad_audio, model_common.py:110-123, is folded into the
+ * first conv's loads).  hidden_out [N, frame_num, 768] (last_hidden_state) and/or
+ * feat_out [N, feat_frames, d_out]; either may be NULL.
+ * Weights: "audio_encoder.*" (HF key names) and optionally "audio_feature_map.*".
+ * ------------------------------------------------------------------------- */
+typedef struct msmd_audio msmd_audio;
+int msmd_audio_create(int max_clips, int max_samples, int d_out, int device, msmd_audio** out);
+void msmd_audio_destroy(msmd_audio* m);
+int msmd_audio_load_weights(msmd_audio* m, const char* const* names, const void* const* data,
+                            const int64_t* numel, int n);
+int msmd_audio_encode(msmd_audio* m, const float* wav, int N, int n_samples, int output_fps, int frame_num,
+                      float* hidden_out, int feat_frames, float* feat_out, void* stream);
+
+/* ------------------------------------------------------------------------- *
  * FLAME decode — utils/flame.py:180-244 (FLAME.forward) -> utils/lbs.py:141-223 (lbs)
  *
  * msmd_flame_create packs the static bases once:

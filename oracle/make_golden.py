@@ -163,7 +163,34 @@ def style_inputs():
     return x, eps, x2
 
 
-SECTIONS = dict(rot=gen_rot, flame=gen_flame, denoiser=gen_denoiser, sampler=gen_sampler, style=gen_style)
+AUDIO_GOLD = dict(weight_seed=4321, clips=2, samples=64000, frames=100, short_samples=48000, short_frames=75)
+
+
+def audio_inputs():
+    c = AUDIO_GOLD
+    x = torch.stack([synth.clip_audio(i, c['samples']) for i in range(c['clips'])])
+    xs = torch.stack([synth.clip_audio(9, c['short_samples'])])
+    return x, xs
+
+
+def gen_audio():
+    c = AUDIO_GOLD
+    m = ref_shims.ref_modules()
+    res = {}
+    for am in ('hubert', 'wav2vec2'):
+        model = m.model.get_diffusion_model(ref_shims.pinned_args(audio_model=am), 'cpu').eval()
+        fill = synth.fill_state_dict(synth.param_spec(model, skip=('denoising_net.',)), c['weight_seed'])
+        missing, unexpected = model.load_state_dict(fill, strict=False)
+        assert not unexpected
+        x, xs = audio_inputs()
+        res[am] = model.extract_audio_feature(x, c['frames']).numpy()
+        res[am + '_short'] = model.extract_audio_feature(xs, c['short_frames']).numpy()
+    np.savez_compressed(os.path.join(OUT, 'audio.npz'), **res)
+    print('audio.npz', {k: v.shape for k, v in res.items()})
+
+
+SECTIONS = dict(rot=gen_rot, flame=gen_flame, denoiser=gen_denoiser, sampler=gen_sampler, style=gen_style,
+                audio=gen_audio)
 
 
 def main(argv):

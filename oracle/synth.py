@@ -93,6 +93,8 @@ def fill_state_dict(spec, seed=1234):
             t = 1.0 + 0.1 * torch.randn(shape, generator=g)
         elif is_norm and leaf == 'bias':
             t = 0.1 * torch.randn(shape, generator=g)
+        elif leaf == 'masked_spec_embed':
+            t = torch.rand(shape, generator=g)
         elif leaf in ('weight', 'in_proj_weight', 'original1', 'weight_v') and len(shape) >= 2:
             fan_in = int(np.prod(shape[1:]))
             b = 1.0 / math.sqrt(fan_in)

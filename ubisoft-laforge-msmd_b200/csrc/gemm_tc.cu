@@ -77,7 +77,10 @@ static int launch_cfg2(const GemmDesc& d, cudaStream_t st) {
   const int esz = Cfg::ELT;
   int rc;
   if ((rc = make_tmap_23(&p.a_map, d.A, in_dt, esz, d.K, d.M, d.lda, d.batch, d.sA, Cfg::BK, Cfg::BM))) return rc;
-  if ((rc = make_tmap_23(&p.b_map, d.W, in_dt, esz, d.K, d.N, d.ldw, d.batch, d.sW, Cfg::BK, Cfg::BN))) return rc;
+  {
+    const int wb = (d.batch > 1 && d.wz_mod != 0) ? (d.wz_mod > 0 ? d.wz_mod : d.batch) : 1;
+    if ((rc = make_tmap_23(&p.b_map, d.W, in_dt, esz, d.K, d.N, d.ldw, wb, d.sW, Cfg::BK, Cfg::BN))) return rc;
+  }
   if (MODE == 1) {
     MSMD_REQUIRE(d.A_lo && d.W_lo, "gemm: tf32x3 mode needs the lo operands");
     MSMD_REQUIRE(d.batch <= 1, "gemm: batched tf32x3 is not implemented");
@@ -99,6 +102,8 @@ static int launch_cfg2(const GemmDesc& d, cudaStream_t st) {
   p.M = d.M; p.N = d.N; p.K = d.K;
   p.act = d.act;
   p.batch = d.batch < 1 ? 1 : d.batch;
+  p.wz_mod = d.wz_mod;
+  p.bias_zstride = d.bias_zstride;
   p.tiles_m = cdiv(d.M, Cfg::BM);
   p.tiles_n = cdiv(d.N, Cfg::BN);
   const int tiles = p.tiles_m * p.tiles_n * p.batch;

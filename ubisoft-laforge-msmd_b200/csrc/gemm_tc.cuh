@@ -25,6 +25,8 @@ struct GemmParams {
   int M, N, K;
   int act;                         // 0 none, 1 exact-erf GELU
   int batch;                       // z tiles (3-D maps) or 1
+  int wz_mod;                      // batched W: -1 -> W[z], 0 -> one 2-D W shared by every z, n > 0 -> W[z % n]
+  int bias_zstride;                // bias offset per W batch index (wz_mod > 0)
   int tiles_m, tiles_n;
 };
 
@@ -148,7 +150,8 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_tc_kernel(const __grid_c
           mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
           if (p.batch > 1) {
             tma_load_3d(sa, &p.a_map, &full_bar[s], kb * BK, m0, z);
-            tma_load_3d(sb, &p.b_map, &full_bar[s], kb * BK, n0, z);
+            if (p.wz_mod == 0) tma_load_2d(sb, &p.b_map, &full_bar[s], kb * BK, n0);
+            else tma_load_3d(sb, &p.b_map, &full_bar[s], kb * BK, n0, p.wz_mod > 0 ? z % p.wz_mod : z);
           } else {
             tma_load_2d(sa, &p.a_map, &full_bar[s], kb * BK, m0);
             tma_load_2d(sb, &p.b_map, &full_bar[s], kb * BK, n0);
@@ -247,8 +250,9 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_tc_kernel(const __grid_c
       // bias tile -> shared (double-buffered by tile parity), overlapped with the wait for the accumulator.
       // The named barrier also keeps the epilogue warps within one tile of each other.
       float* sb = bias_tile + a * BN;
+      const float* bias_z = p.bias + (p.wz_mod > 0 ? (z % p.wz_mod) * p.bias_zstride : 0);
       for (int i = etid; i < BN; i += EPI_THREADS)
-        sb[i] = (p.bias != nullptr && n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
+        sb[i] = (p.bias != nullptr && n0 + i < p.N) ? __ldg(bias_z + n0 + i) : 0.f;
       asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
       mbar_wait(&tfull_bar[a], aph);
       tc_fence_after();
@@ -394,6 +398,8 @@ struct GemmDesc {
   // optional batch (z) dimension: strides in elements; batch<=1 means plain 2-D
   int batch = 1;
   int64_t sA = 0, sW = 0, sO = 0, sAux = 0;
+  int wz_mod = -1;              // see GemmParams (only read when batch > 1)
+  int bias_zstride = 0;
   int gelu_heavy = 0;           // use 8 epilogue warps
 };
 
