@@ -164,32 +164,41 @@ class SamplerWorkload:
         self.n_sub = -(-self.frames // 100)
 
     def config(self, world):
-        return dict(workload=f'{self.clips} clips x {self.seconds:g} s @ 25 fps per GPU, 3 CFG entries, {self.n_sub} windows x 500 steps, '
-                             'bf16 + FLAME decode (BASELINE configs[2])',
+        return dict(workload=f'{self.clips} clips x {self.seconds:g} s @ 25 fps per GPU: HuBERT audio encoder + style encoder + CFG sampler '
+                             f'(3 entries, {self.n_sub} windows x 500 steps, bf16) + FLAME decode (BASELINE configs[2])',
                     clips_per_gpu=self.clips, sequences=3 * self.clips, rows=3 * self.clips * 111,
                     parallelism=f'clips sharded x{world}, no collective',
-                    audio='synthetic audio FEATURES [clips, 300, 512] (CUDA audio encoder not in this step yet)',
-                    noise='externally supplied z [501, clips, 100, 67], shared by the windows',
+                    audio=f'synthetic 16 kHz audio [{self.clips}, {int(self.seconds * 16000)}] (sines + noise, normalised)',
+                    noise='externally supplied z [501, clips, 100, 67], shared by the windows; x_T, style eps supplied',
                     l2_policy='per-layer activations (qkv 65 MB + h 87 MB + ...) exceed the 126 MB L2 every layer')
 
     def setup(self, device, rank):
         from types import SimpleNamespace
-        import torch.nn as nn
+        import transformers
         from msmd_b200 import model as M
+        from msmd_b200.style_encoder import get_style_encoder
+        from msmd_b200.utils import hubert
         from msmd_b200.utils.flame import FLAME
         from oracle import synth
         from oracle.ref_shims import pinned_args
         self.args = pinned_args()
-        m = M.MSMD(self.args, 'cpu', True, use_head_alpha=False, audio_encoder=nn.Identity())
-        m.load_state_dict(synth.fill_state_dict(synth.param_spec(m), 1234), strict=False)
+        enc = hubert.HubertModel(transformers.HubertConfig())
+        m = M.MSMD(self.args, 'cpu', True, use_head_alpha=False, audio_encoder=enc)
+        m.load_state_dict(synth.fill_state_dict(synth.param_spec(m, skip=()), 1234), strict=False)
         self.model = m.to(device).eval()
+        se = get_style_encoder(self.args, 'vae2')
+        se.load_state_dict(synth.fill_state_dict(synth.param_spec(se), 77), strict=False)
+        self.style_enc = se.to(device).eval()
         raw = synth.flame_raw(0, synth.FLAME_V, 400)
         self.flame = FLAME(SimpleNamespace(n_shape=300, n_exp=100, flame_lmk_embedding_path=None), raw=raw).to(device)
         g = torch.Generator().manual_seed(1000 + rank)
-        N, tot = self.clips, self.n_sub * 100
-        self.host = dict(audio_feat=torch.randn(N, tot, 512, generator=g), style=torch.randn(N, 256, generator=g),
-                         shape=torch.zeros(N, 1, 100), x_T=torch.randn(N, 100, 67, generator=g),
-                         z=torch.randn(501, N, 100, 67, generator=g))
+        N = self.clips
+        n_samp = int(self.seconds * 16000)
+        base = rank * N                                   # global clip ids: results do not depend on the GPU count
+        audio = torch.stack([synth.clip_audio(base + i, n_samp) for i in range(N)])
+        self.host = dict(audio=audio, style_motion=torch.randn(N, 100, 67, generator=g),
+                         style_eps=torch.randn(N, 256, generator=g), shape=torch.zeros(N, 1, 100),
+                         x_T=torch.randn(N, 100, 67, generator=g), z=torch.randn(501, N, 100, 67, generator=g))
         self.host = {k: v.pin_memory() for k, v in self.host.items()}
         self.dev = {k: v.to(device) for k, v in self.host.items()}
         self.host_out = torch.empty((N, self.frames, 67)).pin_memory()
@@ -201,12 +210,17 @@ class SamplerWorkload:
 
     def launches_per_step(self):
         per_denoise = 2 + 8 * 11 + 2 + 2          # embed(2) + 8 layers x 11 kernels + motion_dec(2) + update/advance
-        return self.n_sub * (500 * per_denoise + 8 * 2 + 12) + 3
+        return self.n_sub * (500 * per_denoise + 8 * 2 + 12) + 3 + 118 + 22   # + audio encoder + style encoder
 
     def _run(self, d):
         from msmd_b200.inference import infer_coeffs_batched
         from msmd_b200.decode import decode_vertices
-        codes = infer_coeffs_batched(self.model, self.args, d['audio_feat'], d['shape'], d['style'],
+        total = self.n_sub * 100
+        audio = torch.nn.functional.pad(d['audio'], (0, total * 640 - d['audio'].shape[1]))     # inference.py:41-45
+        audio_feat = self.model.extract_audio_feature(audio, total)                            # inference.py:46
+        mu, logvar = self.style_enc._stats(d['style_motion'])
+        style = mu + d['style_eps'] * torch.exp(0.5 * logvar)                                   # style_encoder.py:209-213
+        codes = infer_coeffs_batched(self.model, self.args, audio_feat, d['shape'], style,
                                      clip_len=self.frames, cfg_scale=1.4, x_T=d['x_T'], noise=d['z'])
         verts = decode_vertices(self.flame, codes, n_exp=100)
         return codes, verts
