@@ -230,3 +230,32 @@ def sample(sd, cfg, audio_feat, shape_feat, style_feat, prev_motion=None, prev_a
     if ret_traj:
         return traj, x_T, audio_feat
     return x, x_T, audio_feat
+
+
+# ----------------------------------------------------------------------------- windowing driver
+def infer_coeffs(sd, cfg, audio_feat, shape_coef, style_feat, clip_len, x_T, z_per_window, cfg_mode=None,
+                 cfg_cond=None, cfg_scale=1.15, n_steps=None):
+    """inference.py:34-75 from the extracted audio features on (feature extraction is oracle/audio.py).
+
+    audio_feat [N, n_sub*L, d]; windows are sampled sequentially, each conditioned on the previous
+    window's last n_prev frames of motion and of INPUT audio features; every window re-uses window 0's
+    x_T (inference.py:57-69); the last window's indicator is 0 over the padded frames (:51-53) which are
+    trimmed afterwards (:71-72).  z_per_window: list of [T+1, N, L, 67] noise tensors.
+    """
+    L, Lp = cfg.n_motions, cfg.n_prev_motions
+    N, total = audio_feat.shape[:2]
+    n_sub = total // L
+    n_pad = total - clip_len
+    prev_m = prev_a = None
+    out = []
+    for i in range(n_sub):
+        ind = torch.ones(N, L)
+        if i == n_sub - 1 and n_pad > 0:
+            ind[:, -n_pad:] = 0
+        a_in = audio_feat[:, i * L:(i + 1) * L]
+        x0, _, used = sample(sd, cfg, a_in, shape_coef, style_feat, prev_m, prev_a, x_T, z_per_window[i], ind,
+                             cfg_mode, cfg_cond, cfg_scale, n_steps=n_steps)
+        prev_m = x0[:, -Lp:].clone()
+        prev_a = used[:, -Lp:]
+        out.append(x0[:, :-n_pad] if (i == n_sub - 1 and n_pad > 0) else x0)
+    return torch.cat(out, 1)

@@ -189,8 +189,45 @@ def gen_audio():
     print('audio.npz', {k: v.shape for k, v in res.items()})
 
 
+INFER_GOLD = dict(T=6, weight_seed=1234, samples=160000, clip_id=3)
+
+
+def infer_inputs():
+    """Config-1-shaped inputs: one 10 s clip -> 3 windows, the last one padded by 50 frames."""
+    c = INFER_GOLD
+    audio = synth.clip_audio(c['clip_id'], c['samples'])
+    style = synth.clip_style_eps(c['clip_id'])                    # any [1,256] vector serves as the style code here
+    x_T = synth.clip_xT(c['clip_id'])
+    z = [synth.clip_step_noise(c['clip_id'], w, c['T']).unsqueeze(1) for w in range(3)]
+    return audio, style, x_T, z
+
+
+def gen_infer():
+    """inference.infer_coeffs end to end (audio -> HuBERT -> 3 windows), T=6 diffusion steps to keep the file
+    small; noise injected: x_T through torch.randn (model.py:337), z through torch.randn_like (model.py:379)."""
+    c = INFER_GOLD
+    m = ref_shims.ref_modules()
+    infer = ref_shims.ref_infer_coeffs()
+    args = ref_shims.pinned_args(n_diff_steps=c['T'])
+    model = m.model.get_diffusion_model(args, 'cpu').eval()
+    fill = synth.fill_state_dict(synth.param_spec(model, skip=()), c['weight_seed'])
+    model.load_state_dict(fill, strict=False)
+    audio, style, x_T, z = infer_inputs()
+    zs = [z[w][t] for w in range(3) for t in range(c['T'], 1, -1)]
+    orig_randn = torch.randn
+    torch.randn = lambda *a, **k: x_T.clone()
+    try:
+        with ref_shims.inject_randn_like(zs):
+            out = infer(model, args, audio, torch.zeros(1, 1, 100), 640.0, style, cfg_scale=1.4, dynamic_threshold=None)
+    finally:
+        torch.randn = orig_randn
+    feat = model.extract_audio_feature(torch.nn.functional.pad(audio, (0, 32000)).unsqueeze(0), 300)
+    np.savez_compressed(os.path.join(OUT, 'infer.npz'), coeffs=out.numpy(), audio_feat=feat.numpy())
+    print('infer.npz', out.shape)
+
+
 SECTIONS = dict(rot=gen_rot, flame=gen_flame, denoiser=gen_denoiser, sampler=gen_sampler, style=gen_style,
-                audio=gen_audio)
+                audio=gen_audio, infer=gen_infer)
 
 
 def main(argv):
