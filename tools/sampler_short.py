@@ -7,7 +7,9 @@ clips = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 wl = SamplerWorkload(clips=clips, seconds=4.0)
 wl.setup(torch.device('cuda', 0), 0)
-d = wl.dev
+d = dict(wl.dev)
+d['audio_feat'] = torch.randn(clips, 100, 512, device='cuda', generator=torch.Generator(device='cuda').manual_seed(0))
+d['style'] = torch.randn(clips, 256, device='cuda', generator=torch.Generator(device='cuda').manual_seed(1))
 m = wl.model
 ind = torch.ones(clips, 100, device='cuda')
 for _ in range(2):

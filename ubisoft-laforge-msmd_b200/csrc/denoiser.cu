@@ -3,7 +3,7 @@
 //
 // Data layout in HBM (S sequences, T = 1+Lp+L tokens, M = S*T rows, d = 512):
 //   x     [M, d]     bf16   residual stream = A operand of every GEMM (token-major, features contiguous)
-//   y     [M, d]     fp32   pre-LayerNorm sums written by the out-proj / FF2 GEMM epilogues
+//   y     [M, d]     bf16   sub-layer outputs (out-proj / FF2 epilogues); the residual add happens in the LN kernel
 //   qkv   [M, 3d]    bf16   packed q|k|v
 //   ctx   [M, d]     bf16   attention output
 //   h     [M, d_ff]  bf16   GELU(FF1)
@@ -54,7 +54,8 @@ struct msmd_model {
   // workspaces
   bf16 *x = nullptr, *qkv = nullptr, *ctx = nullptr, *h = nullptr, *dec1 = nullptr, *mem = nullptr, *x0c = nullptr,
        *q0 = nullptr, *ctx0 = nullptr;
-  float *y = nullptr, *y0 = nullptr, *dec2 = nullptr, *pp = nullptr, *pmproj = nullptr, *stat = nullptr,
+  bf16 *y = nullptr, *y0 = nullptr;
+  float *dec2 = nullptr, *pp = nullptr, *pmproj = nullptr, *stat = nullptr,
         *hid = nullptr, *xbuf = nullptr, *mixed = nullptr;
   int* steps = nullptr;
   // window state
@@ -114,20 +115,22 @@ int run_forward(msmd_model* m, const float* xrows, cudaStream_t st) {
     // rows + norm2 for motion tokens
     if ((rc = gemm(m->x, d, w.Wqkv, d, w.bqkv, nullptr, 0, m->qkv, 3 * d, 0, M, 3 * d, d, 0, st))) return rc;
     if ((rc = self_attn_launch(m->qkv, m->ctx, S, T, c.n_heads, st))) return rc;
-    if ((rc = gemm(m->ctx, d, w.Wo, d, w.bo, m->x, d, m->y, d, 1, M, d, d, 0, st))) return rc;
+    if ((rc = gemm(m->ctx, d, w.Wo, d, w.bo, nullptr, 0, m->y, d, 0, M, d, d, 0, st))) return rc;
     LnParams lp;
+    lp.resid = m->x;
     lp.y = m->y; lp.g1 = w.g1; lp.b1 = w.be1; lp.add = w.ca; lp.g2 = w.g2; lp.b2 = w.be2; lp.out = m->x;
     lp.x0 = m->x0c; lp.M = M; lp.T = T; lp.d = d;
     if ((rc = ln_launch(lp, st))) return rc;
     // person token (row 0): real cross attention over the memory (_mha_block) + norm2
     if ((rc = gemm(m->x0c, d, w.Wq0, d, w.bq0, nullptr, 0, m->q0, d, 0, S, d, d, 0, st))) return rc;
     if ((rc = cross_attn_row0_launch(m->q0, w.kv, m->ctx0, S, T - 1, c.n_heads, st))) return rc;
-    if ((rc = gemm(m->ctx0, d, w.Wco, d, w.bco, m->x0c, d, m->y0, d, 1, S, d, d, 0, st))) return rc;
-    if ((rc = ln_row0_launch(m->y0, w.g2, w.be2, m->x, S, T, d, st))) return rc;
+    if ((rc = gemm(m->ctx0, d, w.Wco, d, w.bco, nullptr, 0, m->y0, d, 0, S, d, d, 0, st))) return rc;
+    if ((rc = ln_row0_launch(m->y0, m->x0c, w.g2, w.be2, m->x, S, T, d, st))) return rc;
     // feed-forward block (_ff_block) + norm3
     if ((rc = gemm(m->x, d, w.W1, d, w.b1, nullptr, 0, m->h, c.d_ff, 0, M, c.d_ff, d, 1, st))) return rc;
-    if ((rc = gemm(m->h, c.d_ff, w.W2, c.d_ff, w.b2, m->x, d, m->y, d, 1, M, d, c.d_ff, 0, st))) return rc;
+    if ((rc = gemm(m->h, c.d_ff, w.W2, c.d_ff, w.b2, nullptr, 0, m->y, d, 0, M, d, c.d_ff, 0, st))) return rc;
     LnParams l3;
+    l3.resid = m->x;
     l3.y = m->y; l3.g1 = w.g3; l3.b1 = w.be3; l3.add = nullptr; l3.g2 = nullptr; l3.b2 = nullptr; l3.out = m->x;
     l3.x0 = nullptr; l3.M = M; l3.T = T; l3.d = d;
     if ((rc = ln_launch(l3, st))) return rc;

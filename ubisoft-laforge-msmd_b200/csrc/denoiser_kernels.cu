@@ -200,11 +200,25 @@ __global__ void __launch_bounds__(256) ln_kernel(LnParams p) {
   if (row >= p.M) return;
   const int s = row / p.T, tok = row % p.T;
   float v[NV];
-  const float* y = p.y + (int64_t)row * D;
+  const bf16* y = p.y + (int64_t)row * D;
 #pragma unroll
   for (int i = 0; i < NV / 4; ++i) {
-    const float4 t4 = *reinterpret_cast<const float4*>(y + i * 128 + lane * 4);
-    v[4 * i] = t4.x; v[4 * i + 1] = t4.y; v[4 * i + 2] = t4.z; v[4 * i + 3] = t4.w;
+    const uint2 u = *reinterpret_cast<const uint2*>(y + i * 128 + lane * 4);
+    v[4 * i + 0] = __uint_as_float(u.x << 16);
+    v[4 * i + 1] = __uint_as_float(u.x & 0xffff0000u);
+    v[4 * i + 2] = __uint_as_float(u.y << 16);
+    v[4 * i + 3] = __uint_as_float(u.y & 0xffff0000u);
+  }
+  if (p.resid != nullptr) {  // x + sublayer(x): the residual add of the post-LN layer (model.py:874-878)
+    const bf16* r = p.resid + (int64_t)row * D;
+#pragma unroll
+    for (int i = 0; i < NV / 4; ++i) {
+      const uint2 u = *reinterpret_cast<const uint2*>(r + i * 128 + lane * 4);
+      v[4 * i + 0] += __uint_as_float(u.x << 16);
+      v[4 * i + 1] += __uint_as_float(u.x & 0xffff0000u);
+      v[4 * i + 2] += __uint_as_float(u.y << 16);
+      v[4 * i + 3] += __uint_as_float(u.y & 0xffff0000u);
+    }
   }
   ln_row<D>(v, p.g1, p.b1, lane);
   if (tok == 0 && p.x0 != nullptr) {
@@ -238,8 +252,9 @@ int ln_launch(const LnParams& p, cudaStream_t st) {
 }
 
 template <int D>
-__global__ void __launch_bounds__(256) ln_row0_kernel(const float* __restrict__ y0, const float* __restrict__ g,
-                                                      const float* __restrict__ b, bf16* __restrict__ out, int S, int T) {
+__global__ void __launch_bounds__(256) ln_row0_kernel(const bf16* __restrict__ y0, const bf16* __restrict__ resid0,
+                                                      const float* __restrict__ g, const float* __restrict__ b,
+                                                      bf16* __restrict__ out, int S, int T) {
   constexpr int NV = D / 32;
   const int lane = threadIdx.x & 31;
   const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -247,17 +262,28 @@ __global__ void __launch_bounds__(256) ln_row0_kernel(const float* __restrict__ 
   float v[NV];
 #pragma unroll
   for (int i = 0; i < NV / 4; ++i) {
-    const float4 t4 = *reinterpret_cast<const float4*>(y0 + (int64_t)s * D + i * 128 + lane * 4);
-    v[4 * i] = t4.x; v[4 * i + 1] = t4.y; v[4 * i + 2] = t4.z; v[4 * i + 3] = t4.w;
+    const uint2 uy = *reinterpret_cast<const uint2*>(y0 + (int64_t)s * D + i * 128 + lane * 4);
+    v[4 * i + 0] = __uint_as_float(uy.x << 16);
+    v[4 * i + 1] = __uint_as_float(uy.x & 0xffff0000u);
+    v[4 * i + 2] = __uint_as_float(uy.y << 16);
+    v[4 * i + 3] = __uint_as_float(uy.y & 0xffff0000u);
+    if (resid0 != nullptr) {
+      const uint2 u = *reinterpret_cast<const uint2*>(resid0 + (int64_t)s * D + i * 128 + lane * 4);
+      v[4 * i + 0] += __uint_as_float(u.x << 16);
+      v[4 * i + 1] += __uint_as_float(u.x & 0xffff0000u);
+      v[4 * i + 2] += __uint_as_float(u.y << 16);
+      v[4 * i + 3] += __uint_as_float(u.y & 0xffff0000u);
+    }
   }
   ln_row<D>(v, g, b, lane);
   bf16* o = out + (int64_t)s * T * D;
 #pragma unroll
   for (int i = 0; i < NV / 4; ++i) store_bf16x4(o + i * 128 + lane * 4, v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
 }
-int ln_row0_launch(const float* y0, const float* g, const float* b, bf16* out, int S, int T, int d, cudaStream_t st) {
+int ln_row0_launch(const bf16* y0, const bf16* resid0, const float* g, const float* b, bf16* out, int S, int T, int d,
+                   cudaStream_t st) {
   MSMD_REQUIRE(d == 512, "ln_row0: only d_model = 512 is instantiated");
-  ln_row0_kernel<512><<<cdiv(S, 8), 256, 0, st>>>(y0, g, b, out, S, T);
+  ln_row0_kernel<512><<<cdiv(S, 8), 256, 0, st>>>(y0, resid0, g, b, out, S, T);
   MSMD_CHECK_LAUNCH();
   return MSMD_OK;
 }

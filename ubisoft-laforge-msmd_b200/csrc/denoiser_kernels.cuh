@@ -37,7 +37,8 @@ int embed_launch(const EmbedParams& p, cudaStream_t st);
 // y [M,512] fp32 -> LayerNorm(g1,b1); rows with (token != 0): + add[(seq, token-1)] then LayerNorm(g2,b2) (optional)
 // -> out bf16 [M,512]; token-0 rows: LN1 only, written to x0 [S,512] (and NOT to out) when x0 != null.
 struct LnParams {
-  const float* y;           // [M, d]
+  const bf16* y;            // [M, d] sub-layer output (GEMM epilogue writes bf16)
+  const bf16* resid;        // [M, d] residual stream added to y before the first LayerNorm (may alias out), or null
   const float* g1; const float* b1;
   const bf16* add;          // [S, T-1, d] or null
   const float* g2; const float* b2;   // used iff add != null
@@ -47,7 +48,8 @@ struct LnParams {
 };
 int ln_launch(const LnParams& p, cudaStream_t st);
 // row-0 finish: LayerNorm(y0 [S,d]; g,b) -> out[s*T + 0]
-int ln_row0_launch(const float* y0, const float* g, const float* b, bf16* out, int S, int T, int d, cudaStream_t st);
+int ln_row0_launch(const bf16* y0, const bf16* resid0, const float* g, const float* b, bf16* out, int S, int T, int d,
+                   cudaStream_t st);
 
 // self-attention over T <= 112 tokens, head dim 64: qkv [S*T, 3*d] bf16 (q|k|v) -> ctx [S*T, d] bf16
 int self_attn_launch(const bf16* qkv, bf16* ctx, int S, int T, int H, cudaStream_t st);
