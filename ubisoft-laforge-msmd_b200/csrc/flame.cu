@@ -381,11 +381,8 @@ extern "C" int msmd_flame_decode(msmd_flame* fh, const float* betas, const float
                                                   impl == 0 ? fh->A_lo : nullptr, fh->xf, joints_out);
   MSMD_CHECK_LAUNCH();
   MSMD_REQUIRE(impl == 0 || impl == 1, "msmd_flame_decode: unknown impl %d", impl);
-  if (impl == 0) {
-    rc = flame_decode_tc(fh, B, verts_out, st);
-    if (rc != MSMD_ERR_UNSUPPORTED) return rc;  // TEMPORARY until flame_tc.cu lands: run the CUDA-core kernel
-  }
-  ProfileScope prof("flame_fused", st);
+  if (impl == 0) return flame_decode_tc(fh, B, verts_out, st);
+  ProfileScope prof("flame_simt", st);
   dim3 grid(cdiv(fh->N3, FBN), cdiv(B, FBM));
   flame_simt_kernel<5><<<grid, 256, 0, st>>>(fh->A, fh->basis, fh->v_template, fh->weights, fh->xf, B, fh->V,
                                             fh->Kpad, verts_out);
