@@ -84,7 +84,7 @@ def test_gemm_bf16_gelu(built_lib, M, N, K):
     assert err < 6e-3, err
     got = run_linear(0, x, w, b, None, 1, True)
     err = ((got.double() - want).abs() / (want.abs() + 1.0)).max().item()
-    assert err < 1e-4, err
+    assert err < 4e-4, err          # tanh-form GELU (fit 2.5e-5) + tanh.approx (2^-11 relative)
 
 
 @pytest.mark.parametrize('M,N,K', [(333, 512, 512), (2664, 512, 2048), (64, 512, 512), (2000, 768, 768)])

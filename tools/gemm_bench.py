@@ -38,6 +38,9 @@ def bench(M, N, K, aux=False, act=0, out_f32=False, mode=0, reps=20):
 
 if __name__ == '__main__':
     M = 21312
+    bench(M, 512, 512)
+    bench(M, 512, 2048)
+    bench(M, 768, 3072)
     bench(M, 1536, 512)
     bench(M, 512, 512, aux=True, out_f32=True)
     bench(M, 2048, 512, act=1)

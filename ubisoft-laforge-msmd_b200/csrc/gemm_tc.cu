@@ -3,6 +3,7 @@
 #include "profile.cuh"
 #include <cudaTypedefs.h>
 #include <mutex>
+#include <cstdlib>
 
 namespace msmd {
 
@@ -79,7 +80,7 @@ static int launch_cfg2(const GemmDesc& d, cudaStream_t st) {
   if ((rc = make_tmap_23(&p.a_map, d.A, in_dt, esz, d.K, d.M, d.lda, d.batch, d.sA, Cfg::BK, Cfg::BM))) return rc;
   {
     const int wb = (d.batch > 1 && d.wz_mod != 0) ? (d.wz_mod > 0 ? d.wz_mod : d.batch) : 1;
-    if ((rc = make_tmap_23(&p.b_map, d.W, in_dt, esz, d.K, d.N, d.ldw, wb, d.sW, Cfg::BK, Cfg::BN))) return rc;
+    if ((rc = make_tmap_23(&p.b_map, d.W, in_dt, esz, d.K, d.N, d.ldw, wb, d.sW, Cfg::BK, Cfg::B_ROWS))) return rc;
   }
   if (MODE == 1) {
     MSMD_REQUIRE(d.A_lo && d.W_lo, "gemm: tf32x3 mode needs the lo operands");
@@ -104,7 +105,7 @@ static int launch_cfg2(const GemmDesc& d, cudaStream_t st) {
   p.batch = d.batch < 1 ? 1 : d.batch;
   p.wz_mod = d.wz_mod;
   p.bias_zstride = d.bias_zstride;
-  p.tiles_m = cdiv(d.M, Cfg::BM);
+  p.tiles_m = cdiv(d.M, Cfg::CTA2 ? 2 * Cfg::BM : Cfg::BM);
   p.tiles_n = cdiv(d.N, Cfg::BN);
   const int tiles = p.tiles_m * p.tiles_n * p.batch;
   auto kern = gemm_tc_kernel<Cfg, MODE, GELU>;
@@ -113,9 +114,24 @@ static int launch_cfg2(const GemmDesc& d, cudaStream_t st) {
     MSMD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  const int grid = tiles < kNumSMs ? tiles : kNumSMs;
   ProfileScope prof(MODE == 0 ? "gemm_bf16" : "gemm_tf32x3", st);
-  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(p);
+  if constexpr (Cfg::CTA2) {
+    const int pairs = tiles < kNumSMs / 2 ? tiles : kNumSMs / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(Cfg::THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    MSMD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
+  } else {
+    const int grid = tiles < kNumSMs ? tiles : kNumSMs;
+    kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(p);
+  }
   MSMD_CHECK_LAUNCH();
   return MSMD_OK;
 }
@@ -133,6 +149,15 @@ int gemm_tc_launch(const GemmDesc& d, cudaStream_t st) {
   if (d.mode == 0) {
     // narrow outputs (N <= 128) use the 128-wide tile so small problems still spread over SMs
     const bool narrow = d.N <= 128;
+    static const bool cta2_env = [] { const char* e = getenv("MSMD_GEMM_CTA2"); return !e || atoi(e) != 0; }();
+    // measured on B200 (tools/gemm_bench.py): the pair wins when the main loop dominates (K >= 1024: +11% at
+    // N=512,K=2048, 93% of cuBLAS at 768x3072) and loses ~12% at K=512 where the per-tile epilogue dominates
+    const bool pair = d.cta2 == 1 || (d.cta2 < 0 && cta2_env && !aux && !d.out_f32 && d.batch <= 1 && d.N >= 256 &&
+                                      d.M >= 2048 && d.K >= 1024);
+    if (pair) {
+      if (d.gelu_heavy) return launch_cfg<GemmCfg<0, 256, 8, false, bf, bf, true>, 0>(d, st);
+      return launch_cfg<GemmCfg<0, 256, 4, false, bf, bf, true>, 0>(d, st);
+    }
     if (!aux) {
       if (d.out_f32) {
         return narrow ? launch_cfg<GemmCfg<0, 128, 4, false, float, float>, 0>(d, st)

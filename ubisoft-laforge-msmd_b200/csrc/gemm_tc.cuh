@@ -30,8 +30,12 @@ struct GemmParams {
   int tiles_m, tiles_n;
 };
 
-template <int MODE, int BN_, int EPI_WARPS_, bool HAS_AUX_, typename OutT_, typename AuxT_>
+template <int MODE, int BN_, int EPI_WARPS_, bool HAS_AUX_, typename OutT_, typename AuxT_, bool CTA2_ = false>
 struct GemmCfg {
+  // CTA2: the tile is 256 x BN on a CTA PAIR (cta_group::2): each CTA holds its 128 rows of A and HALF of the
+  // W tile, the leader issues M=256 MMAs that read both shared memories -> 2/3 of the operand bytes per FLOP
+  // and 32 KB stages (6 deep) instead of 48 KB (4 deep).
+  static constexpr bool CTA2 = CTA2_;
   using OutT = OutT_;
   using AuxT = AuxT_;
   static constexpr int BN = BN_, EPI_WARPS = EPI_WARPS_;
@@ -40,7 +44,9 @@ struct GemmCfg {
   static constexpr int ELT = MODE == 0 ? 2 : 4;
   static constexpr int BK = 128 / ELT;  // one 128-byte swizzle atom of K per stage
   static constexpr int UK = 32 / ELT;   // K per tcgen05.mma (32 bytes)
-  static constexpr int A_BYTES = BM * 128, B_BYTES = BN * 128;
+  static constexpr int B_ROWS = CTA2 ? BN / 2 : BN;     // W rows this CTA stages per k-block
+  static constexpr int A_BYTES = BM * 128, B_BYTES = B_ROWS * 128;
+  static constexpr int UMMA_M = CTA2 ? 256 : 128;
   static constexpr int NSPLIT = MODE == 0 ? 1 : 2;
   static constexpr int STAGE_BYTES = NSPLIT * (A_BYTES + B_BYTES);
   static constexpr int OUT_COLS = 128 / (int)sizeof(OutT);
@@ -66,6 +72,7 @@ struct GemmCfg {
   static_assert(COLS_PER_WARP % 64 == 0, "the epilogue processes 32-column chunks in pairs");
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
   static_assert(STAGES >= 2, "not enough shared memory for a pipeline");
+  static_assert(!CTA2 || (MODE == 0 && !HAS_AUX && BN % 32 == 0), "CTA-pair variant: bf16, no aux");
 };
 
 // erf by Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7): enough for a bf16-rounded GELU, 3x cheaper than erff
@@ -79,9 +86,23 @@ __device__ __forceinline__ float erf_fast(float x) {
   const float r = 1.0f - p * t * __expf(-ax * ax);
   return copysignf(r, x);
 }
+// exact-erf GELU through the identity Phi(x) = 0.5 (1 + tanh(atanh(erf(x/sqrt2)))): the odd function
+// atanh(erf(x/sqrt2)) is fitted by x (a + b x^2 + c x^4) on |x| <= 8 (max |GELU error| 2.5e-5, fitted in
+// tools/, 150x below the bf16 rounding of the output), so one MUFU.TANH replaces erf's RCP + EX2:
+// 9 instructions per element instead of ~25 - the bf16 GELU epilogue must stay below the 4096-cycle MMA time
+// of a 128x256x512 tile.
+__device__ __forceinline__ float gelu_tanh3(float x) {
+  const float xc = fminf(fmaxf(x, -8.0f), 8.0f);
+  const float x2 = xc * xc;
+  const float u = xc * fmaf(x2, fmaf(x2, -0.000351516788570472f, 0.037005646019657945f), 0.7975078842869763f);
+  float th;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(u));
+  const float hx = 0.5f * x;
+  return fmaf(hx, th, hx);
+}
 template <int MODE>
 __device__ __forceinline__ float gelu_erf(float x) {
-  if constexpr (MODE == 0) return 0.5f * x * (1.0f + erf_fast(x * 0.70710678118654752f));
+  if constexpr (MODE == 0) return gelu_tanh3(x);
   else return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
 }
 
@@ -107,6 +128,9 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_tc_kernel(const __grid_c
   if (threadIdx.x == 0 && reinterpret_cast<uint8_t*>(bias_tile) + 2 * 256 * 4 > smem_raw + Cfg::SMEM_BYTES) __trap();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cta_rank = Cfg::CTA2 ? (int)cluster_ctarank() : 0;
+  const int tile0 = Cfg::CTA2 ? (int)blockIdx.x / 2 : (int)blockIdx.x;       // first tile of this CTA (pair)
+  const int tstride = Cfg::CTA2 ? (int)gridDim.x / 2 : (int)gridDim.x;
   const int num_tiles = p.tiles_m * p.tiles_n * p.batch;
   const int num_kb = (p.K + BK - 1) / BK;
 
@@ -117,13 +141,17 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_tc_kernel(const __grid_c
     if (MODE == 1) { prefetch_tmap(&p.a_lo_map); prefetch_tmap(&p.b_lo_map); }
     if (Cfg::HAS_AUX) prefetch_tmap(&p.aux_map);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], Cfg::EPI_WARPS); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], Cfg::EPI_WARPS * (Cfg::CTA2 ? 2 : 1)); }
     for (int i = 0; i < 2 * Cfg::EPI_WARPS; ++i) mbar_init(&aux_bar[i], 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  if (warp == 1) {
+    if constexpr (Cfg::CTA2) tmem_alloc_2sm(tmem_slot, Cfg::TMEM_COLS);
+    else tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (Cfg::CTA2) cluster_sync();  // the peer's barriers are initialised before anyone signals them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -131,7 +159,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_tc_kernel(const __grid_c
     const int per_z = p.tiles_m * p.tiles_n;
     z = t / per_z;
     const int r = t - z * per_z;
-    m0 = (r / p.tiles_n) * BM;
+    m0 = (r / p.tiles_n) * (Cfg::CTA2 ? 2 * BM : BM) + cta_rank * BM;
     n0 = (r % p.tiles_n) * BN;
   };
 
@@ -139,7 +167,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_tc_kernel(const __grid_c
     // ------------------------------------------------ TMA producer (lane 0 issues; the warp stays converged)
     int s = 0;
     uint32_t ph = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    for (int t = tile0; t < num_tiles; t += tstride) {
       int m0, n0, z;
       tile_coords(t, m0, n0, z);
       for (int kb = 0; kb < num_kb; ++kb) {
@@ -147,12 +175,17 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_tc_kernel(const __grid_c
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* sa = stage_base + s * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::NSPLIT * Cfg::A_BYTES;
-          mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
-          if (p.batch > 1) {
+          if constexpr (Cfg::CTA2) {
+            if (cta_rank == 0) mbar_expect_tx(&full_bar[s], 2 * Cfg::STAGE_BYTES);  // both CTAs' boxes land here
+            tma_load_2d_2sm(sa, &p.a_map, &full_bar[s], kb * BK, m0);
+            tma_load_2d_2sm(sb, &p.b_map, &full_bar[s], kb * BK, n0 + cta_rank * Cfg::B_ROWS);
+          } else if (p.batch > 1) {
+            mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
             tma_load_3d(sa, &p.a_map, &full_bar[s], kb * BK, m0, z);
             if (p.wz_mod == 0) tma_load_2d(sb, &p.b_map, &full_bar[s], kb * BK, n0);
             else tma_load_3d(sb, &p.b_map, &full_bar[s], kb * BK, n0, p.wz_mod > 0 ? z % p.wz_mod : z);
           } else {
+            mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
             tma_load_2d(sa, &p.a_map, &full_bar[s], kb * BK, m0);
             tma_load_2d(sb, &p.b_map, &full_bar[s], kb * BK, n0);
             if (MODE == 1) {
@@ -167,11 +200,11 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_tc_kernel(const __grid_c
     }
   } else if (warp == 1) {
     // ------------------------------------------------ MMA issuer (lane 0 issues for the whole CTA)
-    constexpr uint32_t idesc = make_idesc(MODE == 0 ? 1 : 2, BM, BN);
+    constexpr uint32_t idesc = make_idesc(MODE == 0 ? 1 : 2, Cfg::UMMA_M, BN);
     int s = 0;
     uint32_t ph = 0;
     int it = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+    for (int t = (Cfg::CTA2 && cta_rank != 0) ? num_tiles : tile0; t < num_tiles; t += tstride, ++it) {  // leader only
       const int a = it & 1;
       const uint32_t aph = (it >> 1) & 1;
       const uint32_t d_tmem = tmem_base + a * Cfg::ACC_COLS;
@@ -190,7 +223,9 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_tc_kernel(const __grid_c
 #pragma unroll
           for (int k = 0; k < BK / Cfg::UK; ++k) {
             const uint32_t acc = (kb | k) != 0;
-            if constexpr (MODE == 0) {
+            if constexpr (Cfg::CTA2) {
+              umma_2sm(d_tmem, desc_advance(da, k * 32), desc_advance(db, k * 32), idesc, acc);
+            } else if constexpr (MODE == 0) {
               umma<0>(d_tmem, desc_advance(da, k * 32), desc_advance(db, k * 32), idesc, acc);
             } else {
               const uint64_t dal = make_smem_desc_sw128(sa + Cfg::A_BYTES), dbl = make_smem_desc_sw128(sb + Cfg::B_BYTES);
@@ -199,12 +234,16 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_tc_kernel(const __grid_c
               umma<1>(d_tmem, desc_advance(da, k * 32), desc_advance(db, k * 32), idesc, acc);        // hi * hi
             }
           }
-          umma_commit(&empty_bar[s]);  // smem slot reusable once these MMAs have read it
+          if constexpr (Cfg::CTA2) umma_commit_2sm(&empty_bar[s]);
+          else umma_commit(&empty_bar[s]);  // smem slot reusable once these MMAs have read it
         }
         __syncwarp();
         if (++s == STAGES) { s = 0; ph ^= 1; }
       }
-      if (lane == 0) umma_commit(&tfull_bar[a]);  // accumulator complete -> epilogue
+      if (lane == 0) {  // accumulator complete -> epilogue (of both CTAs in pair mode)
+        if constexpr (Cfg::CTA2) umma_commit_2sm(&tfull_bar[a]);
+        else umma_commit(&tfull_bar[a]);
+      }
       __syncwarp();
     }
   } else {
@@ -225,7 +264,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_tc_kernel(const __grid_c
     auto issue_aux = [&](int f) {  // flat aux-chunk index over this CTA's tiles
       if constexpr (Cfg::HAS_AUX) {
         const int lt = f / AUX_PER_TILE, ck = f % AUX_PER_TILE;
-        const int t = blockIdx.x + lt * gridDim.x;
+        const int t = tile0 + lt * tstride;
         if (t < num_tiles && lane == 0) {
           int m0, n0, z;
           tile_coords(t, m0, n0, z);
@@ -242,7 +281,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_tc_kernel(const __grid_c
     issue_aux(0);
 
     int it = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+    for (int t = tile0; t < num_tiles; t += tstride, ++it) {
       int m0, n0, z;
       tile_coords(t, m0, n0, z);
       const int a = it & 1;
@@ -367,16 +406,21 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_tc_kernel(const __grid_c
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[a]);
+      if (lane == 0) {
+        if (Cfg::CTA2 && cta_rank != 0) mbar_arrive_cluster(&tempty_bar[a], 0);  // the leader's MMA warp waits for both
+        else mbar_arrive(&tempty_bar[a]);
+      }
     }
     if (lane == 0) tma_store_wait<0>();
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (Cfg::CTA2) cluster_sync();  // the peer may still be reading this CTA's smem / signalling its barriers
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if constexpr (Cfg::CTA2) tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
+    else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
@@ -401,6 +445,7 @@ struct GemmDesc {
   int wz_mod = -1;              // see GemmParams (only read when batch > 1)
   int bias_zstride = 0;
   int gelu_heavy = 0;           // use 8 epilogue warps
+  int cta2 = -1;                // CTA-pair tiles: -1 auto (large bf16 GEMMs without aux), 0 off, 1 force
 };
 
 int gemm_tc_launch(const GemmDesc& d, cudaStream_t st);
