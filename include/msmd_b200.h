@@ -44,6 +44,8 @@ const char* msmd_version(void);
 int msmd_profile_enable(int on);
 int msmd_profile_reset(void);
 int msmd_profile_query(const char* name, double* total_ms, int64_t* launches);
+/* All classes as text lines "name total_ms launches" (NUL-terminated, truncated to cap). */
+int msmd_profile_dump(char* buf, int64_t cap);
 
 /* ------------------------------------------------------------------------- *
  * Rotation conversions — utils/rotation_conversions.py:38-569

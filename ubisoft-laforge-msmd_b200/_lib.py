@@ -20,6 +20,7 @@ SIGNATURES = {
     'msmd_profile_enable': (_i, [_i]),
     'msmd_profile_reset': (_i, []),
     'msmd_profile_query': (_i, [C.c_char_p, C.POINTER(C.c_double), C.POINTER(_i64)]),
+    'msmd_profile_dump': (_i, [C.c_char_p, _i64]),
     'msmd_rot_convert': (_i, [_i, _vp, _vp, _i64, _i, _vp]),
     'msmd_quat_binary': (_i, [_i, _vp, _vp, _vp, _i64, _vp]),
     'msmd_linear': (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i64, _i64, _i64, _i, _i, _i, _vp]),
@@ -104,3 +105,14 @@ def profile_query(name):
     ms, n = C.c_double(0), C.c_int64(0)
     check(lib().msmd_profile_query(name.encode(), C.byref(ms), C.byref(n)))
     return ms.value, n.value
+
+
+def profile_dump():
+    """{kernel class: (total_ms, launches)} since the last reset."""
+    buf = C.create_string_buffer(1 << 16)
+    check(lib().msmd_profile_dump(buf, len(buf)))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, ms, n = line.rsplit(' ', 2)
+        out[name] = (float(ms), int(n))
+    return out

@@ -152,6 +152,7 @@ __global__ void __launch_bounds__(256) embed_x_kernel(EmbedParams p) {
   }
 }
 int embed_launch(const EmbedParams& p, cudaStream_t st) {
+  ProfileScope prof("embed", st);
   embed_ctx_kernel<<<p.S * (p.Lp + 1), 128, 0, st>>>(p);
   MSMD_CHECK_LAUNCH();
   const int blocks = p.NX * ((p.L + kEmbedRows - 1) / kEmbedRows);
@@ -246,6 +247,7 @@ __global__ void __launch_bounds__(256) ln_kernel(LnParams p) {
 }
 int ln_launch(const LnParams& p, cudaStream_t st) {
   MSMD_REQUIRE(p.d == 512, "ln: only d_model = 512 is instantiated (got %d)", p.d);
+  ProfileScope prof(p.add ? "ln1_ln2" : "ln3", st);
   ln_kernel<512><<<cdiv(p.M, 8), 256, 0, st>>>(p);
   MSMD_CHECK_LAUNCH();
   return MSMD_OK;
@@ -283,6 +285,7 @@ __global__ void __launch_bounds__(256) ln_row0_kernel(const bf16* __restrict__ y
 int ln_row0_launch(const bf16* y0, const bf16* resid0, const float* g, const float* b, bf16* out, int S, int T, int d,
                    cudaStream_t st) {
   MSMD_REQUIRE(d == 512, "ln_row0: only d_model = 512 is instantiated");
+  ProfileScope prof("ln_row0", st);
   ln_row0_kernel<512><<<cdiv(S, 8), 256, 0, st>>>(y0, resid0, g, b, out, S, T);
   MSMD_CHECK_LAUNCH();
   return MSMD_OK;
@@ -299,115 +302,146 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
 }
 
 constexpr int kAttT = 112, kAttDh = 64, kQKStride = 72;
+constexpr int kAttBuf = 3 * kAttT * kQKStride;   // bf16 elements of one (Q,K,V) buffer
 
-__global__ void __launch_bounds__(224, 3) self_attn_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ ctx, int T,
-                                                        int H) {
-  __shared__ __align__(16) bf16 sQ[kAttT * kQKStride];
-  __shared__ __align__(16) bf16 sK[kAttT * kQKStride];
-  __shared__ __align__(16) bf16 sV[kAttT * kQKStride];
-  const int h = blockIdx.x, s = blockIdx.y;
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem)
+               : "memory");
+}
+
+// One CTA per sequence, looping over its heads: the (Q,K,V) tile of head h+1 streams into the second
+// shared-memory buffer with cp.async while head h is computed, so loads and MMAs overlap and every SM keeps
+// ~2 x 42 KB of loads in flight.
+constexpr int kAttHeadsPerCta = 4;   // 2*S*H/4 CTAs: enough CTAs to balance 148 SMs, enough heads to overlap loads
+__global__ void __launch_bounds__(224, 2) self_attn_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ ctx, int T,
+                                                           int H) {
+  extern __shared__ __align__(16) bf16 att_smem[];
+  const int s = blockIdx.x;
   const int d = H * kAttDh;
   const int tid = threadIdx.x;
-  const bf16* base = qkv + (int64_t)s * T * 3 * d + h * kAttDh;
-  for (int idx = tid; idx < kAttT * 8; idx += blockDim.x) {
-    const int row = idx >> 3, ch = idx & 7;
-    uint4 q = make_uint4(0, 0, 0, 0), k = q, v = q;
-    if (row < T) {
-      const bf16* r = base + (int64_t)row * 3 * d + ch * 8;
-      q = *reinterpret_cast<const uint4*>(r);
-      k = *reinterpret_cast<const uint4*>(r + d);
-      v = *reinterpret_cast<const uint4*>(r + 2 * d);
-    }
-    *reinterpret_cast<uint4*>(&sQ[row * kQKStride + ch * 8]) = q;
-    *reinterpret_cast<uint4*>(&sK[row * kQKStride + ch * 8]) = k;
-    *reinterpret_cast<uint4*>(&sV[row * kQKStride + ch * 8]) = v;
-  }
+  const bf16* base = qkv + (int64_t)s * T * 3 * d;
+  // rows >= T stay zero in both buffers (the loads below never touch them)
+  for (int i = tid; i < 2 * kAttBuf / 8; i += blockDim.x) reinterpret_cast<uint4*>(att_smem)[i] = make_uint4(0, 0, 0, 0);
   __syncthreads();
+  auto issue = [&](int h) {
+    bf16* buf = att_smem + (h & 1) * kAttBuf;
+    for (int idx = tid; idx < T * 8; idx += blockDim.x) {
+      const int row = idx >> 3, ch = idx & 7;
+      const bf16* src = base + (int64_t)row * 3 * d + h * kAttDh + ch * 8;
+      bf16* dst = buf + row * kQKStride + ch * 8;
+      cp_async16(dst, src);                                    // q
+      cp_async16(dst + kAttT * kQKStride, src + d);            // k
+      cp_async16(dst + 2 * kAttT * kQKStride, src + 2 * d);    // v
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  const int h_begin = blockIdx.y * kAttHeadsPerCta, h_end = min(H, h_begin + kAttHeadsPerCta);
+  issue(h_begin);
 
   const int warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
   const int r0 = warp * 16;
-  uint32_t aq[4][4];
-#pragma unroll
-  for (int ks = 0; ks < 4; ++ks) {
-    aq[ks][0] = *reinterpret_cast<const uint32_t*>(&sQ[(r0 + g) * kQKStride + ks * 16 + 2 * t]);
-    aq[ks][1] = *reinterpret_cast<const uint32_t*>(&sQ[(r0 + g + 8) * kQKStride + ks * 16 + 2 * t]);
-    aq[ks][2] = *reinterpret_cast<const uint32_t*>(&sQ[(r0 + g) * kQKStride + ks * 16 + 8 + 2 * t]);
-    aq[ks][3] = *reinterpret_cast<const uint32_t*>(&sQ[(r0 + g + 8) * kQKStride + ks * 16 + 8 + 2 * t]);
-  }
-  float sc[14][4];
-#pragma unroll
-  for (int j = 0; j < 14; ++j) {
-    sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f;
+  for (int h = h_begin; h < h_end; ++h) {
+    if (h + 1 < h_end) {
+      issue(h + 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const bf16* sQ = att_smem + (h & 1) * kAttBuf;
+    const bf16* sK = sQ + kAttT * kQKStride;
+    const bf16* sV = sK + kAttT * kQKStride;
+
+    uint32_t aq[4][4];
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
-      const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&sK[(j * 8 + g) * kQKStride + ks * 16 + 2 * t]);
-      const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&sK[(j * 8 + g) * kQKStride + ks * 16 + 8 + 2 * t]);
-      mma_bf16_16816(sc[j], aq[ks], b0, b1);
+      aq[ks][0] = *reinterpret_cast<const uint32_t*>(&sQ[(r0 + g) * kQKStride + ks * 16 + 2 * t]);
+      aq[ks][1] = *reinterpret_cast<const uint32_t*>(&sQ[(r0 + g + 8) * kQKStride + ks * 16 + 2 * t]);
+      aq[ks][2] = *reinterpret_cast<const uint32_t*>(&sQ[(r0 + g) * kQKStride + ks * 16 + 8 + 2 * t]);
+      aq[ks][3] = *reinterpret_cast<const uint32_t*>(&sQ[(r0 + g + 8) * kQKStride + ks * 16 + 8 + 2 * t]);
     }
-  }
-  // softmax over keys (columns): thread holds cols j*8+2t, +1 of rows g (regs 0,1) and g+8 (regs 2,3)
-  const float kScale = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
-  float m0 = -INFINITY, m1 = -INFINITY;
+    float sc[14][4];
 #pragma unroll
-  for (int j = 0; j < 14; ++j) {
-    const int c = j * 8 + 2 * t;
-    if (c >= T) { sc[j][0] = -INFINITY; sc[j][2] = -INFINITY; }
-    if (c + 1 >= T) { sc[j][1] = -INFINITY; sc[j][3] = -INFINITY; }
-    m0 = fmaxf(m0, fmaxf(sc[j][0], sc[j][1]));
-    m1 = fmaxf(m1, fmaxf(sc[j][2], sc[j][3]));
-  }
-  m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
-  m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
-  float l0 = 0.f, l1 = 0.f;
+    for (int j = 0; j < 14; ++j) {
+      sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f;
 #pragma unroll
-  for (int j = 0; j < 14; ++j) {
-    sc[j][0] = exp2f((sc[j][0] - m0) * kScale); sc[j][1] = exp2f((sc[j][1] - m0) * kScale);
-    sc[j][2] = exp2f((sc[j][2] - m1) * kScale); sc[j][3] = exp2f((sc[j][3] - m1) * kScale);
-    l0 += sc[j][0] + sc[j][1];
-    l1 += sc[j][2] + sc[j][3];
-  }
-  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+      for (int ks = 0; ks < 4; ++ks) {
+        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&sK[(j * 8 + g) * kQKStride + ks * 16 + 2 * t]);
+        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&sK[(j * 8 + g) * kQKStride + ks * 16 + 8 + 2 * t]);
+        mma_bf16_16816(sc[j], aq[ks], b0, b1);
+      }
+    }
+    // softmax over keys (columns): thread holds cols j*8+2t, +1 of rows g (regs 0,1) and g+8 (regs 2,3)
+    const float kScale = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
+    float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 14; ++j) {
+      const int c = j * 8 + 2 * t;
+      if (c >= T) { sc[j][0] = -INFINITY; sc[j][2] = -INFINITY; }
+      if (c + 1 >= T) { sc[j][1] = -INFINITY; sc[j][3] = -INFINITY; }
+      m0 = fmaxf(m0, fmaxf(sc[j][0], sc[j][1]));
+      m1 = fmaxf(m1, fmaxf(sc[j][2], sc[j][3]));
+    }
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+    float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 14; ++j) {
+      sc[j][0] = exp2f((sc[j][0] - m0) * kScale); sc[j][1] = exp2f((sc[j][1] - m0) * kScale);
+      sc[j][2] = exp2f((sc[j][2] - m1) * kScale); sc[j][3] = exp2f((sc[j][3] - m1) * kScale);
+      l0 += sc[j][0] + sc[j][1];
+      l1 += sc[j][2] + sc[j][3];
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
 
-  float o[8][4];
+    float o[8][4];
 #pragma unroll
-  for (int n = 0; n < 8; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+    for (int n = 0; n < 8; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
 #pragma unroll
-  for (int kb = 0; kb < 7; ++kb) {
-    uint32_t ap[4];
-    ap[0] = pack_bf16(sc[2 * kb][0], sc[2 * kb][1]);
-    ap[1] = pack_bf16(sc[2 * kb][2], sc[2 * kb][3]);
-    ap[2] = pack_bf16(sc[2 * kb + 1][0], sc[2 * kb + 1][1]);
-    ap[3] = pack_bf16(sc[2 * kb + 1][2], sc[2 * kb + 1][3]);
-    // V is [key][dh] row-major: ldmatrix.trans hands out the (k = key, n = dh) B fragments, two dh tiles per x4
+    for (int kb = 0; kb < 7; ++kb) {
+      uint32_t ap[4];
+      ap[0] = pack_bf16(sc[2 * kb][0], sc[2 * kb][1]);
+      ap[1] = pack_bf16(sc[2 * kb][2], sc[2 * kb][3]);
+      ap[2] = pack_bf16(sc[2 * kb + 1][0], sc[2 * kb + 1][1]);
+      ap[3] = pack_bf16(sc[2 * kb + 1][2], sc[2 * kb + 1][3]);
+      // V is [key][dh] row-major: ldmatrix.trans hands out the (k = key, n = dh) B fragments, two dh tiles per x4
 #pragma unroll
-    for (int n2 = 0; n2 < 4; ++n2) {
-      const int mrow = kb * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;   // matrices 0/1: keys 0-7 / 8-15 of dh tile 2*n2
-      const int mcol = (2 * n2 + (lane >> 4)) * 8;                     // matrices 2/3: same keys, dh tile 2*n2+1
-      uint32_t b0, b1, b2, b3;
-      const uint32_t addr = (uint32_t)__cvta_generic_to_shared(&sV[mrow * kQKStride + mcol]);
-      asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
-                   : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3) : "r"(addr));
-      mma_bf16_16816(o[2 * n2], ap, b0, b1);
-      mma_bf16_16816(o[2 * n2 + 1], ap, b2, b3);
+      for (int n2 = 0; n2 < 4; ++n2) {
+        const int mrow = kb * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+        const int mcol = (2 * n2 + (lane >> 4)) * 8;
+        uint32_t b0, b1, b2, b3;
+        const uint32_t addr = (uint32_t)__cvta_generic_to_shared(&sV[mrow * kQKStride + mcol]);
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3) : "r"(addr));
+        mma_bf16_16816(o[2 * n2], ap, b0, b1);
+        mma_bf16_16816(o[2 * n2 + 1], ap, b2, b3);
+      }
     }
-  }
-  const float i0 = 1.0f / l0, i1 = 1.0f / l1;
-  const int row_a = r0 + g, row_b = r0 + g + 8;
+    const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+    const int row_a = r0 + g, row_b = r0 + g + 8;
 #pragma unroll
-  for (int n = 0; n < 8; ++n) {
-    const int col = h * kAttDh + n * 8 + 2 * t;
-    if (row_a < T)
-      *reinterpret_cast<uint32_t*>(ctx + ((int64_t)s * T + row_a) * d + col) = pack_bf16(o[n][0] * i0, o[n][1] * i0);
-    if (row_b < T)
-      *reinterpret_cast<uint32_t*>(ctx + ((int64_t)s * T + row_b) * d + col) = pack_bf16(o[n][2] * i1, o[n][3] * i1);
+    for (int n = 0; n < 8; ++n) {
+      const int col = h * kAttDh + n * 8 + 2 * t;
+      if (row_a < T)
+        *reinterpret_cast<uint32_t*>(ctx + ((int64_t)s * T + row_a) * d + col) = pack_bf16(o[n][0] * i0, o[n][1] * i0);
+      if (row_b < T)
+        *reinterpret_cast<uint32_t*>(ctx + ((int64_t)s * T + row_b) * d + col) = pack_bf16(o[n][2] * i1, o[n][3] * i1);
+    }
+    __syncthreads();   // every warp is done with this buffer before head h+2 streams into it
   }
 }
 int self_attn_launch(const bf16* qkv, bf16* ctx, int S, int T, int H, cudaStream_t st) {
   MSMD_REQUIRE(T <= kAttT, "self_attn: sequence length %d exceeds the %d-token tile", T, kAttT);
+  constexpr int smem = 2 * kAttBuf * (int)sizeof(bf16);
+  static bool attr = false;
+  if (!attr) {
+    MSMD_CHECK_CUDA(cudaFuncSetAttribute(self_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr = true;
+  }
   ProfileScope prof("self_attn", st);
-  self_attn_kernel<<<dim3(H, S), 224, 0, st>>>(qkv, ctx, T, H);
+  self_attn_kernel<<<dim3(S, cdiv(H, kAttHeadsPerCta)), 224, smem, st>>>(qkv, ctx, T, H);
   MSMD_CHECK_LAUNCH();
   return MSMD_OK;
 }
@@ -463,25 +497,23 @@ __global__ void __launch_bounds__(256) cross_attn_row0_kernel(const bf16* __rest
 #pragma unroll
   for (int i = 0; i < 4; ++i) { sc[i] = (sc[i] == -INFINITY) ? 0.f : __expf(sc[i] - m); l += sc[i]; }
   l = warp_sum(l);
-  // output: lane owns dims 2*lane, 2*lane+1; V rows are read coalesced (128 B per key)
+  // output: lane owns dims 2*lane, 2*lane+1; V rows are read coalesced (128 B per key).  All of a 32-key
+  // group's loads are issued before the first FMA so only four memory latencies are exposed.
   float oa = 0.f, ob = 0.f;
   const bf16* vbase = kv + (int64_t)s * Tk * 2 * d + d + h * 64 + 2 * lane;
 #pragma unroll
   for (int grp = 0; grp < 4; ++grp) {
+    uint32_t vu[32];
 #pragma unroll
-    for (int j8 = 0; j8 < 32; j8 += 8) {   // 8 independent V loads in flight per batch
-      uint32_t vu[8];
+    for (int u = 0; u < 32; ++u) {
+      const int j = grp * 32 + u;
+      vu[u] = (j < Tk) ? __ldg(reinterpret_cast<const uint32_t*>(vbase + (int64_t)j * 2 * d)) : 0u;
+    }
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int j = grp * 32 + j8 + u;
-        vu[u] = (j < Tk) ? __ldg(reinterpret_cast<const uint32_t*>(vbase + (int64_t)j * 2 * d)) : 0u;
-      }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const float p = __shfl_sync(0xffffffffu, sc[grp], j8 + u);   // 0 for keys >= Tk
-        oa = fmaf(p, __uint_as_float(vu[u] << 16), oa);
-        ob = fmaf(p, __uint_as_float(vu[u] & 0xffff0000u), ob);
-      }
+    for (int u = 0; u < 32; ++u) {
+      const float p = __shfl_sync(0xffffffffu, sc[grp], u);   // 0 for keys >= Tk
+      oa = fmaf(p, __uint_as_float(vu[u] << 16), oa);
+      ob = fmaf(p, __uint_as_float(vu[u] & 0xffff0000u), ob);
     }
   }
   const float inv = 1.0f / l;
@@ -489,6 +521,7 @@ __global__ void __launch_bounds__(256) cross_attn_row0_kernel(const bf16* __rest
 }
 int cross_attn_row0_launch(const bf16* q0, const bf16* kv, bf16* ctx0, int S, int Tk, int H, cudaStream_t st) {
   MSMD_REQUIRE(Tk <= 128, "cross_attn_row0: memory length %d > 128", Tk);
+  ProfileScope prof("cross_attn_row0", st);
   cross_attn_row0_kernel<<<cdiv(S * H, 8), 256, 0, st>>>(q0, kv, ctx0, S, Tk, H);
   MSMD_CHECK_LAUNCH();
   return MSMD_OK;
@@ -559,6 +592,7 @@ __global__ void __launch_bounds__(256) update_kernel(UpdateParams p) {
 }
 int update_launch(const UpdateParams& p, cudaStream_t st) {
   const int64_t n = (int64_t)p.NX * p.L * p.dm;
+  ProfileScope prof("update", st);
   update_kernel<<<(int)std::min<int64_t>(cdiv(n, 256), kNumSMs * 8), 256, 0, st>>>(p);
   MSMD_CHECK_LAUNCH();
   return MSMD_OK;

@@ -5,6 +5,8 @@
 #include <mutex>
 #include <string>
 #include <vector>
+#include <cstring>
+#include <algorithm>
 
 namespace msmd {
 static thread_local char g_err[1024] = "";
@@ -77,5 +79,23 @@ extern "C" int msmd_profile_query(const char* name, double* total_ms, int64_t* l
   auto it = msmd::g_totals.find(name ? name : "");
   if (total_ms) *total_ms = it == msmd::g_totals.end() ? 0.0 : it->second.first;
   if (launches) *launches = it == msmd::g_totals.end() ? 0 : it->second.second;
+  return MSMD_OK;
+}
+
+// Writes "name total_ms launches\n" lines for every kernel class seen since the last reset.
+extern "C" int msmd_profile_dump(char* buf, int64_t cap) {
+  msmd_profile_query("", nullptr, nullptr);   // drain pending events
+  std::lock_guard<std::mutex> lk(msmd::g_prof_mu);
+  std::string out;
+  for (auto& kv : msmd::g_totals) {
+    char line[256];
+    snprintf(line, sizeof(line), "%s %.6f %ld\n", kv.first.c_str(), kv.second.first, kv.second.second);
+    out += line;
+  }
+  if (buf && cap > 0) {
+    const size_t n = std::min<size_t>(out.size(), (size_t)cap - 1);
+    memcpy(buf, out.data(), n);
+    buf[n] = 0;
+  }
   return MSMD_OK;
 }

@@ -4,6 +4,7 @@
 #include <cudaTypedefs.h>
 #include <mutex>
 #include <cstdlib>
+#include <cstring>
 
 namespace msmd {
 
@@ -115,6 +116,9 @@ static int launch_cfg2(const GemmDesc& d, cudaStream_t st) {
     attr_set = true;
   }
   ProfileScope prof(MODE == 0 ? "gemm_bf16" : "gemm_tf32x3", st);
+  char shape_name[64];
+  snprintf(shape_name, sizeof(shape_name), "gemm_%dx%dx%d%s", d.M, d.N, d.K, Cfg::CTA2 ? "_pair" : "");
+  ProfileScope prof2(profiling_on() ? strdup(shape_name) : "", st);
   if constexpr (Cfg::CTA2) {
     const int pairs = tiles < kNumSMs / 2 ? tiles : kNumSMs / 2;
     cudaLaunchConfig_t cfg = {};
