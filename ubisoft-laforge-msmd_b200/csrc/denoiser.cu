@@ -119,20 +119,20 @@ int run_forward(msmd_model* m, const float* xrows, cudaStream_t st) {
     LnParams lp;
     lp.resid = m->x;
     lp.y = m->y; lp.g1 = w.g1; lp.b1 = w.be1; lp.add = w.ca; lp.g2 = w.g2; lp.b2 = w.be2; lp.out = m->x;
-    lp.x0 = m->x0c; lp.M = M; lp.T = T; lp.d = d;
+    lp.x0 = m->x0c; lp.skip_tok0 = 0; lp.M = M; lp.T = T; lp.d = d;
     if ((rc = ln_launch(lp, st))) return rc;
     // person token (row 0): real cross attention over the memory (_mha_block) + norm2
     if ((rc = gemm(m->x0c, d, w.Wq0, d, w.bq0, nullptr, 0, m->q0, d, 0, S, d, d, 0, st))) return rc;
     if ((rc = cross_attn_row0_launch(m->q0, w.kv, m->ctx0, S, T - 1, c.n_heads, st))) return rc;
     if ((rc = gemm(m->ctx0, d, w.Wco, d, w.bco, nullptr, 0, m->y0, d, 0, S, d, d, 0, st))) return rc;
-    if ((rc = ln_row0_launch(m->y0, m->x0c, w.g2, w.be2, m->x, S, T, d, st))) return rc;
+    if ((rc = ln_row0_launch(m->y0, m->x0c, w.g2, w.be2, m->x, nullptr, S, T, d, st))) return rc;
     // feed-forward block (_ff_block) + norm3
     if ((rc = gemm(m->x, d, w.W1, d, w.b1, nullptr, 0, m->h, c.d_ff, 0, M, c.d_ff, d, 1, st))) return rc;
     if ((rc = gemm(m->h, c.d_ff, w.W2, c.d_ff, w.b2, nullptr, 0, m->y, d, 0, M, d, c.d_ff, 0, st))) return rc;
     LnParams l3;
     l3.resid = m->x;
     l3.y = m->y; l3.g1 = w.g3; l3.b1 = w.be3; l3.add = nullptr; l3.g2 = nullptr; l3.b2 = nullptr; l3.out = m->x;
-    l3.x0 = nullptr; l3.M = M; l3.T = T; l3.d = d;
+    l3.x0 = nullptr; l3.skip_tok0 = 0; l3.M = M; l3.T = T; l3.d = d;
     if ((rc = ln_launch(l3, st))) return rc;
   }
   // motion_dec (model.py:961): Linear(d, d/2) + GELU + Linear(d/2, dm + n_basis)

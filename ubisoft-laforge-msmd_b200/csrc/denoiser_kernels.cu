@@ -221,6 +221,7 @@ __global__ void __launch_bounds__(256) ln_kernel(LnParams p) {
       v[4 * i + 3] += __uint_as_float(u.y & 0xffff0000u);
     }
   }
+  if (tok == 0 && p.skip_tok0) return;
   ln_row<D>(v, p.g1, p.b1, lane);
   if (tok == 0 && p.x0 != nullptr) {
 #pragma unroll
@@ -256,7 +257,7 @@ int ln_launch(const LnParams& p, cudaStream_t st) {
 template <int D>
 __global__ void __launch_bounds__(256) ln_row0_kernel(const bf16* __restrict__ y0, const bf16* __restrict__ resid0,
                                                       const float* __restrict__ g, const float* __restrict__ b,
-                                                      bf16* __restrict__ out, int S, int T) {
+                                                      bf16* __restrict__ out, bf16* __restrict__ out_c, int S, int T) {
   constexpr int NV = D / 32;
   const int lane = threadIdx.x & 31;
   const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -278,15 +279,17 @@ __global__ void __launch_bounds__(256) ln_row0_kernel(const bf16* __restrict__ y
     }
   }
   ln_row<D>(v, g, b, lane);
-  bf16* o = out + (int64_t)s * T * D;
 #pragma unroll
-  for (int i = 0; i < NV / 4; ++i) store_bf16x4(o + i * 128 + lane * 4, v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  for (int i = 0; i < NV / 4; ++i) {
+    if (out) store_bf16x4(out + (int64_t)s * T * D + i * 128 + lane * 4, v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    if (out_c) store_bf16x4(out_c + (int64_t)s * D + i * 128 + lane * 4, v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  }
 }
-int ln_row0_launch(const bf16* y0, const bf16* resid0, const float* g, const float* b, bf16* out, int S, int T, int d,
-                   cudaStream_t st) {
+int ln_row0_launch(const bf16* y0, const bf16* resid0, const float* g, const float* b, bf16* out, bf16* out_c, int S,
+                   int T, int d, cudaStream_t st) {
   MSMD_REQUIRE(d == 512, "ln_row0: only d_model = 512 is instantiated");
   ProfileScope prof("ln_row0", st);
-  ln_row0_kernel<512><<<cdiv(S, 8), 256, 0, st>>>(y0, resid0, g, b, out, S, T);
+  ln_row0_kernel<512><<<cdiv(S, 8), 256, 0, st>>>(y0, resid0, g, b, out, out_c, S, T);
   MSMD_CHECK_LAUNCH();
   return MSMD_OK;
 }
@@ -447,15 +450,26 @@ int self_attn_launch(const bf16* qkv, bf16* ctx, int S, int T, int H, cudaStream
 }
 
 // ------------------------------------------------------------------------------------------- row-0 cross attention
-// The alignment mask (model.py:879-883) lets only the person token attend to all memory; one warp per (s, head).
-__global__ void __launch_bounds__(256) cross_attn_row0_kernel(const bf16* __restrict__ q0, const bf16* __restrict__ kv,
-                                                              bf16* __restrict__ ctx0, int S, int Tk, int H) {
-  const int lane = threadIdx.x & 31;
-  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (w >= S * H) return;
-  const int s = w / H, h = w % H;
-  const int d = H * 64;
-  // every lane keeps the whole 64-dim query (broadcast loads), and scores keys lane, lane+32, lane+64, lane+96
+// The alignment mask (model.py:879-883) lets only the person token attend to all memory.  One CTA per
+// sequence, one warp per head.  The sequence's K block ([Tk, d], all heads) is streamed into shared memory
+// with cp.async (every load in flight at once), scores are computed, then V streams into the same buffer:
+// HBM-bound (2 x Tk x d x 2 B per sequence per layer), two memory latencies in total.
+constexpr int kCaPitch = 1024 + 16;   // bytes per key row in smem: +16 B so 128-bit row reads spread over banks
+
+__global__ void __launch_bounds__(256, 2) cross_attn_row0_kernel(const bf16* __restrict__ q0, const bf16* __restrict__ kv,
+                                                                 bf16* __restrict__ ctx0, int Tk) {
+  extern __shared__ __align__(16) uint8_t ca_smem[];
+  constexpr int d = 512;
+  const int s = blockIdx.x, tid = threadIdx.x, h = tid >> 5, lane = tid & 31;
+  const bf16* kbase = kv + (int64_t)s * Tk * 2 * d;
+  auto stream = [&](int off) {  // off = 0: K half of each row, d: V half
+    for (int idx = tid; idx < Tk * 64; idx += 256) {
+      const int row = idx >> 6, ch = idx & 63;
+      cp_async16(ca_smem + row * kCaPitch + ch * 16, kbase + (int64_t)row * 2 * d + off + ch * 8);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  stream(0);
   float q[64];
   {
     const uint4* qp = reinterpret_cast<const uint4*>(q0 + (int64_t)s * d + h * 64);
@@ -470,17 +484,19 @@ __global__ void __launch_bounds__(256) cross_attn_row0_kernel(const bf16* __rest
       }
     }
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
   float sc[4];
 #pragma unroll
   for (int grp = 0; grp < 4; ++grp) {
     const int j = grp * 32 + lane;
     float dot = -INFINITY;
     if (j < Tk) {
-      const uint4* kp = reinterpret_cast<const uint4*>(kv + ((int64_t)s * Tk + j) * 2 * d + h * 64);
+      const uint4* kp = reinterpret_cast<const uint4*>(ca_smem + j * kCaPitch + h * 128);
       float acc = 0.f;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const uint4 u = __ldg(kp + i);
+        const uint4 u = kp[i];
         const uint32_t ww[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -492,37 +508,111 @@ __global__ void __launch_bounds__(256) cross_attn_row0_kernel(const bf16* __rest
     }
     sc[grp] = dot;
   }
+  __syncthreads();   // every warp has read K: the buffer can take V
+  stream(d);
   const float m = warp_max(fmaxf(fmaxf(sc[0], sc[1]), fmaxf(sc[2], sc[3])));
   float l = 0.f;
 #pragma unroll
   for (int i = 0; i < 4; ++i) { sc[i] = (sc[i] == -INFINITY) ? 0.f : __expf(sc[i] - m); l += sc[i]; }
   l = warp_sum(l);
-  // output: lane owns dims 2*lane, 2*lane+1; V rows are read coalesced (128 B per key).  All of a 32-key
-  // group's loads are issued before the first FMA so only four memory latencies are exposed.
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
   float oa = 0.f, ob = 0.f;
-  const bf16* vbase = kv + (int64_t)s * Tk * 2 * d + d + h * 64 + 2 * lane;
+  const uint8_t* vcol = ca_smem + h * 128 + lane * 4;   // lane owns dims 2*lane, 2*lane+1 of this head
 #pragma unroll
   for (int grp = 0; grp < 4; ++grp) {
-    uint32_t vu[32];
-#pragma unroll
+#pragma unroll 8
     for (int u = 0; u < 32; ++u) {
       const int j = grp * 32 + u;
-      vu[u] = (j < Tk) ? __ldg(reinterpret_cast<const uint32_t*>(vbase + (int64_t)j * 2 * d)) : 0u;
-    }
-#pragma unroll
-    for (int u = 0; u < 32; ++u) {
-      const float p = __shfl_sync(0xffffffffu, sc[grp], u);   // 0 for keys >= Tk
-      oa = fmaf(p, __uint_as_float(vu[u] << 16), oa);
-      ob = fmaf(p, __uint_as_float(vu[u] & 0xffff0000u), ob);
+      if (j >= Tk) break;
+      const float p = __shfl_sync(0xffffffffu, sc[grp], u);
+      const uint32_t vu = *reinterpret_cast<const uint32_t*>(vcol + j * kCaPitch);
+      oa = fmaf(p, __uint_as_float(vu << 16), oa);
+      ob = fmaf(p, __uint_as_float(vu & 0xffff0000u), ob);
     }
   }
   const float inv = 1.0f / l;
   *reinterpret_cast<uint32_t*>(ctx0 + (int64_t)s * d + h * 64 + 2 * lane) = pack_bf16(oa * inv, ob * inv);
 }
 int cross_attn_row0_launch(const bf16* q0, const bf16* kv, bf16* ctx0, int S, int Tk, int H, cudaStream_t st) {
-  MSMD_REQUIRE(Tk <= 128, "cross_attn_row0: memory length %d > 128", Tk);
+  MSMD_REQUIRE(Tk <= 110 && H == 8, "cross_attn_row0: built for 8 heads x 64 and <= 110 memory tokens (got %d, %d)", H, Tk);
+  const int smem = Tk * kCaPitch;
+  static bool attr = false;
+  if (!attr) {
+    MSMD_CHECK_CUDA(cudaFuncSetAttribute(cross_attn_row0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * kCaPitch));
+    attr = true;
+  }
   ProfileScope prof("cross_attn_row0", st);
-  cross_attn_row0_kernel<<<cdiv(S * H, 8), 256, 0, st>>>(q0, kv, ctx0, S, Tk, H);
+  cross_attn_row0_kernel<<<S, 256, smem, st>>>(q0, kv, ctx0, Tk);
+  MSMD_CHECK_LAUNCH();
+  return MSMD_OK;
+}
+
+// ------------------------------------------------------------------------------------------- small-M linear
+// out[r, f] = bias[f] + sum_k x[r,k] W[f,k] for a handful of rows (the person-token projections, M = S):
+// a 128-row tcgen05 tile would idle 87% of the tensor pipe and pay a 6 us kernel prologue, so this runs on
+// mma.sync m16n8k16: CTA = 16 rows x 64 features, 4 warps x 16 features, W fragments straight from L2.
+__global__ void __launch_bounds__(128) rowgemm_kernel(const bf16* __restrict__ x, const bf16* __restrict__ W,
+                                                      const float* __restrict__ bias, bf16* __restrict__ out, int R,
+                                                      int F, int K, int gelu) {
+  extern __shared__ __align__(16) bf16 rg_x[];    // [16][K + 8]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int r0 = blockIdx.y * 16, f0 = blockIdx.x * 64 + warp * 16;
+  const int pitch = K + 8;
+  for (int idx = tid; idx < 16 * (K / 8); idx += 128) {
+    const int row = idx / (K / 8), ch = idx % (K / 8);
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (r0 + row < R) v = *reinterpret_cast<const uint4*>(x + (int64_t)(r0 + row) * K + ch * 8);
+    *reinterpret_cast<uint4*>(rg_x + row * pitch + ch * 8) = v;
+  }
+  __syncthreads();
+  float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+  const bf16* w0 = W + (int64_t)(f0 + g) * K + 2 * t;
+  const bf16* w1 = w0 + (int64_t)8 * K;
+  for (int k0 = 0; k0 < K; k0 += 128) {          // 8 k-steps per batch: 32 independent loads in flight per lane
+    uint32_t b[8][4];
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+      const int k = k0 + ks * 16;
+      b[ks][0] = __ldg(reinterpret_cast<const uint32_t*>(w0 + k));
+      b[ks][1] = __ldg(reinterpret_cast<const uint32_t*>(w0 + k + 8));
+      b[ks][2] = __ldg(reinterpret_cast<const uint32_t*>(w1 + k));
+      b[ks][3] = __ldg(reinterpret_cast<const uint32_t*>(w1 + k + 8));
+    }
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+      const int k = k0 + ks * 16;
+      uint32_t a[4];
+      a[0] = *reinterpret_cast<const uint32_t*>(rg_x + g * pitch + k + 2 * t);
+      a[1] = *reinterpret_cast<const uint32_t*>(rg_x + (g + 8) * pitch + k + 2 * t);
+      a[2] = *reinterpret_cast<const uint32_t*>(rg_x + g * pitch + k + 8 + 2 * t);
+      a[3] = *reinterpret_cast<const uint32_t*>(rg_x + (g + 8) * pitch + k + 8 + 2 * t);
+      mma_bf16_16816(acc[0], a, b[ks][0], b[ks][1]);
+      mma_bf16_16816(acc[1], a, b[ks][2], b[ks][3]);
+    }
+  }
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt) {
+    const int f = f0 + nt * 8 + 2 * t;
+    const float b0 = bias ? bias[f] : 0.f, b1 = bias ? bias[f + 1] : 0.f;
+    float v0 = acc[nt][0] + b0, v1 = acc[nt][1] + b1, v2 = acc[nt][2] + b0, v3 = acc[nt][3] + b1;
+    if (gelu) { v0 = gelu_exact(v0); v1 = gelu_exact(v1); v2 = gelu_exact(v2); v3 = gelu_exact(v3); }
+    if (r0 + g < R) *reinterpret_cast<uint32_t*>(out + (int64_t)(r0 + g) * F + f) = pack_bf16(v0, v1);
+    if (r0 + g + 8 < R) *reinterpret_cast<uint32_t*>(out + (int64_t)(r0 + g + 8) * F + f) = pack_bf16(v2, v3);
+  }
+}
+int rowgemm_launch(const bf16* x, const bf16* W, const float* bias, bf16* out, int R, int F, int K, int gelu,
+                   cudaStream_t st) {
+  MSMD_REQUIRE(F % 64 == 0 && K % 128 == 0, "rowgemm: F %% 64 and K %% 128 required (got %d, %d)", F, K);
+  ProfileScope prof("rowgemm", st);
+  const int smem = 16 * (K + 8) * (int)sizeof(bf16);
+  static bool attr = false;
+  if (!attr) {
+    MSMD_CHECK_CUDA(cudaFuncSetAttribute(rowgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * (4096 + 8) * 2));
+    attr = true;
+  }
+  MSMD_REQUIRE(K <= 4096, "rowgemm: K %d > 4096", K);
+  rowgemm_kernel<<<dim3(F / 64, cdiv(R, 16)), 128, smem, st>>>(x, W, bias, out, R, F, K, gelu);
   MSMD_CHECK_LAUNCH();
   return MSMD_OK;
 }

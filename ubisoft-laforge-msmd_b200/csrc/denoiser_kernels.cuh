@@ -44,17 +44,23 @@ struct LnParams {
   const float* g2; const float* b2;   // used iff add != null
   bf16* out;                // [M, d]
   bf16* x0;                 // [S, d] or null
+  int skip_tok0;            // do not write token-0 rows at all (they are produced by the person-token stream)
   int M, T, d;
 };
 int ln_launch(const LnParams& p, cudaStream_t st);
 // row-0 finish: LayerNorm(y0 [S,d]; g,b) -> out[s*T + 0]
-int ln_row0_launch(const bf16* y0, const bf16* resid0, const float* g, const float* b, bf16* out, int S, int T, int d,
-                   cudaStream_t st);
+// LayerNorm(y0 + resid0) of the S person-token rows -> out[s*T + 0] (if out) and compact out_c[s] (if out_c)
+int ln_row0_launch(const bf16* y0, const bf16* resid0, const float* g, const float* b, bf16* out, bf16* out_c, int S,
+                   int T, int d, cudaStream_t st);
 
 // self-attention over T <= 112 tokens, head dim 64: qkv [S*T, 3*d] bf16 (q|k|v) -> ctx [S*T, d] bf16
 int self_attn_launch(const bf16* qkv, bf16* ctx, int S, int T, int H, cudaStream_t st);
 // row-0 cross attention: q0 [S,d]; kv [S*Tk, 2d] (k|v) -> ctx0 [S,d]
 int cross_attn_row0_launch(const bf16* q0, const bf16* kv, bf16* ctx0, int S, int Tk, int H, cudaStream_t st);
+
+// out[R,F] = x[R,K] W[F,K]^T + bias for small R (mma.sync; the person-token projections)
+int rowgemm_launch(const bf16* x, const bf16* W, const float* bias, bf16* out, int R, int F, int K, int gelu,
+                   cudaStream_t st);
 
 struct UpdateParams {
   const float* dec;       // [S, T, ldd] fp32: motion_dec output (dm dynamic + nb alphas)

@@ -446,6 +446,7 @@ struct GemmDesc {
   int bias_zstride = 0;
   int gelu_heavy = 0;           // use 8 epilogue warps
   int cta2 = -1;                // CTA-pair tiles: -1 auto (large bf16 GEMMs without aux), 0 off, 1 force
+  int max_ctas = 0;             // > 0: cap the persistent grid (leave SMs to a concurrent stream)
 };
 
 int gemm_tc_launch(const GemmDesc& d, cudaStream_t st);
