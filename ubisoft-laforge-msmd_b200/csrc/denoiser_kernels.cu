@@ -93,6 +93,8 @@ int build_memory_bf16(const float* prev_audio, const float* audio, bf16* mem, in
 // ------------------------------------------------------------------------------------------- embeddings
 // rows 0..Lp: person token (+ timestep embedding) and the projected previous-motion context
 __global__ void embed_ctx_kernel(EmbedParams p) {
+  griddep_launch();
+  griddep_wait();
   const int T = 1 + p.Lp + p.L;
   const int row = blockIdx.x;  // s * (Lp+1) + i
   const int s = row / (p.Lp + 1), i = row % (p.Lp + 1);
@@ -107,6 +109,8 @@ __global__ void embed_ctx_kernel(EmbedParams p) {
 // rows Lp+1..: feature_proj([x_t, indicator]) + PE, computed once per x row and written to its E sequences
 constexpr int kEmbedRows = 20;
 __global__ void __launch_bounds__(256) embed_x_kernel(EmbedParams p) {
+  griddep_launch();
+  griddep_wait();
   extern __shared__ float xs[];  // [kEmbedRows][dm] x rows, then [E][kEmbedRows] indicators
   const int T = 1 + p.Lp + p.L;
   const int blocks_per_x = (p.L + kEmbedRows - 1) / kEmbedRows;
@@ -153,10 +157,10 @@ __global__ void __launch_bounds__(256) embed_x_kernel(EmbedParams p) {
 }
 int embed_launch(const EmbedParams& p, cudaStream_t st) {
   ProfileScope prof("embed", st);
-  embed_ctx_kernel<<<p.S * (p.Lp + 1), 128, 0, st>>>(p);
+  MSMD_CHECK_CUDA(launch_pdl(embed_ctx_kernel, dim3(p.S * (p.Lp + 1)), dim3(128), 0, st, p));
   MSMD_CHECK_LAUNCH();
   const int blocks = p.NX * ((p.L + kEmbedRows - 1) / kEmbedRows);
-  embed_x_kernel<<<blocks, 256, (kEmbedRows * p.dm + 3 * kEmbedRows) * sizeof(float), st>>>(p);
+  MSMD_CHECK_CUDA(launch_pdl(embed_x_kernel, dim3(blocks), dim3(256), (kEmbedRows * p.dm + 3 * kEmbedRows) * sizeof(float), st, p));
   MSMD_CHECK_LAUNCH();
   return MSMD_OK;
 }
@@ -195,6 +199,8 @@ __device__ __forceinline__ void store_bf16x4(bf16* dst, float a, float b, float 
 
 template <int D>
 __global__ void __launch_bounds__(256) ln_kernel(LnParams p) {
+  griddep_launch();
+  griddep_wait();
   constexpr int NV = D / 32;
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -249,7 +255,7 @@ __global__ void __launch_bounds__(256) ln_kernel(LnParams p) {
 int ln_launch(const LnParams& p, cudaStream_t st) {
   MSMD_REQUIRE(p.d == 512, "ln: only d_model = 512 is instantiated (got %d)", p.d);
   ProfileScope prof(p.add ? "ln1_ln2" : "ln3", st);
-  ln_kernel<512><<<cdiv(p.M, 8), 256, 0, st>>>(p);
+  MSMD_CHECK_CUDA(launch_pdl(ln_kernel<512>, dim3(cdiv(p.M, 8)), dim3(256), 0, st, p));
   MSMD_CHECK_LAUNCH();
   return MSMD_OK;
 }
@@ -258,6 +264,8 @@ template <int D>
 __global__ void __launch_bounds__(256) ln_row0_kernel(const bf16* __restrict__ y0, const bf16* __restrict__ resid0,
                                                       const float* __restrict__ g, const float* __restrict__ b,
                                                       bf16* __restrict__ out, bf16* __restrict__ out_c, int S, int T) {
+  griddep_launch();
+  griddep_wait();
   constexpr int NV = D / 32;
   const int lane = threadIdx.x & 31;
   const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -289,7 +297,7 @@ int ln_row0_launch(const bf16* y0, const bf16* resid0, const float* g, const flo
                    int T, int d, cudaStream_t st) {
   MSMD_REQUIRE(d == 512, "ln_row0: only d_model = 512 is instantiated");
   ProfileScope prof("ln_row0", st);
-  ln_row0_kernel<512><<<cdiv(S, 8), 256, 0, st>>>(y0, resid0, g, b, out, out_c, S, T);
+  MSMD_CHECK_CUDA(launch_pdl(ln_row0_kernel<512>, dim3(cdiv(S, 8)), dim3(256), 0, st, y0, resid0, g, b, out, out_c, S, T));
   MSMD_CHECK_LAUNCH();
   return MSMD_OK;
 }
@@ -319,6 +327,8 @@ constexpr int kAttHeadsPerCta = 4;   // 2*S*H/4 CTAs: enough CTAs to balance 148
 __global__ void __launch_bounds__(224, 2) self_attn_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ ctx, int T,
                                                            int H) {
   extern __shared__ __align__(16) bf16 att_smem[];
+  griddep_launch();
+  griddep_wait();
   const int s = blockIdx.x;
   const int d = H * kAttDh;
   const int tid = threadIdx.x;
@@ -444,7 +454,7 @@ int self_attn_launch(const bf16* qkv, bf16* ctx, int S, int T, int H, cudaStream
     attr = true;
   }
   ProfileScope prof("self_attn", st);
-  self_attn_kernel<<<dim3(S, cdiv(H, kAttHeadsPerCta)), 224, smem, st>>>(qkv, ctx, T, H);
+  MSMD_CHECK_CUDA(launch_pdl(self_attn_kernel, dim3(S, cdiv(H, kAttHeadsPerCta)), dim3(224), smem, st, qkv, ctx, T, H));
   MSMD_CHECK_LAUNCH();
   return MSMD_OK;
 }
@@ -459,6 +469,8 @@ constexpr int kCaPitch = 1024 + 16;   // bytes per key row in smem: +16 B so 128
 __global__ void __launch_bounds__(256, 2) cross_attn_row0_kernel(const bf16* __restrict__ q0, const bf16* __restrict__ kv,
                                                                  bf16* __restrict__ ctx0, int Tk) {
   extern __shared__ __align__(16) uint8_t ca_smem[];
+  griddep_launch();
+  griddep_wait();
   constexpr int d = 512;
   const int s = blockIdx.x, tid = threadIdx.x, h = tid >> 5, lane = tid & 31;
   const bf16* kbase = kv + (int64_t)s * Tk * 2 * d;
@@ -543,7 +555,7 @@ int cross_attn_row0_launch(const bf16* q0, const bf16* kv, bf16* ctx0, int S, in
     attr = true;
   }
   ProfileScope prof("cross_attn_row0", st);
-  cross_attn_row0_kernel<<<S, 256, smem, st>>>(q0, kv, ctx0, Tk);
+  MSMD_CHECK_CUDA(launch_pdl(cross_attn_row0_kernel, dim3(S), dim3(256), smem, st, q0, kv, ctx0, Tk));
   MSMD_CHECK_LAUNCH();
   return MSMD_OK;
 }
@@ -645,6 +657,8 @@ __device__ __forceinline__ float mixed_target(const UpdateParams& p, int s, int 
 }
 
 __global__ void __launch_bounds__(256) update_kernel(UpdateParams p) {
+  griddep_launch();
+  griddep_wait();
   const int64_t n_el = (int64_t)p.NX * p.L * p.dm;
   const int t = p.steps[0];
   // model.py:383-386, :421-428 — 0-dim fp32 tensor arithmetic, same operation order
@@ -683,7 +697,7 @@ __global__ void __launch_bounds__(256) update_kernel(UpdateParams p) {
 int update_launch(const UpdateParams& p, cudaStream_t st) {
   const int64_t n = (int64_t)p.NX * p.L * p.dm;
   ProfileScope prof("update", st);
-  update_kernel<<<(int)std::min<int64_t>(cdiv(n, 256), kNumSMs * 8), 256, 0, st>>>(p);
+  MSMD_CHECK_CUDA(launch_pdl(update_kernel, dim3((int)std::min<int64_t>(cdiv(n, 256), kNumSMs * 8)), dim3(256), 0, st, p));
   MSMD_CHECK_LAUNCH();
   return MSMD_OK;
 }
@@ -693,6 +707,8 @@ __global__ void steps_set_kernel(int* steps, int S, int v) {
   if (i < S) steps[i] = v;
 }
 __global__ void steps_advance_kernel(int* steps, int S) {
+  griddep_launch();
+  griddep_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < S) steps[i] -= 1;
 }
@@ -702,7 +718,7 @@ int steps_set(int* steps, int S, int value, cudaStream_t st) {
   return MSMD_OK;
 }
 int steps_advance(int* steps, int S, cudaStream_t st) {
-  steps_advance_kernel<<<cdiv(S, 256), 256, 0, st>>>(steps, S);
+  MSMD_CHECK_CUDA(launch_pdl(steps_advance_kernel, dim3(cdiv(S, 256)), dim3(256), 0, st, steps, S));
   MSMD_CHECK_LAUNCH();
   return MSMD_OK;
 }

@@ -6,6 +6,7 @@
 #include <string>
 #include <vector>
 #include <cstring>
+#include <cstdlib>
 #include <algorithm>
 
 namespace msmd {
@@ -25,6 +26,11 @@ static std::vector<Pending> g_pending;
 static std::map<std::string, std::pair<double, long>> g_totals;
 
 bool profiling_on() { return g_prof; }
+
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("MSMD_PDL"); return e && atoi(e) != 0; }();
+  return on;
+}
 
 ProfileScope::ProfileScope(const char* n, cudaStream_t s) : name(n), st(s) {
   if (!g_prof) return;

@@ -127,16 +127,18 @@ static int launch_cfg2(const GemmDesc& d, cudaStream_t st) {
     cfg.blockDim = dim3(Cfg::THREADS);
     cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     MSMD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
   } else {
     const int sms = (d.max_ctas > 0 && d.max_ctas < kNumSMs) ? d.max_ctas : kNumSMs;
     const int grid = tiles < sms ? tiles : sms;
-    kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(p);
+    MSMD_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, p));
   }
   MSMD_CHECK_LAUNCH();
   return MSMD_OK;

@@ -127,6 +127,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_tc_kernel(const __grid_c
   static_assert((2 * Cfg::STAGES + 4 + 2 * Cfg::EPI_WARPS) * 8 + 4 <= 256, "barrier block overflows its 256 bytes");
   if (threadIdx.x == 0 && reinterpret_cast<uint8_t*>(bias_tile) + 2 * 256 * 4 > smem_raw + Cfg::SMEM_BYTES) __trap();
 
+  griddep_launch();   // PDL: let the next kernel of the stream get scheduled behind this one
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cta_rank = Cfg::CTA2 ? (int)cluster_ctarank() : 0;
   const int tile0 = Cfg::CTA2 ? (int)blockIdx.x / 2 : (int)blockIdx.x;       // first tile of this CTA (pair)
@@ -154,6 +155,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_tc_kernel(const __grid_c
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();     // PDL: everything above overlapped the previous kernel's tail; its outputs are visible from here
 
   auto tile_coords = [&](int t, int& m0, int& n0, int& z) {
     const int per_z = p.tiles_m * p.tiles_n;
