@@ -123,15 +123,20 @@ class FlameWorkload:
         return sum(h.numel() * 4 for h in self.host), self.host_out.numel() * 4
 
     def roofline(self, peaks, kernel_ms):
-        # fused minimal bytes = betas + pose + bases (once) + verts out
+        # fused kernel = tf32x3 tcgen05 GEMM [B,436]x[436,15069] (fp32-grade: 3 MMA passes) + LBS epilogue.
+        # Tensor-bound: algorithmic 2*B*15069*436 fp32-equivalent FLOPs against (bf16 peak / 2 for tf32) / 3 passes;
+        # the HBM floor (534 MB minimal traffic at B=8192) is reported next to it.
         B = self.frames
-        alg = B * 400 * 4 + B * 15 * 4 + 15069 * 436 * 4 + B * 15069 * 4
-        ach = alg / (kernel_ms * 1e-3) / 1e9
         flops = 2.0 * B * 15069 * 436
-        return dict(bound='hbm', kernel=self.kernel, achieved=ach, peak=peaks['hbm_gbs'], unit='GB/s',
-                    frac=ach / peaks['hbm_gbs'], traffic=None, peak_source=peaks['_source'] + ' (burst copy)',
-                    algorithmic_bytes=alg, kernel_ms=kernel_ms,
-                    gemm_fp32_equiv_tflops=flops / (kernel_ms * 1e-3) / 1e12)
+        ach = flops / (kernel_ms * 1e-3) / 1e12
+        pk = peaks['bf16_tflops'] / 2.0 / 3.0
+        alg = B * 400 * 4 + B * 15 * 4 + 15069 * 436 * 4 + B * 15069 * 4
+        return dict(bound='tensor', kernel=self.kernel + ' (tcgen05 kind::tf32 x3 + LBS epilogue)', achieved=ach, peak=pk,
+                    unit='TFLOP/s', frac=ach / pk, traffic=849.5e6 if B == 8192 else None,   # profiles/r01_flame_tc_ncu.txt
+                    peak_source=peaks['_source'] + ' burst cuBLAS bf16 / 2 (tf32) / 3 (passes)',
+                    algorithmic_flops_per_launch=flops, kernel_ms=kernel_ms,
+                    hbm=dict(algorithmic_bytes=alg, achieved_gbs=alg / (kernel_ms * 1e-3) / 1e9, peak_gbs=peaks['hbm_gbs'],
+                             frac=alg / (kernel_ms * 1e-3) / 1e9 / peaks['hbm_gbs']))
 
     def cpu_reference(self, seconds=10.0):
         """oracle port (oracle/flame_lbs.py) on the host cores, 512-frame batches like common.py:176-196."""
@@ -156,8 +161,6 @@ class SamplerWorkload:
     metric = 'generated_animation_seconds_per_second'
     unit = 'animation-s/s'
     dtype = 'bf16'
-    kernel = 'gemm_bf16'
-
     def __init__(self, clips=64, seconds=10.0):
         self.clips, self.seconds = clips, seconds
         self.frames = int(seconds * 25)
@@ -243,18 +246,31 @@ class SamplerWorkload:
     def e2e_bytes(self):
         return sum(v.numel() * 4 for v in self.host.values()), (self.host_out.numel() + self.host_verts.numel()) * 4
 
+    @property
+    def kernel(self):
+        # dominant kernel = the FF1 GEMM (linear1 + GELU) of the decoder layers: largest single share of the step
+        return f'gemm_{3 * self.clips * 111}x2048x512'
+
     def roofline(self, peaks, kernel_ms):
-        # dominant kernel class = the bf16 tcgen05 GEMM.  Algorithmic FLOPs per denoiser forward as executed
-        # (hoisted basis): per sequence 8 x (in_proj 174.6M + out 58.2M + FFN 465.6M) + motion_dec 32.8M
+        M = 3 * self.clips * 111
+        flops = 2.0 * M * 2048 * 512                      # algorithmic FLOPs of one launch (FFN linear1)
+        ach = flops / (kernel_ms * 1e-3) / 1e12
+        pk = peaks.get('bf16_tflops_sustained', peaks['bf16_tflops'])
+        from msmd_b200 import _lib
+        prof = _lib.profile_dump()
+        cls_ms, cls_n = prof.get('gemm_bf16', (0.0, 0))
+        # all bf16 GEMMs of one denoiser forward (hoisted basis): 8 x (in_proj + out_proj + FFN) + motion_dec + row-0 q/o
         S = 3 * self.clips
         per_fwd = S * (8 * (174.6e6 + 58.2e6 + 465.6e6) + 32.8e6)
-        n_gemm = 8 * 4 + 2 + 8 * 2          # big GEMMs + motion_dec + the row-0 q/out projections
-        flops_per_launch = per_fwd / n_gemm
-        ach = flops_per_launch / (kernel_ms * 1e-3) / 1e12
-        pk = peaks.get('bf16_tflops_sustained', peaks['bf16_tflops'])
-        return dict(bound='tensor', kernel=self.kernel, achieved=ach, peak=pk, unit='TFLOP/s', frac=ach / pk,
-                    traffic=None, peak_source=peaks['_source'] + ' (sustained cuBLAS bf16)',
-                    algorithmic_flops_per_launch=flops_per_launch, launches_per_forward=n_gemm, kernel_ms=kernel_ms)
+        n_fwd = max(1, cls_n // 50)
+        return dict(bound='tensor', kernel=self.kernel + ' (tcgen05 bf16, bias+GELU epilogue)', achieved=ach, peak=pk,
+                    unit='TFLOP/s', frac=ach / pk,
+                    traffic=52.4e6 if self.clips == 64 else None,     # dram read+write per launch, ncu --set full: profiles/r01_gemm_ff1_ncu.txt
+                    peak_source=peaks['_source'] + ' (sustained cuBLAS bf16)', algorithmic_flops_per_launch=flops,
+                    kernel_ms=kernel_ms, timing='CUDA events around each launch on its stream, eager steps (msmd_profile_*)',
+                    gemm_class=dict(launches_per_forward=50, ms_per_forward=cls_ms / n_fwd,
+                                    tflops=per_fwd / (cls_ms / n_fwd * 1e-3) / 1e12 if cls_ms else None,
+                                    note='event timing adds ~5 us per launch; the 16 row-0 / motion_dec GEMMs are launch-bound'))
 
     def cpu_reference(self, seconds=15.0):
         """oracle port of the sampler (oracle/denoiser.py) on the host cores: a bounded number of sampling

@@ -162,6 +162,26 @@ int msmd_sample_window(msmd_model* m, const float* x_T, const float* z, uint64_t
                        float scale0, float scale1, float flexibility, int t_start, int n_steps,
                        float* x_out, float* traj, void* stream);
 
+/* Optional extras of the sampling loop.
+ *   dynamic thresholding (model.py:396-402): per sequence, clamp the network output to +-s with
+ *     s = clamp(quantile(|x0_hat[:, -L:]|, dt_ratio), dt_min, dt_max)   (torch.quantile, 'linear');
+ *   separate outputs of MSMD.sample_separate (model.py:442-651, alpah_t_modification = None):
+ *     target_dynamic [NX,L,dm] (CFG-combined dynamic part of the last executed step),
+ *     cumulative_static [NX,L,dm] (sum over steps of c1(t) * CFG-combined static part; zeroed by the call),
+ *     alpha_traj [n_steps,NX,L,n_basis] (CFG-combined alphas, first executed step first).
+ * Any output pointer may be NULL. */
+typedef struct {
+  int use_dynamic_threshold;
+  float dt_ratio, dt_min, dt_max;
+  float* target_dynamic;
+  float* cumulative_static;
+  float* alpha_traj;
+} msmd_sample_extras;
+
+int msmd_sample_window_ex(msmd_model* m, const float* x_T, const float* z, uint64_t seed, int cfg_independent,
+                          float scale0, float scale1, float flexibility, int t_start, int n_steps,
+                          float* x_out, float* traj, const msmd_sample_extras* extras, void* stream);
+
 /* ------------------------------------------------------------------------- *
  * Style encoder — style_encoder.py:119-213 (StyleEncoder_VAE2.forward / .sample)
  * motion [N,L,d_in] -> mu, logvar [N,d_style]; style = mu + eps * exp(0.5 logvar) with the

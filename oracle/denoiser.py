@@ -159,12 +159,15 @@ def cfg_entries(sd, cfg, audio_feat, shape_feat, style_feat, cfg_mode, cfg_cond)
 
 def sample(sd, cfg, audio_feat, shape_feat, style_feat, prev_motion=None, prev_audio=None, x_T=None,
            z=None, indicator=None, cfg_mode=None, cfg_cond=None, cfg_scale=1.15, flexibility=0,
-           ret_traj=False, n_steps=None, denoise_fn=None):
+           ret_traj=False, n_steps=None, denoise_fn=None, dynamic_threshold=None, separate=False):
     """model.py:282-440 with externally supplied noise.
 
     z: [T+1, N, L, 67] indexed by t (z[t] used at step t > 1; zeros at t == 1), or None -> torch.randn.
     n_steps (< T) stops early after that many steps (tests); returns the state reached.
     Returns (x, x_T, audio_feat) like the reference; with ret_traj a dict {t: x_t}.
+    dynamic_threshold = (ratio, min, max): per-sequence quantile clamp of the network output (model.py:396-402).
+    separate=True follows MSMD.sample_separate (model.py:442-651, alpah_t_modification=None) and returns
+    (x, x_T, audio_feat, target_dynamic, cumulative_static, alpha_traj[T_run*N, L, n_basis]).
     """
     N = audio_feat.shape[0]
     sched = {k[len('diffusion_sched.'):]: v for k, v in sd.items() if k.startswith('diffusion_sched.')}
@@ -197,7 +200,9 @@ def sample(sd, cfg, audio_feat, shape_feat, style_feat, prev_motion=None, prev_a
     pa = torch.cat([prev_audio] * E, 0)
     ind = torch.cat([indicator] * E, 0) if indicator is not None else None
     st = torch.cat([style_feat] * E, 0)                        # real style for every entry (model.py:374)
-    fn = denoise_fn or (lambda *a: denoiser_forward(sd, cfg, *a))
+    fn = denoise_fn or (lambda *a: denoiser_forward(sd, cfg, *a, keep_separate=separate))
+    cum_static = torch.zeros_like(x_T)
+    alpha_traj, tgt_dyn = [], None
     x = x_T
     traj = {T: x_T}
     last = T - n_steps if n_steps else 0
@@ -207,6 +212,17 @@ def sample(sd, cfg, audio_feat, shape_feat, style_feat, prev_motion=None, prev_a
         sigma = sched['sigmas_flex'][t] * flexibility + sched['sigmas_inflex'][t] * (1 - flexibility)
         step = torch.full((N * E,), t, dtype=torch.long)
         res = fn(torch.cat([x] * E, 0), audio_in, person_in, st, pm, pa, step, ind)
+        if separate:
+            dyn, stat_b, alph = res                                     # model.py:557-575
+            face = torch.einsum('nlb,nbc->nlc', alph, stat_b[:, :, :-3])
+            pose = stat_b[:, :, -3:].sum(1, keepdim=True).expand(-1, dyn.shape[1], -1)
+            stat = torch.cat([face, pose], -1)
+            res = dyn + stat
+        if dynamic_threshold:                                          # model.py:396-402 / :579-585
+            q, lo, hi = dynamic_threshold
+            a = res[:, -cfg.n_motions:].reshape(N * E, -1).abs()
+            thr = torch.clamp(torch.quantile(a, q, dim=1), min=lo, max=hi)[:, None, None]
+            res = torch.clamp(res, min=-thr, max=thr)
         r = [c[:, -cfg.n_motions:].clone() for c in res.chunk(E)]
         # CFG combine.  The reference accumulates in place through a VIEW of results[0]
         # (model.py:407-417), so wherever it reads results[0] it sees the running target:
@@ -218,6 +234,15 @@ def sample(sd, cfg, audio_feat, shape_feat, style_feat, prev_motion=None, prev_a
             if cfg_mode not in ('independent', 'incremental'):
                 raise NotImplementedError(f'Unknown cfg_mode {cfg_mode}')
             tgt = tgt + cfg_scale[i] * (r[i + 1] - ref_i)
+        if separate:   # the same (aliased) CFG recursion on the dynamic part, the static part and the alphas
+            def combine(parts):
+                parts = [c[:, -cfg.n_motions:] for c in parts]
+                acc = parts[0]
+                for i in range(E - 1):
+                    ref_i = acc if (cfg_mode == 'independent' or i == 0) else parts[i]
+                    acc = acc + cfg_scale[i] * (parts[i + 1] - ref_i)
+                return acc
+            tgt_dyn, tgt_stat, tgt_alpha = combine(dyn.chunk(E)), combine(stat.chunk(E)), combine(alph.chunk(E))
         if cfg.target == 'noise':
             c0 = 1 / torch.sqrt(alpha)
             c1 = (1 - alpha) / torch.sqrt(1 - ab)
@@ -226,9 +251,14 @@ def sample(sd, cfg, audio_feat, shape_feat, style_feat, prev_motion=None, prev_a
             c0 = (1 - ab_prev) * torch.sqrt(alpha) / (1 - ab)
             c1 = (1 - alpha) * torch.sqrt(ab_prev) / (1 - ab)
             x = c0 * x + c1 * tgt + sigma * zt
+        if separate:
+            cum_static = cum_static + c1 * tgt_stat                     # model.py:631 / :637
+            alpha_traj.append(tgt_alpha)
         traj[t - 1] = x
     if ret_traj:
         return traj, x_T, audio_feat
+    if separate:
+        return x, x_T, audio_feat, tgt_dyn, cum_static, torch.cat(alpha_traj, 0)
     return x, x_T, audio_feat
 
 

@@ -226,8 +226,35 @@ def gen_infer():
     print('infer.npz', out.shape)
 
 
+SEP_GOLD = dict(N=1, T=5, seed=23, weight_seed=1234, scales=[1.4, 1.7], dt=(0.8, 0.5, 2.0))
+
+
+def gen_separate():
+    """MSMD.sample with dynamic thresholding (N=2) and MSMD.sample_separate (N=1: the reference's tiling of the
+    static features, model.py:983-984, only works for batch 1)."""
+    c = SEP_GOLD
+    model, args = ref_msmd(c['weight_seed'], n_diff_steps=c['T'])
+    res = {}
+    i2 = synth.sampler_inputs(2, c['T'], c['seed'] + 1)
+    for mode in ('incremental', 'independent'):
+        with ref_shims.inject_randn_like([i2['z'][t] for t in range(c['T'], 1, -1)]):
+            res['dt_' + mode] = model.sample(i2['audio_feat'], i2['shape'], i2['style'], motion_at_T=i2['x_T'],
+                                             indicator=i2['indicator'], cfg_mode=mode, cfg_scale=list(c['scales']),
+                                             dynamic_threshold=c['dt'])[0].numpy()
+    i = synth.sampler_inputs(c['N'], c['T'], c['seed'])
+    for mode in ('incremental', 'independent'):
+        with ref_shims.inject_randn_like([i['z'][t] for t in range(c['T'], 1, -1)]):
+            w = model.sample_separate(i['audio_feat'], i['shape'], i['style'], motion_at_T=i['x_T'],
+                                      indicator=i['indicator'], cfg_mode=mode, cfg_scale=list(c['scales']),
+                                      dynamic_threshold=c['dt'], return_all_alpha=True)
+        for k, v in zip(('x0', 'dyn', 'stat', 'alpha'), (w[0], w[3], w[4], w[5])):
+            res[f'sep_{mode}_{k}'] = v.numpy()
+    np.savez_compressed(os.path.join(OUT, 'separate.npz'), **res)
+    print('separate.npz', {k: v.shape for k, v in res.items()})
+
+
 SECTIONS = dict(rot=gen_rot, flame=gen_flame, denoiser=gen_denoiser, sampler=gen_sampler, style=gen_style,
-                audio=gen_audio, infer=gen_infer)
+                audio=gen_audio, infer=gen_infer, separate=gen_separate)
 
 
 def main(argv):

@@ -13,6 +13,11 @@ class MsmdConfig(C.Structure):
         'max_seqs', 'precision')]
 
 
+class SampleExtras(C.Structure):
+    _fields_ = [('use_dynamic_threshold', C.c_int), ('dt_ratio', C.c_float), ('dt_min', C.c_float), ('dt_max', C.c_float),
+                ('target_dynamic', C.c_void_p), ('cumulative_static', C.c_void_p), ('alpha_traj', C.c_void_p)]
+
+
 class DenoiserEngine:
     """One engine per (device, capacity).  Weights are (re)loaded when the owning module's parameters change."""
 
@@ -65,7 +70,7 @@ class DenoiserEngine:
         return out
 
     def sample_window(self, x_T, z=None, seed=0, cfg_independent=False, scale0=0.0, scale1=0.0, flexibility=0.0,
-                      t_start=None, n_steps=None, want_traj=False):
+                      t_start=None, n_steps=None, want_traj=False, dynamic_threshold=None, separate=False):
         c = self.cfg
         x_T = x_T.detach().to(self.device, torch.float32).contiguous()
         t_start = c.n_diff_steps if t_start is None else t_start
@@ -76,12 +81,22 @@ class DenoiserEngine:
                 raise ValueError(f'noise must be [T+1, N, L, d] = {(c.n_diff_steps + 1,) + tuple(x_T.shape)}, got {tuple(z.shape)}')
         out = torch.empty_like(x_T)
         traj = torch.zeros((c.n_diff_steps + 1,) + tuple(x_T.shape), device=self.device) if want_traj else None
+        ex = SampleExtras()
+        sep = None
+        if dynamic_threshold:
+            ex.use_dynamic_threshold = 1
+            ex.dt_ratio, ex.dt_min, ex.dt_max = [float(v) for v in dynamic_threshold]
+        if separate:
+            sep = (torch.empty_like(x_T), torch.empty_like(x_T),
+                   torch.empty((n_steps,) + tuple(x_T.shape[:2]) + (c.n_basis,), device=self.device))
+            ex.target_dynamic, ex.cumulative_static, ex.alpha_traj = [t.data_ptr() for t in sep]
         with torch.cuda.device(self.device):
-            _lib.check(_lib.lib().msmd_sample_window(self._h, _lib.dev_ptr(x_T), _lib.dev_ptr(z), C.c_uint64(seed),
-                                                     int(cfg_independent), float(scale0), float(scale1),
-                                                     float(flexibility), int(t_start), int(n_steps),
-                                                     _lib.dev_ptr(out), _lib.dev_ptr(traj), _lib.stream_ptr()))
-        return out, traj
+            _lib.check(_lib.lib().msmd_sample_window_ex(self._h, _lib.dev_ptr(x_T), _lib.dev_ptr(z), C.c_uint64(seed),
+                                                        int(cfg_independent), float(scale0), float(scale1),
+                                                        float(flexibility), int(t_start), int(n_steps),
+                                                        _lib.dev_ptr(out), _lib.dev_ptr(traj), C.byref(ex),
+                                                        _lib.stream_ptr()))
+        return (out, traj, sep) if separate else (out, traj)
 
     def __del__(self):
         try:

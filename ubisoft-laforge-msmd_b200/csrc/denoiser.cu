@@ -56,7 +56,7 @@ struct msmd_model {
        *q0 = nullptr, *ctx0 = nullptr;
   bf16 *y = nullptr, *y0 = nullptr;
   float *dec2 = nullptr, *pp = nullptr, *pmproj = nullptr, *stat = nullptr,
-        *hid = nullptr, *xbuf = nullptr, *mixed = nullptr;
+        *hid = nullptr, *xbuf = nullptr, *mixed = nullptr, *thr = nullptr;
   int* steps = nullptr;
   // window state
   int S = 0, NX = 0, E = 0;
@@ -176,6 +176,7 @@ extern "C" int msmd_create(const msmd_config* cfg, int device, msmd_model** out)
   A(&m->mem, S * (T - 1) * d); A(&m->x0c, S * d); A(&m->q0, S * d); A(&m->ctx0, S * d);
   A(&m->y, M * d); A(&m->y0, S * d); A(&m->dec2, M * m->ldd); A(&m->pp, S * d);
   A(&m->pmproj, S * c.n_prev_motions * d); A(&m->stat, S * c.n_basis * c.motion_dim); A(&m->hid, S * d);
+  A(&m->thr, S);
   A(&m->xbuf, S * c.n_motions * c.motion_dim); A(&m->mixed, S * (T - 1) * c.motion_dim); A(&m->steps, S);
   for (auto& w : m->L) { A(&w.kv, S * (T - 1) * 2 * d); A(&w.ca, S * (T - 1) * d); }
   if (rc) { msmd_destroy(m); return rc; }
@@ -349,6 +350,13 @@ extern "C" int msmd_denoise(msmd_model* m, const float* motion, const int64_t* s
 extern "C" int msmd_sample_window(msmd_model* m, const float* x_T, const float* z, uint64_t seed, int cfg_independent,
                                   float scale0, float scale1, float flexibility, int t_start, int n_steps,
                                   float* x_out, float* traj, void* stream) {
+  return msmd_sample_window_ex(m, x_T, z, seed, cfg_independent, scale0, scale1, flexibility, t_start, n_steps, x_out,
+                               traj, nullptr, stream);
+}
+
+extern "C" int msmd_sample_window_ex(msmd_model* m, const float* x_T, const float* z, uint64_t seed, int cfg_independent,
+                                     float scale0, float scale1, float flexibility, int t_start, int n_steps,
+                                     float* x_out, float* traj, const msmd_sample_extras* ex, void* stream) {
   MSMD_REQUIRE(m && x_T && x_out, "msmd_sample_window: null argument");
   if (!m->window) { set_error("msmd_sample_window: call msmd_window_begin first"); return MSMD_ERR_STATE; }
   const msmd_config& c = m->c;
@@ -367,10 +375,24 @@ extern "C" int msmd_sample_window(msmd_model* m, const float* x_T, const float* 
   up.scale0 = scale0; up.scale1 = scale1; up.flexibility = flexibility; up.seed = seed;
   up.NX = m->NX; up.E = m->E; up.T = m->T; up.L = c.n_motions; up.Lp = c.n_prev_motions; up.dm = c.motion_dim;
   up.nb = c.n_basis; up.ldd = m->ldd; up.cfg_independent = cfg_independent; up.target_noise = c.target_noise;
+  up.thr = nullptr; up.tgt_dyn = nullptr; up.cum_static = nullptr; up.alpha_traj = nullptr; up.t_start = t_start;
+  bool use_dt = false;
+  float dt_ratio = 0.f, dt_min = 0.f, dt_max = 0.f;
+  if (ex) {
+    use_dt = ex->use_dynamic_threshold != 0;
+    dt_ratio = ex->dt_ratio; dt_min = ex->dt_min; dt_max = ex->dt_max;
+    MSMD_REQUIRE(!use_dt || (dt_ratio >= 0.f && dt_ratio <= 1.f), "quantile() q values must be in the range [0, 1]");
+    if (use_dt) up.thr = m->thr;
+    up.tgt_dyn = ex->target_dynamic; up.cum_static = ex->cumulative_static; up.alpha_traj = ex->alpha_traj;
+    if (up.cum_static) MSMD_CHECK_CUDA(cudaMemsetAsync(up.cum_static, 0, n_el * 4, st));
+  }
 
   auto one_step = [&](cudaStream_t s) -> int {
     int r;
     if ((r = run_forward(m, m->xbuf, s))) return r;
+    if (use_dt && (r = threshold_launch(m->dec2, m->stat, m->thr, m->S, m->T, c.n_motions, c.n_prev_motions, c.motion_dim,
+                                        c.n_basis, m->ldd, dt_ratio, dt_min, dt_max, s)))
+      return r;
     if ((r = update_launch(up, s))) return r;
     return steps_advance(m->steps, m->S, s);
   };

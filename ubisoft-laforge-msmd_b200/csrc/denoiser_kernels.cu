@@ -646,14 +646,16 @@ __device__ __forceinline__ float philox_normal(unsigned long long seed, uint32_t
   return sqrtf(-2.0f * __logf(u1)) * __cosf(6.283185307179586f * u2);
 }
 
-__device__ __forceinline__ float mixed_target(const UpdateParams& p, int s, int l, int c) {
-  // model.py:964-995: dynamic + sum_b alpha_b * static_b (face dims) / sum_b static_b (last 3 dims, unweighted)
-  const float* row = p.dec + ((int64_t)s * p.T + 1 + p.Lp + l) * p.ldd;
-  const float* st = p.stat + (int64_t)s * p.nb * p.dm;
-  float v = row[c];
-  const bool face = c < p.dm - 3;
-  for (int b = 0; b < p.nb; ++b) v += (face ? row[p.dm + b] : 1.0f) * st[b * p.dm + c];
-  return v;
+// model.py:964-995: dynamic + sum_b alpha_b * static_b (face dims) / sum_b static_b (last 3 dims, unweighted)
+__device__ __forceinline__ void split_target(const float* dec, const float* stat, int T, int Lp, int dm, int nb, int ldd,
+                                             int s, int l, int c, float& dyn, float& sta) {
+  const float* row = dec + ((int64_t)s * T + 1 + Lp + l) * ldd;
+  const float* st = stat + (int64_t)s * nb * dm;
+  dyn = row[c];
+  const bool face = c < dm - 3;
+  float v = 0.f;
+  for (int b = 0; b < nb; ++b) v += (face ? row[dm + b] : 1.0f) * st[b * dm + c];
+  sta = v;
 }
 
 __global__ void __launch_bounds__(256) update_kernel(UpdateParams p) {
@@ -661,7 +663,7 @@ __global__ void __launch_bounds__(256) update_kernel(UpdateParams p) {
   griddep_wait();
   const int64_t n_el = (int64_t)p.NX * p.L * p.dm;
   const int t = p.steps[0];
-  // model.py:383-386, :421-428 — 0-dim fp32 tensor arithmetic, same operation order
+  // model.py:383-386, :421-428 - 0-dim fp32 tensor arithmetic, same operation order
   const float alpha = p.alphas[t], ab = p.alpha_bars[t], abp = p.alpha_bars[t - 1];
   const float sigma = p.sig_flex[t] * p.flexibility + p.sig_inflex[t] * (1.0f - p.flexibility);
   float c0, c1;
@@ -672,19 +674,30 @@ __global__ void __launch_bounds__(256) update_kernel(UpdateParams p) {
     c0 = (1.0f - abp) * sqrtf(alpha) / (1.0f - ab);
     c1 = (1.0f - alpha) * sqrtf(abp) / (1.0f - ab);
   }
+  const bool sep = p.tgt_dyn != nullptr || p.cum_static != nullptr;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_el; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % p.dm);
     const int l = (int)((i / p.dm) % p.L);
     const int n = (int)(i / ((int64_t)p.dm * p.L));
     // CFG combine (model.py:404-417); results[0] is updated in place through a view, so 'independent'
-    // subtracts the running target
-    float tgt = mixed_target(p, n, l, c);
-    float prev = tgt;
-    for (int e = 1; e < p.E; ++e) {
-      const float r = mixed_target(p, e * p.NX + n, l, c);
-      const float ref = (p.cfg_independent || e == 1) ? tgt : prev;
-      tgt = tgt + (e == 1 ? p.scale0 : p.scale1) * (r - ref);
-      prev = r;
+    // subtracts the running target.  The same recursion runs on the dynamic / static parts
+    // (model.py:603-626) when the separate outputs are requested.
+    float tgt = 0.f, prev = 0.f, td = 0.f, pd = 0.f, ts = 0.f, psv = 0.f;
+    for (int e = 0; e < p.E; ++e) {
+      const int s = e * p.NX + n;
+      float dyn, sta;
+      split_target(p.dec, p.stat, p.T, p.Lp, p.dm, p.nb, p.ldd, s, l, c, dyn, sta);
+      float r = dyn + sta;
+      if (p.thr) { const float th = p.thr[s]; r = fminf(fmaxf(r, -th), th); }
+      if (e == 0) {
+        tgt = r; td = dyn; ts = sta;
+      } else {
+        const float sc = (e == 1) ? p.scale0 : p.scale1;
+        const bool run = p.cfg_independent || e == 1;
+        tgt = tgt + sc * (r - (run ? tgt : prev));
+        if (sep) { td = td + sc * (dyn - (run ? td : pd)); ts = ts + sc * (sta - (run ? ts : psv)); }
+      }
+      prev = r; pd = dyn; psv = sta;
     }
     float zt = 0.f;
     if (t > 1) zt = p.z ? p.z[(int64_t)t * n_el + i] : philox_normal(p.seed, (uint32_t)t, (uint32_t)i);
@@ -692,8 +705,83 @@ __global__ void __launch_bounds__(256) update_kernel(UpdateParams p) {
     const float xn = p.target_noise ? (c0 * (xo - c1 * tgt) + sigma * zt) : (c0 * xo + c1 * tgt + sigma * zt);
     p.x[i] = xn;
     if (p.traj) p.traj[(int64_t)(t - 1) * n_el + i] = xn;
+    if (p.tgt_dyn) p.tgt_dyn[i] = td;
+    if (p.cum_static) p.cum_static[i] += c1 * ts;
+    if (p.alpha_traj && c < p.nb) {   // alphas: columns dm..dm+nb-1 of the decoder output, same CFG recursion
+      float ta = 0.f, pa = 0.f;
+      for (int e = 0; e < p.E; ++e) {
+        const float a = p.dec[((int64_t)(e * p.NX + n) * p.T + 1 + p.Lp + l) * p.ldd + p.dm + c];
+        if (e == 0) ta = a;
+        else ta = ta + ((e == 1) ? p.scale0 : p.scale1) * (a - ((p.cfg_independent || e == 1) ? ta : pa));
+        pa = a;
+      }
+      p.alpha_traj[(((int64_t)(p.t_start - t) * p.NX + n) * p.L + l) * p.nb + c] = ta;
+    }
   }
 }
+
+// Dynamic thresholding (model.py:396-402): one CTA per sequence; |x0_hat| of the L motion rows in shared memory,
+// exact k-th order statistics by 4-pass radix select on the float bit patterns, linear interpolation like
+// torch.quantile(..., interpolation='linear').
+__global__ void __launch_bounds__(1024) threshold_kernel(const float* __restrict__ dec, const float* __restrict__ stat,
+                                                         float* __restrict__ thr, int T, int L, int Lp, int dm, int nb,
+                                                         int ldd, float ratio, float lo, float hi) {
+  extern __shared__ uint32_t keys[];   // [L*dm] then hist[256], sel[4]
+  const int n = L * dm;
+  uint32_t* hist = keys + n;
+  uint32_t* sel = hist + 256;
+  const int s = blockIdx.x, tid = threadIdx.x;
+  for (int i = tid; i < n; i += blockDim.x) {
+    float dyn, sta;
+    split_target(dec, stat, T, Lp, dm, nb, ldd, s, i / dm, i % dm, dyn, sta);
+    keys[i] = __float_as_uint(fabsf(dyn + sta));
+  }
+  const float pos = ratio * (float)(n - 1);
+  const int k_lo = (int)floorf(pos), k_hi = (int)ceilf(pos);
+  float v[2];
+  for (int which = 0; which < 2; ++which) {
+    int k = which == 0 ? k_lo : k_hi;
+    uint32_t prefix = 0, mask = 0;
+    for (int pass = 3; pass >= 0; --pass) {
+      for (int i = tid; i < 256; i += blockDim.x) hist[i] = 0;
+      __syncthreads();
+      for (int i = tid; i < n; i += blockDim.x) {
+        const uint32_t key = keys[i];
+        if ((key & mask) == prefix) atomicAdd(&hist[(key >> (8 * pass)) & 255u], 1u);
+      }
+      __syncthreads();
+      if (tid == 0) {
+        uint32_t cum = 0, b = 0;
+        for (; b < 256; ++b) {
+          if (cum + hist[b] > (uint32_t)k) break;
+          cum += hist[b];
+        }
+        sel[0] = b; sel[1] = cum;
+      }
+      __syncthreads();
+      prefix |= sel[0] << (8 * pass);
+      mask |= 255u << (8 * pass);
+      k -= (int)sel[1];
+      __syncthreads();
+    }
+    v[which] = __uint_as_float(prefix);
+  }
+  if (tid == 0) {
+    const float w = pos - (float)k_lo;
+    const float q = v[0] + w * (v[1] - v[0]);     // torch.lerp form
+    thr[s] = fminf(fmaxf(q, lo), hi);
+  }
+}
+int threshold_launch(const float* dec, const float* stat, float* thr, int S, int T, int L, int Lp, int dm, int nb, int ldd,
+                     float ratio, float lo, float hi, cudaStream_t st) {
+  MSMD_REQUIRE(ratio >= 0.f && ratio <= 1.f, "quantile() q values must be in the range [0, 1] (got %f)", ratio);
+  const size_t smem = ((size_t)L * dm + 256 + 4) * sizeof(uint32_t);
+  MSMD_REQUIRE(smem <= 48 * 1024, "threshold: %d values per sequence exceed the shared-memory tile", L * dm);
+  threshold_kernel<<<S, 1024, smem, st>>>(dec, stat, thr, T, L, Lp, dm, nb, ldd, ratio, lo, hi);
+  MSMD_CHECK_LAUNCH();
+  return MSMD_OK;
+}
+
 int update_launch(const UpdateParams& p, cudaStream_t st) {
   const int64_t n = (int64_t)p.NX * p.L * p.dm;
   ProfileScope prof("update", st);

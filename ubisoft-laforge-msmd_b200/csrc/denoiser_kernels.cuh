@@ -74,7 +74,17 @@ struct UpdateParams {
   unsigned long long seed;
   int NX, E, T, L, Lp, dm, nb, ldd;
   int cfg_independent, target_noise;
+  // optional (msmd_sample_extras): dynamic thresholding (model.py:396-402) and the separate outputs of
+  // MSMD.sample_separate (model.py:442-651)
+  const float* thr;       // [S] per-sequence clamp of the network output, or null
+  float* tgt_dyn;         // [NX, L, dm] CFG-combined dynamic part of the LAST executed step, or null
+  float* cum_static;      // [NX, L, dm] += c1 * CFG-combined static part, or null
+  float* alpha_traj;      // [n_steps, NX, L, nb] CFG-combined alphas per executed step (index t_start - t), or null
+  int t_start;
 };
+// per-sequence threshold s = clamp(quantile(|x0_hat[:, -L:]|, ratio), lo, hi) -> thr[S] (torch.quantile 'linear')
+int threshold_launch(const float* dec, const float* stat, float* thr, int S, int T, int L, int Lp, int dm, int nb, int ldd,
+                     float ratio, float lo, float hi, cudaStream_t st);
 int update_launch(const UpdateParams& p, cudaStream_t st);
 int steps_set(int* steps, int S, int value, cudaStream_t st);
 int steps_advance(int* steps, int S, cudaStream_t st);

@@ -244,13 +244,11 @@ class MSMD(nn.Module, _EngineOwner):
     @torch.no_grad()
     def sample(self, audio_or_feat, shape_feat, style_feat=None, prev_motion_feat=None, prev_audio_feat=None,
                motion_at_T=None, indicator=None, cfg_mode=None, cfg_cond=None, cfg_scale=1.15, flexibility=0,
-               dynamic_threshold=None, ret_traj=False, noise=None, n_steps=None, t_start=None):
+               dynamic_threshold=None, ret_traj=False, noise=None, n_steps=None, t_start=None, _separate=False):
         """model.py:282-440.  Extra keyword arguments (not in the reference): ``noise`` = externally supplied
         z tensor [T+1, N, L, 67] indexed by step t (default: in-kernel Philox seeded from torch's generator);
         ``t_start`` / ``n_steps`` = start at step t_start (motion_at_T is then x_{t_start}) and run n steps
         (teacher-forced parity tests)."""
-        if dynamic_threshold:
-            raise _lib.MsmdError('msmd_b200: dynamic thresholding (model.py:396-402) is not built yet; pass None')
         N = audio_or_feat.shape[0]
         dev = self.device
         cfg_mode = self.cfg_mode if cfg_mode is None else cfg_mode
@@ -315,8 +313,12 @@ class MSMD(nn.Module, _EngineOwner):
         s0 = float(cfg_scale[0]) if E > 1 else 0.0
         s1 = float(cfg_scale[1]) if E > 2 else 0.0
         T = t_start or self.diffusion_sched.num_steps
-        x0, traj = eng.sample_window(motion_at_T, noise, seed, cfg_mode == 'independent', s0, s1, flexibility,
-                                     t_start=T, n_steps=n_steps, want_traj=ret_traj)
+        res = eng.sample_window(motion_at_T, noise, seed, cfg_mode == 'independent', s0, s1, flexibility,
+                                t_start=T, n_steps=n_steps, want_traj=ret_traj, dynamic_threshold=dynamic_threshold,
+                                separate=_separate)
+        x0, traj = res[0], res[1]
+        if _separate and not ret_traj:
+            return x0, motion_at_T, audio_feat, res[2]
         if ret_traj:
             last = T - (n_steps or T)
             out = {T: motion_at_T.cpu()}
@@ -324,3 +326,26 @@ class MSMD(nn.Module, _EngineOwner):
             out[last] = traj[last]
             return out, motion_at_T, audio_feat
         return x0, motion_at_T, audio_feat
+
+
+def _sample_separate(self, audio_or_feat, shape_feat, style_feat=None, prev_motion_feat=None, prev_audio_feat=None,
+                     motion_at_T=None, indicator=None, cfg_mode=None, cfg_cond=None, cfg_scale=1.15, flexibility=0,
+                     dynamic_threshold=None, ret_traj=False, alpah_t_modification=None, return_all_alpha=False,
+                     noise=None, n_steps=None):
+    """model.py:442-651.  Same loop as ``sample`` plus the decomposition outputs:
+    (x0, x_T, audio_feat, target_dynamic, cumulative_static, alpha) with alpha = all steps concatenated along
+    dim 0 (return_all_alpha) or the last step's [N, L, n_basis].  ``alpah_t_modification`` (a Python callback on
+    the alphas of every step) cannot run inside the fused loop and must be None."""
+    if alpah_t_modification is not None:
+        raise _lib.MsmdError('msmd_b200: alpah_t_modification callbacks are not supported by the fused sampler')
+    out = self.sample(audio_or_feat, shape_feat, style_feat, prev_motion_feat, prev_audio_feat, motion_at_T, indicator,
+                      cfg_mode, cfg_cond, cfg_scale, flexibility, dynamic_threshold, ret_traj, noise=noise,
+                      n_steps=n_steps, _separate=True)
+    if ret_traj:
+        return out
+    x0, x_T, audio_feat, (tgt_dyn, cum_static, alpha_traj) = out
+    alpha = alpha_traj.reshape(-1, *alpha_traj.shape[2:]) if return_all_alpha else alpha_traj[-1]
+    return x0, x_T, audio_feat, tgt_dyn, cum_static, alpha
+
+
+MSMD.sample_separate = torch.no_grad()(_sample_separate)
