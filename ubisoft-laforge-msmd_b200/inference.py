@@ -66,3 +66,24 @@ def infer_coeffs(model, args, audio, shape_coef, audio_unit, style_feats=None, n
     return infer_coeffs_batched(model, args, audio_feat.expand(n_repetitions, -1, -1), rep(shape_coef), style,
                                 clip_len=total - max(n_padding_frames, 0), cfg_mode=cfg_mode, cfg_cond=cfg_cond,
                                 cfg_scale=cfg_scale, dynamic_threshold=dynamic_threshold)
+
+
+def load_model(model_root: str, model_name: str, iter_num: str, device='cuda'):
+    """inference.py:85-103: <model_root>/DPT/<model_name>/{args.json, checkpoints/iter_<iter_num>.pt} ->
+    (model, style_encoder, args).  The checkpoint's 'model' / 'style_enc' state_dicts load unchanged
+    (same keys and shapes as the reference modules)."""
+    import os
+    from pathlib import Path
+    from .model import get_diffusion_model
+    from .style_encoder import get_style_encoder
+    from .utils.model_common import load_args
+    exp = Path(os.path.join(model_root, "DPT", model_name))
+    model_args = load_args(exp)
+    model = get_diffusion_model(model_args, device)
+    ckpt = torch.load(exp / "checkpoints" / f"iter_{iter_num}.pt", map_location=device)
+    style_enc = get_style_encoder(model_args, model_args.style_enc_model_style)
+    style_enc.load_state_dict(ckpt['style_enc'])
+    style_enc.to(device).eval()
+    model.load_state_dict(ckpt['model'])
+    model.eval()
+    return model, style_enc, model_args

@@ -43,3 +43,44 @@ def pad_audio(audio, audio_unit=320, pad_threshold=80):
         if side_len % 2 > 0:
             audio = F.pad(audio, (1, 1), mode='replicate')
     return audio
+
+
+# ---- args.json / checkpoint glue (model_common.py:9-81): host-side only, same file layout ----
+def save_args(args, save_dir):
+    """model_common.py:9-27: vars(args) -> <save_dir>/args.json, dropping None / 'None' entries and
+    stringifying paths."""
+    import json
+    from pathlib import Path
+    d = {k: (str(v) if isinstance(v, Path) else v) for k, v in vars(args).items() if v is not None and v != 'None'}
+    with open(Path(save_dir) / 'args.json', 'w') as f:
+        json.dump(d, f)
+
+
+def load_args(save_dir):
+    """model_common.py:52-56 / inference.py:80-84."""
+    import argparse
+    import json
+    from pathlib import Path
+    with open(Path(save_dir) / 'args.json', 'r') as f:
+        return argparse.Namespace(**json.load(f))
+
+
+def load_args_with_defaults(save_dir, parser):
+    """model_common.py:29-50: saved values on top of the parser's current defaults."""
+    import argparse
+    import json
+    from pathlib import Path
+    with open(Path(save_dir) / 'args.json', 'r') as f:
+        saved = json.load(f)
+    merged = vars(parser.parse_args([]))
+    merged.update(saved)
+    return argparse.Namespace(**merged)
+
+
+def latest_checkpoint(exp_dir):
+    """model_common.py:72-77: lexicographically last checkpoints/iter_*.pt."""
+    from pathlib import Path
+    files = sorted((Path(exp_dir) / 'checkpoints').glob('iter_*.pt'))
+    if not files:
+        raise ValueError(f'No checkpoints found in {Path(exp_dir) / "checkpoints"}')
+    return files[-1]
