@@ -123,7 +123,10 @@ typedef struct {
   int align_mask_width; /* 1 (the only width with step-invariant cross attention; others unsupported) */
   int target_noise;     /* 0: network predicts the sample (args.target == 'sample'), 1: the noise */
   int max_seqs;         /* capacity in sequences (E * clips); workspaces are sized for it at create */
-  int precision;        /* 0: bf16 tensor-core GEMMs (fp32 accumulate, fp32 LayerNorm/softmax statistics) */
+  int precision;        /* 0: bf16 tensor-core GEMMs (fp32 accumulate, fp32 LayerNorm/softmax statistics);
+                         * 1: fp32-grade only — fp32 activations, 3-pass tf32 tcgen05 GEMMs (error ~1e-6), exact erf GELU;
+                         * 2: both sets of weights/workspaces resident, selectable per call (msmd_denoise_ex) or per
+                         *    step (msmd_sample_extras.precise_last_steps) */
 } msmd_config;
 
 typedef struct msmd_model msmd_model;
@@ -151,6 +154,9 @@ int msmd_window_begin(msmd_model* m, const float* audio, const float* person, co
 /* One forward of the denoising network (model.py:914-996) for module-level parity.
  * Needs msmd_window_begin(..., S, NX=S, E=1).  motion [S,L,dm]; steps [S] int64; out [S,Lp+L,dm]. */
 int msmd_denoise(msmd_model* m, const float* motion, const int64_t* steps, float* out, void* stream);
+/* Same, choosing the arithmetic: precise != 0 runs the fp32-grade path (needs precision >= 1), 0 the bf16 path
+ * (needs precision 0 or 2).  msmd_denoise == msmd_denoise_ex(..., precise = (precision == 1)). */
+int msmd_denoise_ex(msmd_model* m, const float* motion, const int64_t* steps, float* out, int precise, void* stream);
 
 /* Ancestral sampling loop of MSMD.sample (model.py:377-435) for the current window, steps
  * t = t_start .. t_start-n_steps+1, captured once as a CUDA graph and replayed per step.
@@ -176,6 +182,9 @@ typedef struct {
   float* target_dynamic;
   float* cumulative_static;
   float* alpha_traj;
+  int precise_last_steps; /* hybrid schedule (precision 2): steps with t <= precise_last_steps run the fp32-grade
+                           * path, earlier (noisier) steps the bf16 path; < 0 = every step.  Ignored (all steps
+                           * precise) when precision == 1; must be 0 when precision == 0. */
 } msmd_sample_extras;
 
 int msmd_sample_window_ex(msmd_model* m, const float* x_T, const float* z, uint64_t seed, int cfg_independent,

@@ -90,3 +90,102 @@ def test_sampler_free_running_and_graph_replay(built_lib):
     torch.manual_seed(7); b, _, _ = m.sample(i['audio_feat'].cuda(), i['shape'].cuda(), i['style'].cuda(), **kw)
     torch.manual_seed(8); d, _, _ = m.sample(i['audio_feat'].cuda(), i['shape'].cuda(), i['style'].cuda(), **kw)
     assert torch.equal(a, b) and not torch.equal(a, d) and torch.isfinite(a).all()
+
+
+# ---- fp32-grade path (precision='fp32') and the hybrid schedule (precision='hybrid') ----
+# north_star: codes within 1e-5 relative L2 of the fp32 reference in fp32 mode, within 1e-3 per sampling step
+# in bf16 mode.  The fp32-grade path (fp32 activations, 3-pass tf32 tensor-core GEMMs) is held to 1e-5 on the
+# network output and on every teacher-forced step; the hybrid schedule to 1e-3 on every step it runs precisely.
+F32_TOL = 1e-5
+
+
+def _set_precision(m, precision, k=0):
+    m.precision = m.denoising_net.precision = precision
+    m.precise_last_steps = k
+    return m
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'hybrid'])
+def test_denoiser_forward_fp32_grade_matches_golden(built_lib, precision):
+    m, args = make_msmd('cuda')
+    _set_precision(m, precision)
+    i = {k: v.cuda() for k, v in synth.denoiser_inputs(DEN_GOLD['N'], DEN_GOLD['seed']).items()}
+    call = lambda **kw: m.denoising_net(i['motion'], i['audio'], i['person'], i['style'], i['prev_motion'],
+                                        i['prev_audio'], i['step'], i['indicator'], **kw)
+    want = np.load(os.path.join(GOLDEN, 'denoiser.npz'))['out']
+    got = call(precise=True)
+    err = rel_l2(got, want)
+    print(f'denoiser x0_hat rel-L2 ({precision}, fp32-grade path vs fp32 reference):', err)
+    assert got.shape == want.shape and err < F32_TOL
+    if precision == 'hybrid':       # the bf16 path of the same engine is still the bf16 path
+        e16 = rel_l2(call(precise=False), want)
+        assert F32_TOL < e16 < X0_TOL
+    else:
+        with pytest.raises(Exception, match='bf16 path needs'):
+            call(precise=False)
+
+
+def test_precise_needs_precision_mode(built_lib):
+    m, args = make_msmd('cuda')
+    i = {k: v.cuda() for k, v in synth.denoiser_inputs(1, 3).items()}
+    with pytest.raises(Exception, match='precision 1 or 2'):
+        m.denoising_net(i['motion'], i['audio'], i['person'], i['style'], i['prev_motion'], i['prev_audio'],
+                        i['step'], i['indicator'], precise=True)
+    with pytest.raises(ValueError, match='precision must be one of'):
+        _set_precision(m, 'fp64').denoising_net(i['motion'], i['audio'], i['person'], i['style'], i['prev_motion'],
+                                                i['prev_audio'], i['step'], i['indicator'])
+
+
+@pytest.mark.parametrize('mode', ['incremental', 'independent'])
+def test_sampler_fp32_grade_teacher_forced_and_free_running(built_lib, mode):
+    c = SAMP_GOLD
+    m, args = make_msmd('cuda', n_diff_steps=c['T'])
+    _set_precision(m, 'fp32')
+    i = synth.sampler_inputs(c['N'], c['T'], c['seed'])
+    gold = np.load(os.path.join(GOLDEN, 'sampler.npz'))[mode]
+    kw = dict(indicator=i['indicator'].cuda(), cfg_mode=mode, cfg_scale=list(c['scales']), noise=i['z'].cuda())
+    worst = 0.0
+    for t in range(c['T'], 0, -1):
+        x_prev, _, _ = m.sample(i['audio_feat'].cuda(), i['shape'].cuda(), i['style'].cuda(),
+                                motion_at_T=torch.from_numpy(gold[t]).cuda(), t_start=t, n_steps=1, **kw)
+        worst = max(worst, rel_l2(x_prev, gold[t - 1]))
+    print('fp32-grade worst teacher-forced step rel-L2:', worst)
+    assert worst < F32_TOL
+    # free running: all T steps chained, every intermediate state against the fp32 reference trajectory
+    traj, _, _ = m.sample(i['audio_feat'].cuda(), i['shape'].cuda(), i['style'].cuda(), motion_at_T=i['x_T'].cuda(),
+                          ret_traj=True, **kw)
+    errs = [rel_l2(traj[t], gold[t]) for t in range(c['T'], -1, -1)]
+    print('fp32-grade free-running rel-L2 per step:', ['%.1e' % e for e in errs])
+    assert max(errs) < 5 * F32_TOL
+
+
+def test_sampler_hybrid_schedule(built_lib):
+    """precision='hybrid': steps t > k in bf16 (graph replay), t <= k in fp32-grade arithmetic.  k = T equals the
+    fp32 engine bit for bit, k = 0 equals the bf16 engine bit for bit, and a teacher-forced precise step meets the
+    bf16-mode bound of 1e-3 with two orders of margin."""
+    c = SAMP_GOLD
+    T = c['T']
+    i = synth.sampler_inputs(c['N'], T, c['seed'])
+    gold = np.load(os.path.join(GOLDEN, 'sampler.npz'))['incremental']
+    kw = dict(motion_at_T=i['x_T'].cuda(), indicator=i['indicator'].cuda(), cfg_mode='incremental',
+              cfg_scale=list(c['scales']), noise=i['z'].cuda())
+    run = lambda m, **k2: m.sample(i['audio_feat'].cuda(), i['shape'].cuda(), i['style'].cuda(), **kw, **k2)[0]
+    m16, _ = make_msmd('cuda', n_diff_steps=T)
+    m32, _ = make_msmd('cuda', n_diff_steps=T)
+    _set_precision(m32, 'fp32')
+    mh, _ = make_msmd('cuda', n_diff_steps=T)
+    _set_precision(mh, 'hybrid')
+    x16, x32 = run(m16), run(m32)
+    assert torch.equal(run(mh, precise_last_steps=0), x16)
+    assert torch.equal(run(mh, precise_last_steps=T), x32)
+    assert torch.equal(run(mh, precise_last_steps=-1), x32)
+    k = T // 2
+    xh = run(mh, precise_last_steps=k)
+    e16, eh, e32 = rel_l2(x16, gold[0]), rel_l2(xh, gold[0]), rel_l2(x32, gold[0])
+    print(f'final-state rel-L2 vs fp32 reference: bf16 {e16:.2e}, hybrid(k={k}) {eh:.2e}, fp32-grade {e32:.2e}')
+    assert e32 < 5 * F32_TOL and eh <= e16 * 1.05
+    # the module-level default is used when the call does not say
+    mh.precise_last_steps = k
+    assert torch.equal(run(mh), xh)
+    with pytest.raises(Exception, match='precision 2'):
+        m16._eng.sample_window(i['x_T'].cuda(), i['z'].cuda(), precise_last_steps=2)

@@ -15,7 +15,11 @@ class MsmdConfig(C.Structure):
 
 class SampleExtras(C.Structure):
     _fields_ = [('use_dynamic_threshold', C.c_int), ('dt_ratio', C.c_float), ('dt_min', C.c_float), ('dt_max', C.c_float),
-                ('target_dynamic', C.c_void_p), ('cumulative_static', C.c_void_p), ('alpha_traj', C.c_void_p)]
+                ('target_dynamic', C.c_void_p), ('cumulative_static', C.c_void_p), ('alpha_traj', C.c_void_p),
+                ('precise_last_steps', C.c_int)]
+
+
+PRECISIONS = {'bf16': 0, 'fp32': 1, 'hybrid': 2}
 
 
 class DenoiserEngine:
@@ -59,18 +63,23 @@ class DenoiserEngine:
                                                     _lib.stream_ptr()))
         self.S, self.NX, self.E = S, NX, E
 
-    def denoise(self, motion, steps):
+    def denoise(self, motion, steps, precise=None):
+        """precise: None = the engine's native arithmetic (fp32-grade iff precision == 'fp32'); True/False picks
+        the path on a 'hybrid' engine."""
+        if precise is None:
+            precise = self.cfg.precision == 1
         motion = motion.detach().to(self.device, torch.float32).contiguous()
         steps = steps.detach().to(self.device, torch.int64).contiguous()
         c = self.cfg
         out = torch.empty((self.S, c.n_prev_motions + c.n_motions, c.motion_dim), device=self.device)
         with torch.cuda.device(self.device):
-            _lib.check(_lib.lib().msmd_denoise(self._h, _lib.dev_ptr(motion), _lib.dev_ptr(steps, torch.int64),
-                                               _lib.dev_ptr(out), _lib.stream_ptr()))
+            _lib.check(_lib.lib().msmd_denoise_ex(self._h, _lib.dev_ptr(motion), _lib.dev_ptr(steps, torch.int64),
+                                                  _lib.dev_ptr(out), int(bool(precise)), _lib.stream_ptr()))
         return out
 
     def sample_window(self, x_T, z=None, seed=0, cfg_independent=False, scale0=0.0, scale1=0.0, flexibility=0.0,
-                      t_start=None, n_steps=None, want_traj=False, dynamic_threshold=None, separate=False):
+                      t_start=None, n_steps=None, want_traj=False, dynamic_threshold=None, separate=False,
+                      precise_last_steps=0):
         c = self.cfg
         x_T = x_T.detach().to(self.device, torch.float32).contiguous()
         t_start = c.n_diff_steps if t_start is None else t_start
@@ -82,6 +91,7 @@ class DenoiserEngine:
         out = torch.empty_like(x_T)
         traj = torch.zeros((c.n_diff_steps + 1,) + tuple(x_T.shape), device=self.device) if want_traj else None
         ex = SampleExtras()
+        ex.precise_last_steps = int(precise_last_steps)
         sep = None
         if dynamic_threshold:
             ex.use_dynamic_threshold = 1

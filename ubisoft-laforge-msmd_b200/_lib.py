@@ -30,6 +30,7 @@ SIGNATURES = {
     'msmd_load_weights': (_i, [_vp, C.POINTER(C.c_char_p), C.POINTER(_vp), C.POINTER(_i64), _i]),
     'msmd_window_begin': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     'msmd_denoise': (_i, [_vp, _vp, _vp, _vp, _vp]),
+    'msmd_denoise_ex': (_i, [_vp, _vp, _vp, _vp, _i, _vp]),
     'msmd_sample_window': (_i, [_vp, _vp, _vp, C.c_uint64, _i, C.c_float, C.c_float, C.c_float, _i, _i, _vp, _vp, _vp]),
     'msmd_style_create': (_i, [_i, _i, _i, _i, _i, _i, C.POINTER(_vp)]),
     'msmd_style_destroy': (None, [_vp]),

@@ -26,6 +26,11 @@ struct LayerW {
   float *bqkv = nullptr, *bo = nullptr, *bq0 = nullptr, *bkv = nullptr, *bco = nullptr, *b1 = nullptr, *b2 = nullptr;
   float *g1 = nullptr, *be1 = nullptr, *g2 = nullptr, *be2 = nullptr, *g3 = nullptr, *be3 = nullptr;
   bf16 *kv = nullptr, *ca = nullptr;  // per-window caches
+  // fp32-grade path (precision >= 1): tf32 hi/lo splits of the same weights and fp32 caches
+  float *Wqkv_h = nullptr, *Wqkv_l = nullptr, *Wo_h = nullptr, *Wo_l = nullptr, *Wq0_h = nullptr, *Wq0_l = nullptr,
+        *Wkv_h = nullptr, *Wkv_l = nullptr, *Wco_h = nullptr, *Wco_l = nullptr, *W1_h = nullptr, *W1_l = nullptr,
+        *W2_h = nullptr, *W2_l = nullptr;
+  float *kv32 = nullptr, *ca32 = nullptr;
 };
 
 uint16_t f2bf(float f) {  // round-to-nearest-even
@@ -58,6 +63,12 @@ struct msmd_model {
   float *dec2 = nullptr, *pp = nullptr, *pmproj = nullptr, *stat = nullptr,
         *hid = nullptr, *xbuf = nullptr, *mixed = nullptr, *thr = nullptr;
   int* steps = nullptr;
+  // fp32-grade path workspaces
+  float *Wd1_h = nullptr, *Wd1_l = nullptr, *Wd2_h = nullptr, *Wd2_l = nullptr;
+  float *fx = nullptr, *fqkv = nullptr, *fctx = nullptr, *fh = nullptr, *fy = nullptr, *fdec1 = nullptr, *fmem = nullptr,
+        *fx0c = nullptr, *fq0 = nullptr, *fctx0 = nullptr, *fy0 = nullptr, *ws_hi = nullptr, *ws_lo = nullptr;
+  bool f32_ready = false, window32 = false;
+  const float *w_audio = nullptr, *w_prev_audio = nullptr;   // conditioning kept for the lazy fp32 window pass
   // window state
   int S = 0, NX = 0, E = 0;
   const float* indicator = nullptr;
@@ -96,6 +107,85 @@ int gemm(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const float* bi
   d.M = M; d.N = N; d.K = K; d.lda = lda; d.ldw = ldw; d.ldo = ldo; d.ld_aux = ld_aux;
   d.out_f32 = out_f32; d.aux_f32 = 0; d.act = act; d.gelu_heavy = act;
   return gemm_tc_launch(d, st);
+}
+
+int up_split(msmd_model* m, float** hi, float** lo, const float* h, size_t n) {
+  std::vector<float> a(n), b(n);
+  for (size_t i = 0; i < n; ++i) {
+    uint32_t u;
+    memcpy(&u, &h[i], 4);
+    u &= 0xffffe000u;
+    memcpy(&a[i], &u, 4);
+    b[i] = h[i] - a[i];
+  }
+  int rc = up_f32(m, hi, a);
+  return rc ? rc : up_f32(m, lo, b);
+}
+
+// fp32-grade linear: split the activations (tf32 hi + remainder), then the 3-pass tcgen05 GEMM
+int gemm32(msmd_model* m, const float* A, int64_t lda, const float* Wh, const float* Wl, int64_t ldw, const float* bias,
+           float* out, int64_t ldo, int M, int N, int K, int act, cudaStream_t st) {
+  int rc;
+  // the split kernel works on contiguous [M, lda] storage; K <= lda columns are used by the GEMM
+  if ((rc = split_tf32(A, m->ws_hi, m->ws_lo, (int64_t)(M - 1) * lda + K, st))) return rc;
+  GemmDesc d;
+  d.mode = 1; d.A = m->ws_hi; d.A_lo = m->ws_lo; d.W = Wh; d.W_lo = Wl; d.bias = bias; d.out = out;
+  d.M = M; d.N = N; d.K = K; d.lda = lda; d.ldw = ldw; d.ldo = ldo; d.out_f32 = 1; d.aux_f32 = 1; d.act = act;
+  return gemm_tc_launch(d, st);
+}
+
+int window_begin_f32(msmd_model* m, cudaStream_t st);
+
+// fp32-grade forward (same graph of operations as run_forward, fp32 activations, tf32x3 GEMMs)
+int run_forward_f32(msmd_model* m, const float* xrows, cudaStream_t st) {
+  const msmd_config& c = m->c;
+  const int S = m->S, T = m->T, d = c.d_model, M = S * T;
+  int rc;
+  if (!m->window32 && (rc = window_begin_f32(m, st))) return rc;
+  EmbedParams ep;
+  ep.pp = m->pp; ep.temb = m->temb; ep.pmproj = m->pmproj; ep.PE = m->PE; ep.steps = m->steps;
+  ep.x = xrows; ep.indicator = c.use_indicator ? m->indicator : nullptr; ep.WfT = m->WfT; ep.bf = m->bf_;
+  ep.out = nullptr; ep.S = S; ep.NX = m->NX; ep.E = m->E; ep.Lp = c.n_prev_motions; ep.L = c.n_motions; ep.d = d;
+  ep.dm = c.motion_dim;
+  if ((rc = embed_f32_launch(ep, m->fx, st))) return rc;
+  for (int l = 0; l < c.n_layers; ++l) {
+    LayerW& w = m->L[l];
+    if ((rc = gemm32(m, m->fx, d, w.Wqkv_h, w.Wqkv_l, d, w.bqkv, m->fqkv, 3 * d, M, 3 * d, d, 0, st))) return rc;
+    if ((rc = self_attn_f32_launch(m->fqkv, m->fctx, S, T, c.n_heads, st))) return rc;
+    if ((rc = gemm32(m, m->fctx, d, w.Wo_h, w.Wo_l, d, w.bo, m->fy, d, M, d, d, 0, st))) return rc;
+    if ((rc = ln_f32_launch(m->fy, m->fx, w.g1, w.be1, w.ca32, w.g2, w.be2, m->fx, m->fx0c, M, T, st))) return rc;
+    if ((rc = gemm32(m, m->fx0c, d, w.Wq0_h, w.Wq0_l, d, w.bq0, m->fq0, d, S, d, d, 0, st))) return rc;
+    if ((rc = cross_attn_row0_f32_launch(m->fq0, w.kv32, m->fctx0, S, T - 1, c.n_heads, st))) return rc;
+    if ((rc = gemm32(m, m->fctx0, d, w.Wco_h, w.Wco_l, d, w.bco, m->fy0, d, S, d, d, 0, st))) return rc;
+    if ((rc = ln_row0_f32_launch(m->fy0, m->fx0c, w.g2, w.be2, m->fx, S, T, st))) return rc;
+    if ((rc = gemm32(m, m->fx, d, w.W1_h, w.W1_l, d, w.b1, m->fh, c.d_ff, M, c.d_ff, d, 1, st))) return rc;
+    if ((rc = gemm32(m, m->fh, c.d_ff, w.W2_h, w.W2_l, c.d_ff, w.b2, m->fy, d, M, d, c.d_ff, 0, st))) return rc;
+    if ((rc = ln_f32_launch(m->fy, m->fx, w.g3, w.be3, nullptr, nullptr, nullptr, m->fx, nullptr, M, T, st))) return rc;
+  }
+  if ((rc = gemm32(m, m->fx, d, m->Wd1_h, m->Wd1_l, d, m->bd1, m->fdec1, d / 2, M, d / 2, d, 1, st))) return rc;
+  if ((rc = gemm32(m, m->fdec1, d / 2, m->Wd2_h, m->Wd2_l, d / 2, m->bd2, m->dec2, m->ldd, M, c.motion_dim + c.n_basis,
+                   d / 2, 0, st)))
+    return rc;
+  return MSMD_OK;
+}
+
+// per-window caches of the fp32-grade path (built lazily: the hybrid schedule only needs them for its last steps)
+int window_begin_f32(msmd_model* m, cudaStream_t st) {
+  const msmd_config& c = m->c;
+  const int S = m->S, d = c.d_model, Tk = m->T - 1;
+  int rc;
+  if ((rc = build_memory_f32(m->w_prev_audio, m->w_audio, m->fmem, S, c.n_prev_motions, c.n_motions, d, st))) return rc;
+  for (auto& w : m->L) {
+    if ((rc = gemm32(m, m->fmem, d, w.Wkv_h, w.Wkv_l, d, w.bkv, w.kv32, 2 * d, S * Tk, 2 * d, d, 0, st))) return rc;
+    // v half of the kv cache as a strided A operand: row stride 2d, K = d columns starting at column d
+    if ((rc = split_tf32(w.kv32, m->ws_hi, m->ws_lo, (int64_t)S * Tk * 2 * d, st))) return rc;
+    GemmDesc g;
+    g.mode = 1; g.A = m->ws_hi + d; g.A_lo = m->ws_lo + d; g.W = w.Wco_h; g.W_lo = w.Wco_l; g.bias = w.bco; g.out = w.ca32;
+    g.M = S * Tk; g.N = d; g.K = d; g.lda = 2 * d; g.ldw = d; g.ldo = d; g.out_f32 = 1; g.aux_f32 = 1;
+    if ((rc = gemm_tc_launch(g, st))) return rc;
+  }
+  m->window32 = true;
+  return MSMD_OK;
 }
 
 // One forward of the network on the current window context: x rows [NX,L,dm] -> dec2 [M, ldd]
@@ -158,10 +248,7 @@ extern "C" int msmd_create(const msmd_config* cfg, int device, msmd_model** out)
     set_error("msmd_create: align_mask_width=%d: only width 1 (step-invariant cross attention) is implemented", c.align_mask_width);
     return MSMD_ERR_UNSUPPORTED;
   }
-  if (c.precision != 0) {
-    set_error("msmd_create: precision %d not implemented (0 = bf16)", c.precision);
-    return MSMD_ERR_UNSUPPORTED;
-  }
+  MSMD_REQUIRE(c.precision >= 0 && c.precision <= 2, "msmd_create: precision %d (0 bf16, 1 fp32-grade, 2 both/hybrid)", c.precision);
   MSMD_CHECK_CUDA(cudaSetDevice(device));
   msmd_model* m = new msmd_model();
   m->c = c;
@@ -179,6 +266,12 @@ extern "C" int msmd_create(const msmd_config* cfg, int device, msmd_model** out)
   A(&m->thr, S);
   A(&m->xbuf, S * c.n_motions * c.motion_dim); A(&m->mixed, S * (T - 1) * c.motion_dim); A(&m->steps, S);
   for (auto& w : m->L) { A(&w.kv, S * (T - 1) * 2 * d); A(&w.ca, S * (T - 1) * d); }
+  if (c.precision >= 1) {
+    A(&m->fx, M * d); A(&m->fqkv, M * 3 * d); A(&m->fctx, M * d); A(&m->fh, M * c.d_ff); A(&m->fy, M * d);
+    A(&m->fdec1, M * d / 2); A(&m->fmem, S * (T - 1) * d); A(&m->fx0c, S * d); A(&m->fq0, S * d); A(&m->fctx0, S * d);
+    A(&m->fy0, S * d); A(&m->ws_hi, M * c.d_ff); A(&m->ws_lo, M * c.d_ff);
+    for (auto& w : m->L) { A(&w.kv32, S * (T - 1) * 2 * d); A(&w.ca32, S * (T - 1) * d); }
+  }
   if (rc) { msmd_destroy(m); return rc; }
   cudaMemset(m->dec2, 0, M * m->ldd * sizeof(float));
   *out = m;
@@ -220,28 +313,36 @@ extern "C" int msmd_load_weights(msmd_model* m, const char* const* names, const 
   const std::string P = "denoising_net.";
   std::vector<float> h, h2;
   auto F32 = [&](const std::string& key, size_t n_, float** dst) { if (!rc && fetch(key, n_, h)) rc = up_f32(m, dst, h); };
-  auto BF = [&](const std::string& key, size_t n_, bf16** dst) { if (!rc && fetch(key, n_, h)) rc = up_bf16(m, dst, h.data(), n_); };
+  const bool want_bf = c.precision != 1, want_f32 = c.precision >= 1;
+  // a GEMM weight: bf16 copy for the bf16 path and/or tf32 hi/lo split for the fp32-grade path
+  auto put_w = [&](const float* src, size_t n_, bf16** dst, float** hi, float** lo) {
+    if (!rc && want_bf) rc = up_bf16(m, dst, src, n_);
+    if (!rc && want_f32) rc = up_split(m, hi, lo, src, n_);
+  };
+  auto BF = [&](const std::string& key, size_t n_, bf16** dst, float** hi, float** lo) {
+    if (!rc && fetch(key, n_, h)) put_w(h.data(), n_, dst, hi, lo);
+  };
 
   for (int l = 0; l < c.n_layers && !rc; ++l) {
     LayerW& w = m->L[l];
     const std::string q = P + "transformer.layers." + std::to_string(l) + ".";
-    BF(q + "self_attn.in_proj_weight", 3 * d * d, &w.Wqkv);
+    BF(q + "self_attn.in_proj_weight", 3 * d * d, &w.Wqkv, &w.Wqkv_h, &w.Wqkv_l);
     F32(q + "self_attn.in_proj_bias", 3 * d, &w.bqkv);
-    BF(q + "self_attn.out_proj.weight", d * d, &w.Wo);
+    BF(q + "self_attn.out_proj.weight", d * d, &w.Wo, &w.Wo_h, &w.Wo_l);
     F32(q + "self_attn.out_proj.bias", d, &w.bo);
     if (!rc && fetch(q + "multihead_attn.in_proj_weight", 3 * d * d, h)) {  // packed q|k|v (model.py:874 / App. E)
-      rc = up_bf16(m, &w.Wq0, h.data(), d * d);
-      if (!rc) rc = up_bf16(m, &w.Wkv, h.data() + d * d, 2 * d * d);
+      put_w(h.data(), d * d, &w.Wq0, &w.Wq0_h, &w.Wq0_l);
+      put_w(h.data() + d * d, 2 * d * d, &w.Wkv, &w.Wkv_h, &w.Wkv_l);
     }
     if (!rc && fetch(q + "multihead_attn.in_proj_bias", 3 * d, h)) {
       rc = up_f32(m, &w.bq0, std::vector<float>(h.begin(), h.begin() + d));
       if (!rc) rc = up_f32(m, &w.bkv, std::vector<float>(h.begin() + d, h.end()));
     }
-    BF(q + "multihead_attn.out_proj.weight", d * d, &w.Wco);
+    BF(q + "multihead_attn.out_proj.weight", d * d, &w.Wco, &w.Wco_h, &w.Wco_l);
     F32(q + "multihead_attn.out_proj.bias", d, &w.bco);
-    BF(q + "linear1.weight", ff * d, &w.W1);
+    BF(q + "linear1.weight", ff * d, &w.W1, &w.W1_h, &w.W1_l);
     F32(q + "linear1.bias", ff, &w.b1);
-    BF(q + "linear2.weight", d * ff, &w.W2);
+    BF(q + "linear2.weight", d * ff, &w.W2, &w.W2_h, &w.W2_l);
     F32(q + "linear2.bias", d, &w.b2);
     F32(q + "norm1.weight", d, &w.g1); F32(q + "norm1.bias", d, &w.be1);
     F32(q + "norm2.weight", d, &w.g2); F32(q + "norm2.bias", d, &w.be2);
@@ -264,9 +365,9 @@ extern "C" int msmd_load_weights(msmd_model* m, const char* const* names, const 
     F32(q + "0.weight", d * c.d_style, &m->Ws0[b]); F32(q + "0.bias", d, &m->bs0[b]);
     F32(q + "2.weight", dm * d, &m->Ws2[b]); F32(q + "2.bias", dm, &m->bs2[b]);
   }
-  BF(P + "motion_dec.0.weight", (d / 2) * d, &m->Wd1);
+  BF(P + "motion_dec.0.weight", (d / 2) * d, &m->Wd1, &m->Wd1_h, &m->Wd1_l);
   F32(P + "motion_dec.0.bias", d / 2, &m->bd1);
-  BF(P + "motion_dec.2.weight", (dm + c.n_basis) * (d / 2), &m->Wd2);
+  BF(P + "motion_dec.2.weight", (dm + c.n_basis) * (d / 2), &m->Wd2, &m->Wd2_h, &m->Wd2_l);
   if (!rc && fetch(P + "motion_dec.2.bias", dm + c.n_basis, h)) {
     h.resize(m->ldd, 0.f);
     rc = up_f32(m, &m->bd2, h);
@@ -309,8 +410,13 @@ extern "C" int msmd_window_begin(msmd_model* m, const float* audio, const float*
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int d = c.d_model, Tk = m->T - 1, Lp = c.n_prev_motions, dm = c.motion_dim;
   int rc;
-  if ((rc = build_memory_bf16(prev_audio, audio, m->mem, S, Lp, c.n_motions, d, st))) return rc;
+  m->S = S; m->NX = NX; m->E = E;
+  m->w_audio = audio; m->w_prev_audio = prev_audio;
+  m->window32 = false;
+  if (c.precision == 1 && (rc = window_begin_f32(m, st))) return rc;  // precision 2 builds these on first use
+  if (c.precision != 1 && (rc = build_memory_bf16(prev_audio, audio, m->mem, S, Lp, c.n_motions, d, st))) return rc;
   for (auto& w : m->L) {
+    if (c.precision == 1) break;
     // memory K|V projection, then the motion rows' cross-attention output out_proj(v_proj(mem)) (softmax over
     // a single visible key is 1, so the query drops out: SURVEY section 0)
     if ((rc = gemm(m->mem, d, w.Wkv, d, w.bkv, nullptr, 0, w.kv, 2 * d, 0, S * Tk, 2 * d, d, 0, st))) return rc;
@@ -324,7 +430,6 @@ extern "C" int msmd_window_begin(msmd_model* m, const float* audio, const float*
     if ((rc = linear_simt(m->hid, d, m->Ws2[b], d, m->bs2[b], m->stat + b * dm, (int64_t)c.n_basis * dm, S, dm, d, 0, st)))
       return rc;
   }
-  m->S = S; m->NX = NX; m->E = E;
   m->indicator = indicator;
   m->window = true;
   return MSMD_OK;
@@ -335,15 +440,36 @@ __global__ void steps_from_i64_kernel(const int64_t* in, int* out, int S) {
   if (i < S) out[i] = (int)in[i];
 }
 
+namespace {
+int check_precise(const msmd_model* m, int precise, const char* who) {
+  if (precise && m->c.precision == 0) {
+    set_error("%s: the fp32-grade path needs a model created with precision 1 or 2", who);
+    return MSMD_ERR_STATE;
+  }
+  if (!precise && m->c.precision == 1) {
+    set_error("%s: the bf16 path needs a model created with precision 0 or 2", who);
+    return MSMD_ERR_STATE;
+  }
+  return MSMD_OK;
+}
+}  // namespace
+
 extern "C" int msmd_denoise(msmd_model* m, const float* motion, const int64_t* steps, float* out, void* stream) {
+  MSMD_REQUIRE(m, "msmd_denoise: null argument");
+  return msmd_denoise_ex(m, motion, steps, out, m->c.precision == 1, stream);
+}
+
+extern "C" int msmd_denoise_ex(msmd_model* m, const float* motion, const int64_t* steps, float* out, int precise,
+                               void* stream) {
   MSMD_REQUIRE(m && motion && steps && out, "msmd_denoise: null argument");
   if (!m->window) { set_error("msmd_denoise: call msmd_window_begin first"); return MSMD_ERR_STATE; }
   MSMD_REQUIRE(m->E == 1 && m->NX == m->S, "msmd_denoise: window must be opened with NX == S, E == 1");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   steps_from_i64_kernel<<<cdiv(m->S, 256), 256, 0, st>>>(steps, m->steps, m->S);
   MSMD_CHECK_LAUNCH();
-  int rc = run_forward(m, motion, st);
+  int rc = check_precise(m, precise, "msmd_denoise");
   if (rc) return rc;
+  if ((rc = precise ? run_forward_f32(m, motion, st) : run_forward(m, motion, st))) return rc;
   return mix_static_launch(m->dec2, m->stat, out, m->S, m->T, m->c.motion_dim, m->c.n_basis, m->ldd, st);
 }
 
@@ -378,6 +504,12 @@ extern "C" int msmd_sample_window_ex(msmd_model* m, const float* x_T, const floa
   up.thr = nullptr; up.tgt_dyn = nullptr; up.cum_static = nullptr; up.alpha_traj = nullptr; up.t_start = t_start;
   bool use_dt = false;
   float dt_ratio = 0.f, dt_min = 0.f, dt_max = 0.f;
+  int k_precise = c.precision == 1 ? c.n_diff_steps : 0;   // steps with t <= k_precise run the fp32-grade path
+  if (ex && c.precision != 1) {
+    k_precise = ex->precise_last_steps < 0 ? c.n_diff_steps : ex->precise_last_steps;
+    MSMD_REQUIRE(k_precise == 0 || c.precision == 2,
+                 "msmd_sample_window: precise_last_steps needs a model created with precision 2");
+  }
   if (ex) {
     use_dt = ex->use_dynamic_threshold != 0;
     dt_ratio = ex->dt_ratio; dt_min = ex->dt_min; dt_max = ex->dt_max;
@@ -387,9 +519,9 @@ extern "C" int msmd_sample_window_ex(msmd_model* m, const float* x_T, const floa
     if (up.cum_static) MSMD_CHECK_CUDA(cudaMemsetAsync(up.cum_static, 0, n_el * 4, st));
   }
 
-  auto one_step = [&](cudaStream_t s) -> int {
+  auto one_step = [&](cudaStream_t s, bool precise = false) -> int {
     int r;
-    if ((r = run_forward(m, m->xbuf, s))) return r;
+    if ((r = precise ? run_forward_f32(m, m->xbuf, s) : run_forward(m, m->xbuf, s))) return r;
     if (use_dt && (r = threshold_launch(m->dec2, m->stat, m->thr, m->S, m->T, c.n_motions, c.n_prev_motions, c.motion_dim,
                                         c.n_basis, m->ldd, dt_ratio, dt_min, dt_max, s)))
       return r;
@@ -397,6 +529,11 @@ extern "C" int msmd_sample_window_ex(msmd_model* m, const float* x_T, const floa
     return steps_advance(m->steps, m->S, s);
   };
 
+  // executed steps are t = t_start .. t_end; the last n_hi of them (t <= k_precise) run the fp32-grade path,
+  // eagerly: each is ~5x a bf16 step, so launch latency is hidden and a second graph buys nothing
+  const int t_end = t_start - n_steps + 1;
+  const int n_hi = k_precise >= t_start ? n_steps : (k_precise >= t_end ? k_precise - t_end + 1 : 0);
+  n_steps -= n_hi;
   if (profiling_on() || n_steps < 3) {  // event timing cannot live inside a graph: plain launches
     for (int i = 0; i < n_steps; ++i)
       if ((rc = one_step(st))) return rc;
@@ -436,6 +573,8 @@ extern "C" int msmd_sample_window_ex(msmd_model* m, const float* x_T, const floa
       return MSMD_ERR_CUDA;
     }
   }
+  for (int i = 0; i < n_hi; ++i)
+    if ((rc = one_step(st, true))) return rc;
   MSMD_CHECK_CUDA(cudaMemcpyAsync(x_out, m->xbuf, n_el * 4, cudaMemcpyDeviceToDevice, st));
   return MSMD_OK;
 }

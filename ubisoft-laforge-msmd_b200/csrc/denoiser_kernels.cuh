@@ -92,4 +92,15 @@ int steps_advance(int* steps, int S, cudaStream_t st);
 // out[S, T-1... ] : x̂0 per sequence (module-level parity): dyn + static mix for ALL Lp+L rows -> [S, T-1, dm]
 int mix_static_launch(const float* dec, const float* stat, float* out, int S, int T, int dm, int nb, int ldd, cudaStream_t st);
 
+// ---- fp32-grade variants (denoiser_f32.cu) ----
+int embed_f32_launch(const EmbedParams& p, float* out, cudaStream_t st);
+int ln_f32_launch(const float* y, const float* resid, const float* g1, const float* b1, const float* add, const float* g2,
+                  const float* b2, float* out, float* x0, int M, int T, cudaStream_t st);
+int ln_row0_f32_launch(const float* y0, const float* r0, const float* g, const float* b, float* out, int S, int T,
+                       cudaStream_t st);
+int self_attn_f32_launch(const float* qkv, float* ctx, int S, int T, int H, cudaStream_t st);
+int cross_attn_row0_f32_launch(const float* q0, const float* kv, float* ctx0, int S, int Tk, int H, cudaStream_t st);
+int build_memory_f32(const float* prev_audio, const float* audio, float* mem, int S, int Lp, int L, int d, cudaStream_t st);
+int split_tf32(const float* x, float* hi, float* lo, int64_t n, cudaStream_t st);   // gemm_tc.cu
+
 }  // namespace msmd

@@ -11,7 +11,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from ._engine import DenoiserEngine
+from ._engine import DenoiserEngine, PRECISIONS
 from .utils.model_common import PositionalEncoding, enc_dec_mask
 
 
@@ -65,17 +65,25 @@ class DiffusionSchedule(nn.Module):
         return self.sigmas_flex[t] * flexibility + self.sigmas_inflex[t] * (1 - flexibility)
 
 
-def _engine_cfg(net, n_diff_steps, target, max_seqs):
+def _engine_cfg(net, n_diff_steps, target, max_seqs, precision='bf16'):
+    if precision not in PRECISIONS:
+        raise ValueError(f"precision must be one of {sorted(PRECISIONS)}, got {precision!r}")
     return dict(n_motions=net.n_motions, n_prev_motions=net.n_prev_motions, d_model=net.feature_dim,
                 n_heads=net.n_heads, n_layers=net.n_layers, d_ff=net.mlp_ratio * net.feature_dim,
                 d_style=net.style_feat_dim if net.use_style else 0, d_shape=net.shape_feat_dim,
                 motion_dim=net.motion_feat_dim, n_basis=net.num_of_basis, n_diff_steps=n_diff_steps,
                 use_indicator=int(bool(net.use_indicator)), align_mask_width=net.align_mask_width,
-                target_noise=int(target == 'noise'), max_seqs=max_seqs, precision=0)
+                target_noise=int(target == 'noise'), max_seqs=max_seqs, precision=PRECISIONS[precision])
 
 
 class _EngineOwner:
-    """Mixin: lazily creates / grows the CUDA engine and keeps its packed weights in sync with the module."""
+    """Mixin: lazily creates / grows the CUDA engine and keeps its packed weights in sync with the module.
+
+    ``precision`` picks the engine arithmetic: 'bf16' (default; what the reference runs under autocast),
+    'fp32' (fp32 activations + 3-pass tf32 tensor-core GEMMs, ~1e-6 of the fp32 reference) or 'hybrid' (both
+    resident; ``precise_last_steps`` = the sampler's last k steps run in fp32-grade arithmetic)."""
+    precision = 'bf16'
+    precise_last_steps = 0
 
     def _engine_state(self):
         raise NotImplementedError
@@ -83,7 +91,7 @@ class _EngineOwner:
     def _get_engine(self, n_seqs, device):
         cfg_fn, sd_fn = self._engine_state()
         eng = getattr(self, '_eng', None)
-        if eng is None or eng.device != device or eng.cfg.max_seqs < n_seqs:
+        if eng is None or eng.device != device or eng.cfg.max_seqs < n_seqs or eng.cfg.precision != cfg_fn(1)['precision']:
             cap = max(n_seqs, 0 if eng is None else eng.cfg.max_seqs)
             eng = DenoiserEngine(cfg_fn(cap), device)
             object.__setattr__(self, '_eng', eng)
@@ -158,11 +166,11 @@ class DenoisingNetwork_MSMD(nn.Module, _EngineOwner):
             out = {'denoising_net.' + k: v for k, v in self.state_dict().items()}
             out.update({'diffusion_sched.' + k: v for k, v in sched.state_dict().items()})
             return out
-        return (lambda cap: _engine_cfg(self, self._n_diff_steps, 'sample', cap)), sd
+        return (lambda cap: _engine_cfg(self, self._n_diff_steps, 'sample', cap, self.precision)), sd
 
     @torch.no_grad()
     def forward(self, motion_feat, audio_feat, person_feat, static_style_feat, prev_motion_feat, prev_audio_feat,
-                step, indicator=None, keep_separate=False):
+                step, indicator=None, keep_separate=False, precise=None):
         if keep_separate:
             raise _lib.MsmdError('msmd_b200: keep_separate (sample_separate path, model.py:442) is not built yet')
         if self.use_indicator and indicator is None:
@@ -171,7 +179,7 @@ class DenoisingNetwork_MSMD(nn.Module, _EngineOwner):
         eng = self._get_engine(N, motion_feat.device)
         eng.window_begin(audio_feat, person_feat.reshape(N, -1), static_style_feat.reshape(N, -1), prev_motion_feat,
                          prev_audio_feat, indicator, NX=N, E=1)
-        return eng.denoise(motion_feat, torch.as_tensor(step).reshape(-1).expand(N))
+        return eng.denoise(motion_feat, torch.as_tensor(step).reshape(-1).expand(N), precise)
 
 
 class MSMD(nn.Module, _EngineOwner):
@@ -233,7 +241,7 @@ class MSMD(nn.Module, _EngineOwner):
             out = {'denoising_net.' + k: v for k, v in net.state_dict().items()}
             out.update({'diffusion_sched.' + k: v for k, v in self.diffusion_sched.state_dict().items()})
             return out
-        return (lambda cap: _engine_cfg(net, self.diffusion_sched.num_steps, self.target, cap)), sd
+        return (lambda cap: _engine_cfg(net, self.diffusion_sched.num_steps, self.target, cap, self.precision)), sd
 
     @torch.no_grad()
     def extract_audio_feature(self, audio, frame_num=None):
@@ -244,11 +252,13 @@ class MSMD(nn.Module, _EngineOwner):
     @torch.no_grad()
     def sample(self, audio_or_feat, shape_feat, style_feat=None, prev_motion_feat=None, prev_audio_feat=None,
                motion_at_T=None, indicator=None, cfg_mode=None, cfg_cond=None, cfg_scale=1.15, flexibility=0,
-               dynamic_threshold=None, ret_traj=False, noise=None, n_steps=None, t_start=None, _separate=False):
+               dynamic_threshold=None, ret_traj=False, noise=None, n_steps=None, t_start=None, _separate=False,
+               precise_last_steps=None):
         """model.py:282-440.  Extra keyword arguments (not in the reference): ``noise`` = externally supplied
         z tensor [T+1, N, L, 67] indexed by step t (default: in-kernel Philox seeded from torch's generator);
         ``t_start`` / ``n_steps`` = start at step t_start (motion_at_T is then x_{t_start}) and run n steps
-        (teacher-forced parity tests)."""
+        (teacher-forced parity tests); ``precise_last_steps`` = with ``self.precision == 'hybrid'``, run the steps
+        t <= precise_last_steps in fp32-grade arithmetic (default ``self.precise_last_steps``)."""
         N = audio_or_feat.shape[0]
         dev = self.device
         cfg_mode = self.cfg_mode if cfg_mode is None else cfg_mode
@@ -315,7 +325,9 @@ class MSMD(nn.Module, _EngineOwner):
         T = t_start or self.diffusion_sched.num_steps
         res = eng.sample_window(motion_at_T, noise, seed, cfg_mode == 'independent', s0, s1, flexibility,
                                 t_start=T, n_steps=n_steps, want_traj=ret_traj, dynamic_threshold=dynamic_threshold,
-                                separate=_separate)
+                                separate=_separate,
+                                precise_last_steps=(self.precise_last_steps if precise_last_steps is None
+                                                    else precise_last_steps) if self.precision == 'hybrid' else 0)
         x0, traj = res[0], res[1]
         if _separate and not ret_traj:
             return x0, motion_at_T, audio_feat, res[2]
