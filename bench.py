@@ -303,7 +303,7 @@ class SamplerWorkload:
 
 WORKLOADS = {'flame': FlameWorkload, 'sampler': SamplerWorkload}
 DEFAULT_WORKLOAD = 'sampler'
-DEFAULT_STEPS = {'flame': (20, 5), 'sampler': (2, 1)}
+DEFAULT_STEPS = {'flame': (20, 5), 'sampler': (3, 3)}
 
 
 def main():
@@ -314,6 +314,9 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--precision', default='bf16', choices=['bf16', 'hybrid', 'fp32'],
+                    help='sampler arithmetic (headline = bf16, the mode BASELINE.json quotes)')
+    ap.add_argument('--precise-last-steps', type=int, default=20, help="with --precision hybrid: steps t <= k in fp32-grade")
     a = ap.parse_args()
     if a.steps is None:
         a.steps = DEFAULT_STEPS[a.workload][0]
@@ -363,8 +366,12 @@ def main():
 
     from msmd_b200 import _lib
     wl.setup(device, rank)
+    if a.workload == 'sampler' and a.precision != 'bf16':
+        wl.model.precision = wl.model.denoising_net.precision = a.precision
+        wl.model.precise_last_steps = a.precise_last_steps
+        wl.dtype = {'fp32': 'tf32x3 (fp32-grade)', 'hybrid': f'bf16 + fp32-grade last {a.precise_last_steps} steps'}[a.precision]
     peaks = load_peaks()
-    W = max(3, a.warmup) if a.workload == 'flame' else max(1, a.warmup)
+    W = max(3, a.warmup)      # timing rule: at least 3 untimed warm-up steps
 
     def timed(fn, steps, profile=False, warm=None):
         for _ in range(W if warm is None else warm):
@@ -399,7 +406,7 @@ def main():
                e2e=dict(value=wl.units() * world * a.steps / (ms_e2e * 1e-3), unit=wl.unit, h2d_bytes_per_step=h2d,
                         d2h_bytes_per_step=d2h),
                gpu_launches=wl.launches_per_step() * a.steps,
-               roofline=wl.roofline(peaks, kernel_ms))
+               roofline=wl.roofline(peaks, kernel_ms) if kernel_ms > 0 else None)
     if rank == 0:
         if world == 1 and not a.no_cpu_baseline:
             out['cpu_baseline'] = wl.cpu_reference(10.0)

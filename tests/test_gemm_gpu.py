@@ -55,7 +55,8 @@ def ref_linear(mode, x, w, bias, aux, act):
 
 
 SHAPES = [(128, 256, 64), (128, 256, 512), (333, 512, 512), (21312 // 8, 1536, 512), (2664, 2048, 512),
-          (2664, 512, 2048), (100, 80, 256), (4, 512, 512), (1000, 71 + 1, 256), (257, 768, 3072)]
+          (2664, 512, 2048), (100, 80, 256), (4, 512, 512), (1000, 71 + 1, 256), (257, 768, 3072),
+          (192, 512, 512), (500, 264, 128), (21312, 512, 512)]   # small-M 64-wide tiles; full-size CTA-pair tiles
 
 
 @pytest.mark.parametrize('M,N,K', SHAPES)

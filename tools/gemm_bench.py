@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from msmd_b200 import _lib
 
-def bench(M, N, K, aux=False, act=0, out_f32=False, mode=0, reps=20):
+def bench(M, N, K, aux=False, act=0, out_f32=False, mode=0, reps=20, cublas=True):
     dev = 'cuda'
     dt = torch.bfloat16 if mode == 0 else torch.float32
     x = torch.randn(M, K, device=dev).to(dt); w = (torch.randn(N, K, device=dev) / K ** 0.5).to(dt)
@@ -27,7 +27,7 @@ def bench(M, N, K, aux=False, act=0, out_f32=False, mode=0, reps=20):
     tf = 2.0 * M * N * K / ms / 1e9
     print(f'mode{mode} M={M} N={N} K={K} aux={int(aux)} act={act} f32out={int(out_f32)}: {ms*1e3:8.1f} us  {tf:7.1f} TFLOP/s')
     # cuBLAS comparison (library baseline)
-    if mode == 0:
+    if mode == 0 and cublas:
         y = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
         for _ in range(3): torch.matmul(x, w.t(), out=y)
         torch.cuda.synchronize(); e0.record()

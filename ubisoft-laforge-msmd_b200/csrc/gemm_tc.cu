@@ -5,6 +5,7 @@
 #include <mutex>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 namespace msmd {
 
@@ -106,6 +107,18 @@ static int launch_cfg2(const GemmDesc& d, cudaStream_t st) {
   p.batch = d.batch < 1 ? 1 : d.batch;
   p.wz_mod = d.wz_mod;
   p.bias_zstride = d.bias_zstride;
+#ifdef MSMD_GEMM_TRACE
+  static const bool env_trace = getenv("MSMD_GEMM_TRACE") != nullptr;
+#else
+  constexpr bool env_trace = false;
+#endif
+  static unsigned long long* trace_buf = nullptr;
+  constexpr size_t kTraceN = (size_t)kNumSMs * 3 * 16 * 4;
+  if (env_trace) {
+    if (!trace_buf) MSMD_CHECK_CUDA(cudaMalloc(&trace_buf, kTraceN * 8));
+    MSMD_CHECK_CUDA(cudaMemsetAsync(trace_buf, 0, kTraceN * 8, st));
+    p.trace = trace_buf;
+  }
   p.tiles_m = cdiv(d.M, Cfg::CTA2 ? 2 * Cfg::BM : Cfg::BM);
   p.tiles_n = cdiv(d.N, Cfg::BN);
   const int tiles = p.tiles_m * p.tiles_n * p.batch;
@@ -141,6 +154,29 @@ static int launch_cfg2(const GemmDesc& d, cudaStream_t st) {
     MSMD_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, p));
   }
   MSMD_CHECK_LAUNCH();
+  if (env_trace) {
+    static int dumps = 0;
+    std::vector<unsigned long long> h(kTraceN);
+    MSMD_CHECK_CUDA(cudaStreamSynchronize(st));
+    MSMD_CHECK_CUDA(cudaMemcpy(h.data(), trace_buf, kTraceN * 8, cudaMemcpyDeviceToHost));
+    if (dumps++ % 23 == 22) {   // one warm launch per shape in tools/pair_probe.py
+      for (int cta : {0, 1, 77}) {
+        const unsigned long long t0 = h[((size_t)cta * 3 + 0) * 64 + 0];
+        fprintf(stderr, "[trace] %s cta %d (cycles since the producer's first stamp)\n", shape_name, cta);
+        const char* names[3] = {"tma  [start, slot0 free, last kb issued, -]", "mma  [start, acc free, first full, last issued]",
+                                "epi0 [start, acc full, tmem drained, done]"};
+        for (int role = 0; role < 3; ++role) {
+          fprintf(stderr, "  %s\n", names[role]);
+          for (int it = 0; it < 12; ++it) {
+            const unsigned long long* e = &h[(((size_t)cta * 3 + role) * 16 + it) * 4];
+            if (!e[0] && !e[1]) break;
+            fprintf(stderr, "    tile %2d: %7lld %7lld %7lld %7lld\n", it, (long long)(e[0] - t0), (long long)(e[1] - t0),
+                    (long long)(e[2] ? e[2] - t0 : 0), (long long)(e[3] ? e[3] - t0 : 0));
+          }
+        }
+      }
+    }
+  }
   return MSMD_OK;
 }
 
@@ -157,21 +193,28 @@ int gemm_tc_launch(const GemmDesc& d, cudaStream_t st) {
   if (d.mode == 0) {
     // narrow outputs (N <= 128) use the 128-wide tile so small problems still spread over SMs
     const bool narrow = d.N <= 128;
-    static const bool cta2_env = [] { const char* e = getenv("MSMD_GEMM_CTA2"); return !e || atoi(e) != 0; }();
-    // measured on B200 (tools/gemm_bench.py): the pair wins when the main loop dominates (K >= 1024: +11% at
-    // N=512,K=2048, 93% of cuBLAS at 768x3072) and loses ~12% at K=512 where the per-tile epilogue dominates
+    static const int cta2_mode = [] { const char* e = getenv("MSMD_GEMM_CTA2"); return e ? atoi(e) : 1; }();  // 0 = never use CTA pairs
+    const bool cta2_env = cta2_mode != 0;
+    // measured on B200 (tools/pair_probe.py, M = 21312): the single-CTA 128x256 tile needs 96 B/clk of operands per SM
+    // at MMA peak and the L2->SM path delivers ~60, so its main loop runs at ~1.3 PFLOP/s; the pair (64 B/clk) is
+    // MMA-bound.  Pair vs single: 1536x512 31.8/33.5 us, 2048x512+GELU 50.0/53.2, 512x2048 41.4/46.1, 512x512 tie.
     const bool pair = d.cta2 == 1 || (d.cta2 < 0 && cta2_env && !aux && !d.out_f32 && d.batch <= 1 && d.N >= 256 &&
-                                      d.M >= 2048 && d.K >= 1024);
+                                      d.M >= 2048);
+    const bool epi8 = d.gelu_heavy != 0;
     if (pair) {
-      if (d.gelu_heavy) return launch_cfg<GemmCfg<0, 256, 8, false, bf, bf, true>, 0>(d, st);
+      if (epi8) return launch_cfg<GemmCfg<0, 256, 8, false, bf, bf, true>, 0>(d, st);
       return launch_cfg<GemmCfg<0, 256, 4, false, bf, bf, true>, 0>(d, st);
     }
+    // a handful of rows (the person-token projections, M = sequences): 64-wide tiles spread the N dimension over
+    // 4x more SMs, and the whole K extent of a tile fits the 6-stage ring, so one TMA latency covers it
+    if (!aux && !d.out_f32 && d.batch <= 1 && d.M <= 512 && d.N >= 256)
+      return launch_cfg<GemmCfg<0, 64, 4, false, bf, bf>, 0>(d, st);
     if (!aux) {
       if (d.out_f32) {
         return narrow ? launch_cfg<GemmCfg<0, 128, 4, false, float, float>, 0>(d, st)
                       : launch_cfg<GemmCfg<0, 256, 4, false, float, float>, 0>(d, st);
       }
-      if (d.gelu_heavy && !narrow) return launch_cfg<GemmCfg<0, 256, 8, false, bf, bf>, 0>(d, st);
+      if (epi8 && !narrow) return launch_cfg<GemmCfg<0, 256, 8, false, bf, bf>, 0>(d, st);
       return narrow ? launch_cfg<GemmCfg<0, 128, 4, false, bf, bf>, 0>(d, st)
                     : launch_cfg<GemmCfg<0, 256, 4, false, bf, bf>, 0>(d, st);
     }

@@ -28,10 +28,12 @@ struct GemmParams {
   int wz_mod;                      // batched W: -1 -> W[z], 0 -> one 2-D W shared by every z, n > 0 -> W[z % n]
   int bias_zstride;                // bias offset per W batch index (wz_mod > 0)
   int tiles_m, tiles_n;
+  unsigned long long* trace;       // -DMSMD_GEMM_TRACE builds only: per-role clock64 stamps of the first 16 tiles
 };
 
-template <int MODE, int BN_, int EPI_WARPS_, bool HAS_AUX_, typename OutT_, typename AuxT_, bool CTA2_ = false>
+template <int MODE, int BN_, int EPI_WARPS_, bool HAS_AUX_, typename OutT_, typename AuxT_, bool CTA2_ = false, int OUT_BUFS_ = 2>
 struct GemmCfg {
+  static constexpr int OUT_BUFS = OUT_BUFS_;   // output staging tiles per epilogue warp = TMA stores in flight + 1
   // CTA2: the tile is 256 x BN on a CTA PAIR (cta_group::2): each CTA holds its 128 rows of A and HALF of the
   // W tile, the leader issues M=256 MMAs that read both shared memories -> 2/3 of the operand bytes per FLOP
   // and 32 KB stages (6 deep) instead of 48 KB (4 deep).
@@ -51,7 +53,7 @@ struct GemmCfg {
   static constexpr int STAGE_BYTES = NSPLIT * (A_BYTES + B_BYTES);
   static constexpr int OUT_COLS = 128 / (int)sizeof(OutT);
   static constexpr int AUX_COLS = 128 / (int)sizeof(AuxT);
-  static constexpr int EPI_WARP_BYTES = 8192 + (HAS_AUX ? 8192 : 0);  // 2 out staging (+ 2 aux) tiles of 4 KB
+  static constexpr int EPI_WARP_BYTES = OUT_BUFS * 4096 + (HAS_AUX ? 8192 : 0);  // out staging (+ 2 aux) tiles of 4 KB
   static constexpr int EPI_BYTES = EPI_WARPS * EPI_WARP_BYTES;
   static constexpr int BAR_BYTES = 256 + 2 * 256 * 4;  // mbarriers + TMEM slot, then 2 bias tiles of <= 256 floats
   static constexpr int ALIGN_SLACK = 512;              // dynamic smem base is >= 512-byte aligned in practice; checked
@@ -104,6 +106,13 @@ template <int MODE>
 __device__ __forceinline__ float gelu_erf(float x) {
   if constexpr (MODE == 0) return gelu_tanh3(x);
   else return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+}
+
+// Per-role timeline of the first 16 tiles (clock64 stamps), compiled in only with -DMSMD_GEMM_TRACE (tools/pair_probe.py)
+__device__ __forceinline__ void trace_stamp(unsigned long long* tr, int role, int it, int ev) {
+#ifdef MSMD_GEMM_TRACE
+  if (tr != nullptr && it < 16) tr[((blockIdx.x * 3 + role) * 16 + it) * 4 + ev] = clock64();
+#endif
 }
 
 template <class Cfg, int MODE, bool GELU>
@@ -169,12 +178,16 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_tc_kernel(const __grid_c
     // ------------------------------------------------ TMA producer (lane 0 issues; the warp stays converged)
     int s = 0;
     uint32_t ph = 0;
-    for (int t = tile0; t < num_tiles; t += tstride) {
+    int pit = 0;
+    for (int t = tile0; t < num_tiles; t += tstride, ++pit) {
       int m0, n0, z;
       tile_coords(t, m0, n0, z);
       for (int kb = 0; kb < num_kb; ++kb) {
         if (lane == 0) {
+          if (kb == 0) trace_stamp(p.trace, 0, pit, 0);
           mbar_wait(&empty_bar[s], ph ^ 1);
+          if (kb == 0) trace_stamp(p.trace, 0, pit, 1);
+          if (kb == num_kb - 1) trace_stamp(p.trace, 0, pit, 2);
           uint8_t* sa = stage_base + s * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::NSPLIT * Cfg::A_BYTES;
           if constexpr (Cfg::CTA2) {
@@ -211,14 +224,17 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_tc_kernel(const __grid_c
       const uint32_t aph = (it >> 1) & 1;
       const uint32_t d_tmem = tmem_base + a * Cfg::ACC_COLS;
       if (lane == 0) {
+        trace_stamp(p.trace, 1, it, 0);
         mbar_wait(&tempty_bar[a], aph ^ 1);
         tc_fence_after();
+        trace_stamp(p.trace, 1, it, 1);
       }
       __syncwarp();
       for (int kb = 0; kb < num_kb; ++kb) {
         if (lane == 0) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
+          if (kb == 0) trace_stamp(p.trace, 1, it, 2);
           const uint32_t sa = smem_u32(stage_base + s * Cfg::STAGE_BYTES);
           const uint32_t sb = sa + Cfg::NSPLIT * Cfg::A_BYTES;
           const uint64_t da = make_smem_desc_sw128(sa), db = make_smem_desc_sw128(sb);
@@ -242,6 +258,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_tc_kernel(const __grid_c
         __syncwarp();
         if (++s == STAGES) { s = 0; ph ^= 1; }
       }
+      if (lane == 0) trace_stamp(p.trace, 1, it, 3);
       if (lane == 0) {  // accumulator complete -> epilogue (of both CTAs in pair mode)
         if constexpr (Cfg::CTA2) umma_commit_2sm(&tfull_bar[a]);
         else umma_commit(&tfull_bar[a]);
@@ -255,7 +272,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_tc_kernel(const __grid_c
     const int csplit = e / 4;               // which column range of the tile
     uint8_t* my = epi_base + e * Cfg::EPI_WARP_BYTES;
     uint8_t* out_stage = my;                // 2 x [32 rows][128 B], SW128
-    uint8_t* aux_stage = my + 8192;         // 2 x [32 rows][128 B]
+    uint8_t* aux_stage = my + Cfg::OUT_BUFS * 4096;  // 2 x [32 rows][128 B]
     uint64_t* my_aux_bar = aux_bar + 2 * e;
     constexpr int CPW = Cfg::COLS_PER_WARP;
     constexpr int AUX_PER_TILE = Cfg::HAS_AUX ? CPW / Cfg::AUX_COLS : 1;
@@ -282,21 +299,44 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_tc_kernel(const __grid_c
     int so = 0;        // output staging buffers written so far (alternates between the two)
     issue_aux(0);
 
+    // bias values of the NEXT tile travel in registers while the current tile is processed (their global-load
+    // latency would otherwise sit at the head of every tile's epilogue)
+    constexpr int BPT = (BN + EPI_THREADS - 1) / EPI_THREADS;
+    float bnext[BPT];
+    auto fetch_bias = [&](int t) {
+      if (t < num_tiles) {
+        int m0, n0, z;
+        tile_coords(t, m0, n0, z);
+        const float* bias_z = p.bias + (p.wz_mod > 0 ? (z % p.wz_mod) * p.bias_zstride : 0);
+#pragma unroll
+        for (int i = 0; i < BPT; ++i) {
+          const int col = etid + i * EPI_THREADS;
+          bnext[i] = (p.bias != nullptr && col < BN && n0 + col < p.N) ? __ldg(bias_z + n0 + col) : 0.f;
+        }
+      }
+    };
+    fetch_bias(tile0);
+
     int it = 0;
     for (int t = tile0; t < num_tiles; t += tstride, ++it) {
       int m0, n0, z;
       tile_coords(t, m0, n0, z);
       const int a = it & 1;
       const uint32_t aph = (it >> 1) & 1;
-      // bias tile -> shared (double-buffered by tile parity), overlapped with the wait for the accumulator.
-      // The named barrier also keeps the epilogue warps within one tile of each other.
+      // bias tile -> shared (double-buffered by tile parity).  The named barrier also keeps the epilogue warps
+      // within one tile of each other, which is what makes reusing buffer `a` two tiles later safe.
       float* sb = bias_tile + a * BN;
-      const float* bias_z = p.bias + (p.wz_mod > 0 ? (z % p.wz_mod) * p.bias_zstride : 0);
-      for (int i = etid; i < BN; i += EPI_THREADS)
-        sb[i] = (p.bias != nullptr && n0 + i < p.N) ? __ldg(bias_z + n0 + i) : 0.f;
+#pragma unroll
+      for (int i = 0; i < BPT; ++i) {
+        const int col = etid + i * EPI_THREADS;
+        if (col < BN) sb[col] = bnext[i];
+      }
       asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+      fetch_bias(t + tstride);
+      if (e == 0 && lane == 0) trace_stamp(p.trace, 2, it, 0);
       mbar_wait(&tfull_bar[a], aph);
       tc_fence_after();
+      if (e == 0 && lane == 0) trace_stamp(p.trace, 2, it, 1);
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + a * Cfg::ACC_COLS + csplit * CPW;
       const float* sbw = sb + csplit * CPW;
 
@@ -353,10 +393,10 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_tc_kernel(const __grid_c
         // ---- registers -> swizzled staging (two buffers) -> TMA store
         const int o_off = (c % Cfg::OUT_COLS) * (int)sizeof(OutT) / 16;
         if (c % Cfg::OUT_COLS == 0) {
-          if (lane == 0) tma_store_wait_read<1>();  // the store issued two buffers ago has finished reading smem
+          if (lane == 0) tma_store_wait_read<Cfg::OUT_BUFS - 1>();  // the store that last used this buffer has finished reading it
           __syncwarp();
         }
-        uint8_t* obuf = out_stage + (so & 1) * 4096;
+        uint8_t* obuf = out_stage + (so % Cfg::OUT_BUFS) * 4096;
         uint8_t* orow = obuf + lane * 128;
         if constexpr (sizeof(OutT) == 4) {
 #pragma unroll
@@ -388,30 +428,67 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_tc_kernel(const __grid_c
         }
       };
 
-      // software-pipelined TMEM reads: chunk c+1 is in flight while chunk c is processed
-      uint32_t rA[32], rB[32];
-      uint32_t rA2[MODE == 1 ? 32 : 1], rB2[MODE == 1 ? 32 : 1];
-      tmem_ld32(t_addr, rA);
-      if constexpr (MODE == 1) tmem_ld32(t_addr + BN, rA2);
-#pragma unroll 1
-      for (int c = 0; c < CPW; c += 64) {
-        tmem_ld_wait();
-        tmem_ld32(t_addr + c + 32, rB);
-        if constexpr (MODE == 1) tmem_ld32(t_addr + BN + c + 32, rB2);
-        process(rA, rA2, c);
-        tmem_ld_wait();
-        if (c + 64 < CPW) {
-          tmem_ld32(t_addr + c + 64, rA);
-          if constexpr (MODE == 1) tmem_ld32(t_addr + BN + c + 64, rA2);
+      auto release_acc = [&]() {   // every TMEM read of this tile has landed in registers: hand the accumulator back
+        if (e == 0 && lane == 0) trace_stamp(p.trace, 2, it, 2);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (Cfg::CTA2 && cta_rank != 0) mbar_arrive_cluster(&tempty_bar[a], 0);  // the leader's MMA warp waits for both
+          else mbar_arrive(&tempty_bar[a]);
         }
-        process(rB, rB2, c + 32);
+      };
+      if constexpr (MODE == 1) {
+        // software-pipelined TMEM reads: chunk c+1 is in flight while chunk c is processed
+        uint32_t rA[32], rB[32], rA2[32], rB2[32];
+        tmem_ld32(t_addr, rA);
+        tmem_ld32(t_addr + BN, rA2);
+#pragma unroll 1
+        for (int c = 0; c < CPW; c += 64) {
+          tmem_ld_wait();
+          tmem_ld32(t_addr + c + 32, rB);
+          tmem_ld32(t_addr + BN + c + 32, rB2);
+          process(rA, rA2, c);
+          tmem_ld_wait();
+          if (c + 64 < CPW) {
+            tmem_ld32(t_addr + c + 64, rA);
+            tmem_ld32(t_addr + BN + c + 64, rA2);
+          } else {
+            release_acc();
+          }
+          process(rB, rB2, c + 32);
+        }
+      } else {
+        // 64 columns (two 32-column loads) in flight while the previous 64 are processed
+        uint32_t r0[32], r1[32], r2[32], r3[32];
+        uint32_t none[1];
+        tmem_ld32(t_addr, r0);
+        tmem_ld32(t_addr + 32, r1);
+#pragma unroll 1
+        for (int c = 0; c < CPW; c += 128) {
+          tmem_ld_wait();
+          const bool more = c + 64 < CPW;
+          if (more) {
+            tmem_ld32(t_addr + c + 64, r2);
+            tmem_ld32(t_addr + c + 96, r3);
+          } else {
+            release_acc();
+          }
+          process(r0, none, c);
+          process(r1, none, c + 32);
+          if (more) {
+            tmem_ld_wait();
+            if (c + 128 < CPW) {
+              tmem_ld32(t_addr + c + 128, r0);
+              tmem_ld32(t_addr + c + 160, r1);
+            } else {
+              release_acc();
+            }
+            process(r2, none, c + 64);
+            process(r3, none, c + 96);
+          }
+        }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (Cfg::CTA2 && cta_rank != 0) mbar_arrive_cluster(&tempty_bar[a], 0);  // the leader's MMA warp waits for both
-        else mbar_arrive(&tempty_bar[a]);
-      }
+      if (e == 0 && lane == 0) trace_stamp(p.trace, 2, it, 3);
     }
     if (lane == 0) tma_store_wait<0>();
   }
