@@ -12,6 +12,7 @@
 #include "denoiser_kernels.cuh"
 #include "gemm_tc.cuh"
 #include "profile.cuh"
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -204,7 +205,10 @@ int run_forward(msmd_model* m, const float* xrows, cudaStream_t st) {
     // self-attention block (nn.TransformerDecoderLayer._sa_block) + norm1, then the cached cross-attention
     // rows + norm2 for motion tokens
     if ((rc = gemm(m->x, d, w.Wqkv, d, w.bqkv, nullptr, 0, m->qkv, 3 * d, 0, M, 3 * d, d, 0, st))) return rc;
-    if ((rc = self_attn_launch(m->qkv, m->ctx, S, T, c.n_heads, st))) return rc;
+    static const bool attn_mma_sync = [] { const char* e = getenv("MSMD_ATTN_MMA_SYNC"); return e && atoi(e) != 0; }();  // A/B
+    if ((rc = attn_mma_sync ? self_attn_launch(m->qkv, m->ctx, S, T, c.n_heads, st)
+                            : self_attn_tc_launch(m->qkv, m->ctx, S, T, c.n_heads, st)))
+      return rc;
     if ((rc = gemm(m->ctx, d, w.Wo, d, w.bo, nullptr, 0, m->y, d, 0, M, d, d, 0, st))) return rc;
     LnParams lp;
     lp.resid = m->x;

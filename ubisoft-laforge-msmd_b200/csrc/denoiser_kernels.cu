@@ -106,35 +106,44 @@ __global__ void embed_ctx_kernel(EmbedParams p) {
     p.out[((int64_t)s * T + i) * p.d + c] = __float2bfloat16_rn(v);
   }
 }
-// rows Lp+1..: feature_proj([x_t, indicator]) + PE, computed once per x row and written to its E sequences
-constexpr int kEmbedRows = 20;
-__global__ void __launch_bounds__(256) embed_x_kernel(EmbedParams p) {
+// rows Lp+1..: feature_proj([x_t, indicator]) + PE, computed once per x row and written to its E sequences.
+// CTA = 25 frames x 512 features; the x rows sit in shared memory k-major ([k][28]) so one 128-bit broadcast
+// load feeds 4 frames' FMAs (the scalar-load version was LDS-bound at 65 us; this one is FMA-issue-bound).
+constexpr int kEmbedRows = 25, kEmbedPitch = 28;
+__global__ void __launch_bounds__(256, 2) embed_x_kernel(EmbedParams p) {
   griddep_launch();
   griddep_wait();
-  extern __shared__ float xs[];  // [kEmbedRows][dm] x rows, then [E][kEmbedRows] indicators
+  extern __shared__ __align__(16) float xs[];  // [dm][kEmbedPitch] x values (frame-minor), then [E][kEmbedPitch] indicators
   const int T = 1 + p.Lp + p.L;
   const int blocks_per_x = (p.L + kEmbedRows - 1) / kEmbedRows;
   const int n = blockIdx.x / blocks_per_x;
   const int l0 = (blockIdx.x % blocks_per_x) * kEmbedRows;
   const int nr = min(kEmbedRows, p.L - l0);
-  float* inds = xs + kEmbedRows * p.dm;
-  for (int i = threadIdx.x; i < nr * p.dm; i += blockDim.x) xs[i] = p.x[((int64_t)n * p.L + l0) * p.dm + i];
-  for (int i = threadIdx.x; i < p.E * kEmbedRows; i += blockDim.x) {
-    const int e = i / kEmbedRows, r = i % kEmbedRows;
+  float* inds = xs + p.dm * kEmbedPitch;
+  for (int i = threadIdx.x; i < kEmbedPitch * p.dm; i += blockDim.x) {
+    const int r = i / p.dm, k = i % p.dm;      // coalesced global read, transposed shared write
+    xs[k * kEmbedPitch + r] = r < nr ? p.x[((int64_t)n * p.L + l0 + r) * p.dm + k] : 0.f;
+  }
+  for (int i = threadIdx.x; i < p.E * kEmbedPitch; i += blockDim.x) {
+    const int e = i / kEmbedPitch, r = i % kEmbedPitch;
     inds[i] = (p.indicator && r < nr) ? p.indicator[(int64_t)(e * p.NX + n) * p.L + l0 + r] : 0.f;
   }
   __syncthreads();
   for (int c = 2 * threadIdx.x; c < p.d; c += 2 * blockDim.x) {
-    float a0[kEmbedRows], a1[kEmbedRows];
+    float a0[kEmbedPitch], a1[kEmbedPitch];
 #pragma unroll
-    for (int r = 0; r < kEmbedRows; ++r) a0[r] = a1[r] = 0.f;
+    for (int r = 0; r < kEmbedPitch; ++r) a0[r] = a1[r] = 0.f;
+#pragma unroll 2
     for (int k = 0; k < p.dm; ++k) {
-      const float2 w = *reinterpret_cast<const float2*>(p.WfT + (int64_t)k * p.d + c);
+      const float2 w = __ldg(reinterpret_cast<const float2*>(p.WfT + (int64_t)k * p.d + c));
+      const float4* xr = reinterpret_cast<const float4*>(xs + k * kEmbedPitch);
 #pragma unroll
-      for (int r = 0; r < kEmbedRows; ++r) {
-        const float xv = xs[r * p.dm + k];
-        a0[r] = fmaf(xv, w.x, a0[r]);
-        a1[r] = fmaf(xv, w.y, a1[r]);
+      for (int q = 0; q < kEmbedPitch / 4; ++q) {
+        const float4 xv = xr[q];
+        a0[4 * q + 0] = fmaf(xv.x, w.x, a0[4 * q + 0]); a1[4 * q + 0] = fmaf(xv.x, w.y, a1[4 * q + 0]);
+        a0[4 * q + 1] = fmaf(xv.y, w.x, a0[4 * q + 1]); a1[4 * q + 1] = fmaf(xv.y, w.y, a1[4 * q + 1]);
+        a0[4 * q + 2] = fmaf(xv.z, w.x, a0[4 * q + 2]); a1[4 * q + 2] = fmaf(xv.z, w.y, a1[4 * q + 2]);
+        a0[4 * q + 3] = fmaf(xv.w, w.x, a0[4 * q + 3]); a1[4 * q + 3] = fmaf(xv.w, w.y, a1[4 * q + 3]);
       }
     }
     const float2 wi = *reinterpret_cast<const float2*>(p.WfT + (int64_t)p.dm * p.d + c);
@@ -146,7 +155,7 @@ __global__ void __launch_bounds__(256) embed_x_kernel(EmbedParams p) {
         const float2 pe = *reinterpret_cast<const float2*>(p.PE + (int64_t)(1 + p.Lp + l) * p.d + c);
         const float b0 = a0[r] + bc.x + pe.x, b1 = a1[r] + bc.y + pe.y;
         for (int e = 0; e < p.E; ++e) {
-          const float ind = inds[e * kEmbedRows + r];
+          const float ind = inds[e * kEmbedPitch + r];
           const int s = e * p.NX + n;
           *reinterpret_cast<uint32_t*>(p.out + ((int64_t)s * T + 1 + p.Lp + l) * p.d + c) =
               pack_bf16(b0 + ind * wi.x, b1 + ind * wi.y);
@@ -160,7 +169,7 @@ int embed_launch(const EmbedParams& p, cudaStream_t st) {
   MSMD_CHECK_CUDA(launch_pdl(embed_ctx_kernel, dim3(p.S * (p.Lp + 1)), dim3(128), 0, st, p));
   MSMD_CHECK_LAUNCH();
   const int blocks = p.NX * ((p.L + kEmbedRows - 1) / kEmbedRows);
-  MSMD_CHECK_CUDA(launch_pdl(embed_x_kernel, dim3(blocks), dim3(256), (kEmbedRows * p.dm + 3 * kEmbedRows) * sizeof(float), st, p));
+  MSMD_CHECK_CUDA(launch_pdl(embed_x_kernel, dim3(blocks), dim3(256), (p.dm + 3) * kEmbedPitch * sizeof(float), st, p));
   MSMD_CHECK_LAUNCH();
   return MSMD_OK;
 }
@@ -460,28 +469,33 @@ int self_attn_launch(const bf16* qkv, bf16* ctx, int S, int T, int H, cudaStream
 }
 
 // ------------------------------------------------------------------------------------------- row-0 cross attention
-// The alignment mask (model.py:879-883) lets only the person token attend to all memory.  One CTA per
-// sequence, one warp per head.  The sequence's K block ([Tk, d], all heads) is streamed into shared memory
-// with cp.async (every load in flight at once), scores are computed, then V streams into the same buffer:
-// HBM-bound (2 x Tk x d x 2 B per sequence per layer), two memory latencies in total.
-constexpr int kCaPitch = 1024 + 16;   // bytes per key row in smem: +16 B so 128-bit row reads spread over banks
-
-__global__ void __launch_bounds__(256, 2) cross_attn_row0_kernel(const bf16* __restrict__ q0, const bf16* __restrict__ kv,
-                                                                 bf16* __restrict__ ctx0, int Tk) {
-  extern __shared__ __align__(16) uint8_t ca_smem[];
+// Person token (query row 0) over the Tk memory tokens (nn.MultiheadAttention inside _mha_block): one warp per
+// (sequence, head), no shared memory and no barriers.  K: lane j of key group g reads its key's 128-byte head
+// slice with 8 x 16-byte loads (the half-used sectors of one load are completed by the next, out of L1); V: lane
+// owns 2 of the 64 head dims, so a key's V slice is one coalesced 128-byte warp load, prefetched 28 keys ahead.
+// HBM-bound: 2 x Tk x d x 2 B per sequence per layer.
+constexpr int kCaBatch = 28;
+__global__ void __launch_bounds__(128, 3) cross_attn_row0_kernel(const bf16* __restrict__ q0, const bf16* __restrict__ kv,
+                                                                 bf16* __restrict__ ctx0, int Tk, int H) {
   griddep_launch();
   griddep_wait();
   constexpr int d = 512;
-  const int s = blockIdx.x, tid = threadIdx.x, h = tid >> 5, lane = tid & 31;
-  const bf16* kbase = kv + (int64_t)s * Tk * 2 * d;
-  auto stream = [&](int off) {  // off = 0: K half of each row, d: V half
-    for (int idx = tid; idx < Tk * 64; idx += 256) {
-      const int row = idx >> 6, ch = idx & 63;
-      cp_async16(ca_smem + row * kCaPitch + ch * 16, kbase + (int64_t)row * 2 * d + off + ch * 8);
+  const int w = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;   // warp = (sequence, head)
+  const int s = w / H, h = w % H;
+  const bf16* kbase = kv + (int64_t)s * Tk * 2 * d + h * 64;
+  const uint32_t* vbase = reinterpret_cast<const uint32_t*>(kbase + d) + lane;
+  const int64_t vstride = d;   // one key row = 2d bf16 = d uint32
+
+  uint32_t vb[2][kCaBatch];
+  auto load_v = [&](int b, uint32_t (&dst)[kCaBatch]) {
+#pragma unroll
+    for (int u = 0; u < kCaBatch; ++u) {
+      const int j = b * kCaBatch + u;
+      dst[u] = j < Tk ? __ldg(vbase + (int64_t)j * vstride) : 0u;
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
   };
-  stream(0);
+  load_v(0, vb[0]);
+
   float q[64];
   {
     const uint4* qp = reinterpret_cast<const uint4*>(q0 + (int64_t)s * d + h * 64);
@@ -496,20 +510,20 @@ __global__ void __launch_bounds__(256, 2) cross_attn_row0_kernel(const bf16* __r
       }
     }
   }
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-  __syncthreads();
   float sc[4];
 #pragma unroll
   for (int grp = 0; grp < 4; ++grp) {
     const int j = grp * 32 + lane;
     float dot = -INFINITY;
     if (j < Tk) {
-      const uint4* kp = reinterpret_cast<const uint4*>(ca_smem + j * kCaPitch + h * 128);
+      const uint4* kp = reinterpret_cast<const uint4*>(kbase + (int64_t)j * 2 * d);
+      uint4 kr[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) kr[i] = __ldg(kp + i);
       float acc = 0.f;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const uint4 u = kp[i];
-        const uint32_t ww[4] = {u.x, u.y, u.z, u.w};
+        const uint32_t ww[4] = {kr[i].x, kr[i].y, kr[i].z, kr[i].w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           acc = fmaf(q[i * 8 + 2 * k], __uint_as_float(ww[k] << 16), acc);
@@ -520,42 +534,33 @@ __global__ void __launch_bounds__(256, 2) cross_attn_row0_kernel(const bf16* __r
     }
     sc[grp] = dot;
   }
-  __syncthreads();   // every warp has read K: the buffer can take V
-  stream(d);
   const float m = warp_max(fmaxf(fmaxf(sc[0], sc[1]), fmaxf(sc[2], sc[3])));
   float l = 0.f;
 #pragma unroll
   for (int i = 0; i < 4; ++i) { sc[i] = (sc[i] == -INFINITY) ? 0.f : __expf(sc[i] - m); l += sc[i]; }
   l = warp_sum(l);
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-  __syncthreads();
   float oa = 0.f, ob = 0.f;
-  const uint8_t* vcol = ca_smem + h * 128 + lane * 4;   // lane owns dims 2*lane, 2*lane+1 of this head
+  auto consume = [&](int b, const uint32_t (&src)[kCaBatch]) {
 #pragma unroll
-  for (int grp = 0; grp < 4; ++grp) {
-#pragma unroll 8
-    for (int u = 0; u < 32; ++u) {
-      const int j = grp * 32 + u;
-      if (j >= Tk) break;
-      const float p = __shfl_sync(0xffffffffu, sc[grp], u);
-      const uint32_t vu = *reinterpret_cast<const uint32_t*>(vcol + j * kCaPitch);
-      oa = fmaf(p, __uint_as_float(vu << 16), oa);
-      ob = fmaf(p, __uint_as_float(vu & 0xffff0000u), ob);
+    for (int u = 0; u < kCaBatch; ++u) {
+      const int j = b * kCaBatch + u;            // compile-time after unrolling: sc[] stays in registers
+      const float p = __shfl_sync(0xffffffffu, sc[j >> 5], j & 31);
+      oa = fmaf(p, __uint_as_float(src[u] << 16), oa);
+      ob = fmaf(p, __uint_as_float(src[u] & 0xffff0000u), ob);
     }
-  }
+  };
+  load_v(1, vb[1]); consume(0, vb[0]);
+  load_v(2, vb[0]); consume(1, vb[1]);
+  load_v(3, vb[1]); consume(2, vb[0]);
+  consume(3, vb[1]);
   const float inv = 1.0f / l;
   *reinterpret_cast<uint32_t*>(ctx0 + (int64_t)s * d + h * 64 + 2 * lane) = pack_bf16(oa * inv, ob * inv);
 }
 int cross_attn_row0_launch(const bf16* q0, const bf16* kv, bf16* ctx0, int S, int Tk, int H, cudaStream_t st) {
-  MSMD_REQUIRE(Tk <= 110 && H == 8, "cross_attn_row0: built for 8 heads x 64 and <= 110 memory tokens (got %d, %d)", H, Tk);
-  const int smem = Tk * kCaPitch;
-  static bool attr = false;
-  if (!attr) {
-    MSMD_CHECK_CUDA(cudaFuncSetAttribute(cross_attn_row0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * kCaPitch));
-    attr = true;
-  }
+  MSMD_REQUIRE(Tk <= 4 * kCaBatch && H == 8, "cross_attn_row0: built for 8 heads x 64 and <= %d memory tokens (got %d, %d)",
+               4 * kCaBatch, H, Tk);
   ProfileScope prof("cross_attn_row0", st);
-  MSMD_CHECK_CUDA(launch_pdl(cross_attn_row0_kernel, dim3(S), dim3(256), smem, st, q0, kv, ctx0, Tk));
+  MSMD_CHECK_CUDA(launch_pdl(cross_attn_row0_kernel, dim3(S * H / 4), dim3(128), 0, st, q0, kv, ctx0, Tk, H));
   MSMD_CHECK_LAUNCH();
   return MSMD_OK;
 }

@@ -92,6 +92,9 @@ int steps_advance(int* steps, int S, cudaStream_t st);
 // out[S, T-1... ] : x̂0 per sequence (module-level parity): dyn + static mix for ALL Lp+L rows -> [S, T-1, dm]
 int mix_static_launch(const float* dec, const float* stat, float* out, int S, int T, int dm, int nb, int ldd, cudaStream_t st);
 
+// tcgen05 self-attention (attn_tc.cu): same contract as self_attn_launch
+int self_attn_tc_launch(const bf16* qkv, bf16* ctx, int S, int T, int H, cudaStream_t st);
+
 // ---- fp32-grade variants (denoiser_f32.cu) ----
 int embed_f32_launch(const EmbedParams& p, float* out, cudaStream_t st);
 int ln_f32_launch(const float* y, const float* resid, const float* g1, const float* b1, const float* add, const float* g2,
