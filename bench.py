@@ -265,7 +265,7 @@ class SamplerWorkload:
         n_fwd = max(1, cls_n // 50)
         return dict(bound='tensor', kernel=self.kernel + ' (tcgen05 cta_group::2 bf16, bias+GELU epilogue)', achieved=ach, peak=pk,
                     unit='TFLOP/s', frac=ach / pk,
-                    traffic=52.4e6 if self.clips == 64 else None,     # dram read+write per launch, ncu --set full: profiles/r01_gemm_ff1_ncu.txt
+                    traffic=57.5e6 if self.clips == 64 else None,     # dram read+write per launch, ncu --set full: profiles/r01_gemm_ff1_pair_ncu.txt
                     peak_source=peaks['_source'] + ' (sustained cuBLAS bf16)', algorithmic_flops_per_launch=flops,
                     kernel_ms=kernel_ms, timing='CUDA events around each launch on its stream, eager steps (msmd_profile_*)',
                     gemm_class=dict(launches_per_forward=50, ms_per_forward=cls_ms / n_fwd,

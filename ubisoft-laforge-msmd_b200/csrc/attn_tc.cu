@@ -21,6 +21,7 @@
 #include "denoiser_kernels.cuh"
 #include "profile.cuh"
 #include "tc_common.cuh"
+#include <cstdlib>
 
 namespace msmd {
 namespace {
@@ -41,6 +42,7 @@ struct AttnParams {
   CUtensorMap q_map, kv_map;
   CUtensorMap out_map;     // ctx rows, box {64 head dims, T rows}: a job's store covers exactly its sequence
   int S, T, H, jobs;
+  int early;               // A/B (MSMD_ATTN_EARLY): release S_g right after it is read instead of after O_g is read
 };
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
@@ -167,6 +169,11 @@ __global__ void __launch_bounds__(kThreads, 1) self_attn_tc_kernel(const __grid_
       tmem_ld32(t_s + 64, v + 64);
       tmem_ld16(t_s + 96, v + 96);
       tmem_ld_wait();
+      if (p.early) {   // S_g is in registers: the next Q K^T of this group may run under this job's softmax
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&aempty_bar[g]);
+      }
       float m = -INFINITY;
 #pragma unroll
       for (int c = 0; c < kKeys; ++c) {
@@ -205,9 +212,11 @@ __global__ void __launch_bounds__(kThreads, 1) self_attn_tc_kernel(const __grid_
       tmem_ld32(t_o, o);
       tmem_ld32(t_o + 32, o + 32);
       tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&aempty_bar[g]);
+      if (!p.early) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&aempty_bar[g]);
+      }
       const float inv = 1.0f / l;
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
@@ -258,6 +267,8 @@ int self_attn_tc_launch(const bf16* qkv, bf16* ctx, int S, int T, int H, cudaStr
                          CU_TENSOR_MAP_SWIZZLE_128B)))
     return rc;
   p.S = S; p.T = T; p.H = H; p.jobs = S * H;
+  static const int early_env = [] { const char* e = getenv("MSMD_ATTN_EARLY"); return e ? atoi(e) : 0; }();
+  p.early = early_env;
   static bool attr = false;
   if (!attr) {
     MSMD_CHECK_CUDA(cudaFuncSetAttribute(self_attn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
