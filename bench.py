@@ -339,7 +339,7 @@ def main():
         cb = dict(vals[-1], value=v)
         print(json.dumps(dict(impl='reference', metric=wl.metric, value=v, unit=wl.unit, n_gpus=a.gpus, steps=a.steps,
                               warmup=a.warmup, ms_per_step=1e3 * (time.perf_counter() - t0) / max(1, a.steps + a.warmup),
-                              higher_is_better=True, scaling='weak', vs_baseline=None, dtype=wl.dtype, data='synthetic',
+                              higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
                               config=wl.config(a.gpus), cpu_baseline=cb,
                               e2e=dict(value=v, unit=wl.unit, h2d_bytes_per_step=0, d2h_bytes_per_step=0))))
         return 0
