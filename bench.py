@@ -123,17 +123,17 @@ class FlameWorkload:
         return sum(h.numel() * 4 for h in self.host), self.host_out.numel() * 4
 
     def roofline(self, peaks, kernel_ms):
-        # fused kernel = tf32x3 tcgen05 GEMM [B,436]x[436,15069] (fp32-grade: 3 MMA passes) + LBS epilogue.
-        # Tensor-bound: algorithmic 2*B*15069*436 fp32-equivalent FLOPs against (bf16 peak / 2 for tf32) / 3 passes;
+        # fused kernel = three-pass fp16 (two-term split, 22 mantissa bits) tcgen05 GEMM [B,436]x[436,15069] + LBS epilogue.
+        # Tensor-bound: algorithmic 2*B*15069*436 fp32-equivalent FLOPs against the 16-bit tensor peak / 3 passes;
         # the HBM floor (534 MB minimal traffic at B=8192) is reported next to it.
         B = self.frames
         flops = 2.0 * B * 15069 * 436
         ach = flops / (kernel_ms * 1e-3) / 1e12
-        pk = peaks['bf16_tflops'] / 2.0 / 3.0
+        pk = peaks['bf16_tflops'] / 3.0
         alg = B * 400 * 4 + B * 15 * 4 + 15069 * 436 * 4 + B * 15069 * 4
-        return dict(bound='tensor', kernel=self.kernel + ' (tcgen05 kind::tf32 x3 + LBS epilogue)', achieved=ach, peak=pk,
-                    unit='TFLOP/s', frac=ach / pk, traffic=849.5e6 if B == 8192 else None,   # profiles/r01_flame_tc_ncu.txt
-                    peak_source=peaks['_source'] + ' burst cuBLAS bf16 / 2 (tf32) / 3 (passes)',
+        return dict(bound='tensor', kernel=self.kernel + ' (tcgen05 cta_group::2 kind::f16 x3 + LBS epilogue)', achieved=ach, peak=pk,
+                    unit='TFLOP/s', frac=ach / pk, traffic=498.6e6 if B == 8192 else None,   # profiles/r01_flame_tc_pair_ncu.txt
+                    peak_source=peaks['_source'] + ' burst cuBLAS bf16 / 3 (passes)',
                     algorithmic_flops_per_launch=flops, kernel_ms=kernel_ms,
                     hbm=dict(algorithmic_bytes=alg, achieved_gbs=alg / (kernel_ms * 1e-3) / 1e9, peak_gbs=peaks['hbm_gbs'],
                              frac=alg / (kernel_ms * 1e-3) / 1e9 / peaks['hbm_gbs']))

@@ -24,7 +24,7 @@ __global__ void __launch_bounds__(256) flame_pose_kernel(const float* __restrict
                                                          int pose2rot, int64_t B, int NB, int Kpad,
                                                          const float* __restrict__ Jt, const float* __restrict__ Jb,
                                                          const int* __restrict__ parents_g, float* __restrict__ A,
-                                                         float* __restrict__ A_hi, float* __restrict__ A_lo,
+                                                         __half* __restrict__ A_hi, __half* __restrict__ A_lo,
                                                          float* __restrict__ xf, float* __restrict__ joints_out) {
   const int lane = threadIdx.x & 31;
   const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -38,9 +38,9 @@ __global__ void __launch_bounds__(256) flame_pose_kernel(const float* __restrict
     const float v = be[k];
     Arow[k] = v;
     if (A_hi) {
-      const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+      const __half hi = __float2half_rn(v);
       A_hi[b * Kpad + k] = hi;
-      A_lo[b * Kpad + k] = v - hi;
+      A_lo[b * Kpad + k] = __float2half_rn((v - __half2float(hi)) * 2048.0f);
     }
 #pragma unroll
     for (int i = 0; i < NJ * 3; ++i) acc[i] = fmaf(Jb[i * NB + k], v, acc[i]);
@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(256) flame_pose_kernel(const float* __restrict
   const int K = NB + (NJ - 1) * 9;
   for (int k = K + lane; k < Kpad; k += 32) {
     Arow[k] = 0.f;
-    if (A_hi) { A_hi[b * Kpad + k] = 0.f; A_lo[b * Kpad + k] = 0.f; }
+    if (A_hi) { A_hi[b * Kpad + k] = __float2half_rn(0.f); A_lo[b * Kpad + k] = __float2half_rn(0.f); }
   }
   if (lane != 0) return;
 
@@ -83,9 +83,9 @@ __global__ void __launch_bounds__(256) flame_pose_kernel(const float* __restrict
       const int k = NB + (j - 1) * 9 + i;
       Arow[k] = v;
       if (A_hi) {
-        const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+        const __half hi = __float2half_rn(v);
         A_hi[b * Kpad + k] = hi;
-        A_lo[b * Kpad + k] = v - hi;
+        A_lo[b * Kpad + k] = __float2half_rn((v - __half2float(hi)) * 2048.0f);
       }
     }
 
@@ -257,16 +257,17 @@ __global__ void contour_index_kernel(const float* __restrict__ pose, int pose2ro
 static int ensure_workspace(msmd_flame* fh, int64_t B) {
   if (B <= fh->cap_B) return MSMD_OK;
   cudaFree(fh->A); cudaFree(fh->A_hi); cudaFree(fh->A_lo); cudaFree(fh->xf);
-  fh->A = fh->A_hi = fh->A_lo = fh->xf = nullptr;
+  fh->A = fh->xf = nullptr;
+  fh->A_hi = fh->A_lo = nullptr;
   fh->cap_B = 0;
   const int64_t cap = ((B + 127) / 128) * 128;  // whole 128-frame tiles for the TMA path
   MSMD_CHECK_CUDA(cudaMalloc(&fh->A, cap * fh->Kpad * sizeof(float)));
-  MSMD_CHECK_CUDA(cudaMalloc(&fh->A_hi, cap * fh->Kpad * sizeof(float)));
-  MSMD_CHECK_CUDA(cudaMalloc(&fh->A_lo, cap * fh->Kpad * sizeof(float)));
+  MSMD_CHECK_CUDA(cudaMalloc(&fh->A_hi, cap * fh->Kpad * sizeof(__half)));
+  MSMD_CHECK_CUDA(cudaMalloc(&fh->A_lo, cap * fh->Kpad * sizeof(__half)));
   MSMD_CHECK_CUDA(cudaMalloc(&fh->xf, cap * fh->NJ * 12 * sizeof(float)));
   MSMD_CHECK_CUDA(cudaMemset(fh->A, 0, cap * fh->Kpad * sizeof(float)));
-  MSMD_CHECK_CUDA(cudaMemset(fh->A_hi, 0, cap * fh->Kpad * sizeof(float)));
-  MSMD_CHECK_CUDA(cudaMemset(fh->A_lo, 0, cap * fh->Kpad * sizeof(float)));
+  MSMD_CHECK_CUDA(cudaMemset(fh->A_hi, 0, cap * fh->Kpad * sizeof(__half)));
+  MSMD_CHECK_CUDA(cudaMemset(fh->A_lo, 0, cap * fh->Kpad * sizeof(__half)));
   MSMD_CHECK_CUDA(cudaMemset(fh->xf, 0, cap * fh->NJ * 12 * sizeof(float)));
   fh->cap_B = cap;
   return MSMD_OK;
@@ -290,7 +291,7 @@ extern "C" int msmd_flame_create(const float* v_template, const float* shapedirs
   MSMD_CHECK_CUDA(cudaSetDevice(device));
   const int P = (NJ - 1) * 9;
   const int N3 = 3 * V, K = NB + P;
-  const int Kpad = (K + 31) / 32 * 32;
+  const int Kpad = (K + 63) / 64 * 64;
   const int N3pad = (N3 + 383) / 384 * 384;
   // Stage the assets on the host (they may live on either side); packing is a one-off.
   std::vector<float> h_t(N3), h_s((size_t)N3 * NB), h_p((size_t)P * N3), h_j((size_t)NJ * V), h_w((size_t)V * NJ);
@@ -310,18 +311,16 @@ extern "C" int msmd_flame_create(const float* v_template, const float* shapedirs
   fh->parents[0] = -1;
   for (int j = 1; j < NJ; ++j) fh->parents[j] = (int)h_par[j];
 
-  std::vector<float> basis((size_t)N3pad * Kpad, 0.f), hi(basis.size(), 0.f), lo(basis.size(), 0.f);
+  std::vector<float> basis((size_t)N3pad * Kpad, 0.f);
+  std::vector<__half> hi(basis.size()), lo(basis.size());
   for (int n = 0; n < N3; ++n) {
     float* row = basis.data() + (size_t)n * Kpad;
     memcpy(row, h_s.data() + (size_t)n * NB, NB * sizeof(float));
     for (int p = 0; p < P; ++p) row[NB + p] = h_p[(size_t)p * N3 + n];
   }
   for (size_t i = 0; i < basis.size(); ++i) {
-    uint32_t u;
-    memcpy(&u, &basis[i], 4);
-    u &= 0xffffe000u;
-    memcpy(&hi[i], &u, 4);
-    lo[i] = basis[i] - hi[i];
+    hi[i] = __float2half_rn(basis[i]);
+    lo[i] = __float2half_rn((basis[i] - __half2float(hi[i])) * 2048.0f);
   }
   // Joint regression folded through the blendshapes (double accumulation on the host).
   std::vector<float> Jt(NJ * 3), Jb((size_t)NJ * 3 * NB);
@@ -342,7 +341,12 @@ extern "C" int msmd_flame_create(const float* v_template, const float* shapedirs
     return MSMD_OK;
   };
   int rc = MSMD_OK;
-  if ((rc = up(&fh->basis, basis)) || (rc = up(&fh->basis_hi, hi)) || (rc = up(&fh->basis_lo, lo)) ||
+  auto up16 = [&](__half** d, const std::vector<__half>& h) -> int {
+    MSMD_CHECK_CUDA(cudaMalloc(d, h.size() * sizeof(__half)));
+    MSMD_CHECK_CUDA(cudaMemcpy(*d, h.data(), h.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    return MSMD_OK;
+  };
+  if ((rc = up(&fh->basis, basis)) || (rc = up16(&fh->basis_hi, hi)) || (rc = up16(&fh->basis_lo, lo)) ||
       (rc = up(&fh->v_template, h_t)) || (rc = up(&fh->weights, h_w)) || (rc = up(&fh->Jt, Jt)) ||
       (rc = up(&fh->Jb, Jb))) {
     msmd_flame_destroy(fh);

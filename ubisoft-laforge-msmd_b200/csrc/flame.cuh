@@ -2,19 +2,22 @@
 // flame_tc.cu (tcgen05 path).  Replaces utils/flame.py:180-244 + utils/lbs.py:141-371.
 #pragma once
 #include "common.cuh"
+#include <cuda_fp16.h>
 
 struct msmd_flame {
   int device = 0;
   int V = 0, NB = 0, NJ = 5;
   int N3 = 0;      // 3*V output columns (vertex-major, xyz inner)
   int K = 0;       // NB + 9*(NJ-1): blendshape + pose-corrective depth
-  int Kpad = 0;    // K rounded up to 32 (tf32 k-block)
+  int Kpad = 0;    // K rounded up to 64 (one 128-byte fp16 k-block of the tcgen05 path)
   int N3pad = 0;   // N3 rounded up to 384 rows so every tile load is in-bounds
   int parents[8] = {-1, 0, 1, 1, 1, 0, 0, 0};
   // static device buffers
   float* basis = nullptr;     // [N3pad, Kpad] K-major: row n=(v,c): shapedirs[v,c,:] | posedirs[:,n] | 0
-  float* basis_hi = nullptr;  // tf32-truncated copy, and the exact remainder (3-pass split, flame_tc.cu)
-  float* basis_lo = nullptr;
+  // fp16 two-term split for the 3-pass tensor-core path (flame_tc.cu): x = hi + lo * 2^-11 with hi = fp16(x),
+  // lo = fp16((x - hi) * 2^11): 22 mantissa bits, the residual kept out of the fp16 subnormal range by the scale
+  __half* basis_hi = nullptr;
+  __half* basis_lo = nullptr;
   float* v_template = nullptr;  // [N3]
   float* weights = nullptr;     // [V, NJ]
   float* Jt = nullptr;          // [NJ*3]      J_regressor @ v_template
@@ -23,8 +26,8 @@ struct msmd_flame {
   // per-call workspaces (grown on demand)
   int64_t cap_B = 0;
   float* A = nullptr;     // [cap_B, Kpad]  betas | pose_feature | 0
-  float* A_hi = nullptr;  // tf32 split of A
-  float* A_lo = nullptr;
+  __half* A_hi = nullptr;  // same split of A
+  __half* A_lo = nullptr;
   float* xf = nullptr;    // [cap_B, NJ, 12] skinning affines: G (9) | t - G j (3)
   void* tc_state = nullptr;  // tensor maps etc. owned by flame_tc.cu
 };

@@ -1,33 +1,42 @@
-// FLAME decode, tensor-core path (impl 0): fp32-grade tf32x3 tcgen05 GEMM over K = NB + 36 with the linear
-// blend skinning as its epilogue.  Replaces lbs.py:185 (blend_shapes einsum), :200-204 (pose correctives)
+// FLAME decode, tensor-core path (impl 0): fp32-grade three-pass fp16 tcgen05 GEMM over K = NB + 36 with the
+// linear blend skinning as its epilogue.  Replaces lbs.py:185 (blend_shapes einsum), :200-204 (pose correctives)
 // and :210-221 (per-vertex transform blend + apply) in ONE kernel; the reference materialises ~10 GB of
 // intermediates at B = 8192 (T [B,V,16] alone is 2.6 GB), this kernel writes only the vertices.
 //
-//   tile      = 128 frames x 126 columns (42 whole vertices; the MMA is issued with N = 128, the last two
-//               columns are junk and never stored)
-//   operands  = A_hi/A_lo [B,Kpad] (betas | vec(R-I) | 0) and basis_hi/basis_lo [3V,Kpad], all K-major fp32,
-//               TMA -> 128B-swizzled smem, 3 stages x 64 KB
-//   MMA       = kind::tf32, M128 N128 K8, three passes per k-step: hi*hi -> accumulator 0, lo*hi + hi*lo ->
-//               accumulator 1 (kept apart: the tensor core truncates when it accumulates)
-//   TMEM      = 2 stages x (128 + 128) columns: the epilogue of tile i overlaps the MMAs of tile i+1
+//   tile      = 256 frames x 126 columns on a CTA PAIR (cta_group::2; 42 whole vertices; the MMA is issued with
+//               N = 128, the last two columns are junk and never stored).  Each CTA stages its own 128 frames of
+//               A and HALF of the basis tile: 48 KB of operands per k-block per SM instead of 64 KB — the
+//               single-CTA tile needed ~84 B/clk of operands per SM against the ~60 the L2->SM path delivers.
+//   operands  = two-term fp16 splits x = hi + 2^-11 lo (22 mantissa bits; flame.cuh) of A [B,Kpad] (betas |
+//               vec(R-I) | 0) and of the basis [3V,Kpad], K-major, TMA -> 128B-swizzled smem, 3 stages x 48 KB of
+//               64-deep k-blocks.  (The tf32 hi/lo version of this kernel was bound by shared-memory bandwidth:
+//               a K=8 tf32 MMA reads as many operand bytes as a K=16 fp16 one for half the FLOPs.)
+//   MMA       = kind::f16 (fp16 in, fp32 accumulate), M256 N128 K16 issued by the leader CTA, three passes per
+//               k-step: hi*hi -> accumulator 0 (exact products), lo*hi + hi*lo -> accumulator 1, scaled by 2^-11
+//               in the epilogue (kept apart: the tensor core truncates when it accumulates)
+//   TMEM      = per CTA 2 stages x (128 + 128) columns: the epilogue of tile i overlaps the MMAs of tile i+1
 //   epilogue  = thread <-> frame: v_posed = acc0 + acc1 + template, T = sum_j w[v][j] * A_j[b] (5 joints x 12
 //               coefficients held in registers), x = T [v_posed; 1]; staged through smem for coalesced stores
 #include "flame.cuh"
 #include "tc_common.cuh"
 #include "profile.cuh"
+#include <cstdlib>
 
 namespace msmd {
 
 namespace {
 
-constexpr int FT_BM = 128, FT_VERT = 42, FT_BN = 126, FT_UN = 128, FT_BK = 32, FT_STAGES = 3;
+constexpr int FT_BM = 128, FT_VERT = 42, FT_BN = 126, FT_UN = 128, FT_BK = 64, FT_STAGES = 3;
 constexpr int FT_TILE_BYTES = 128 * 128;                 // one operand tile: 128 rows x 128 B
-constexpr int FT_STAGE_BYTES = 4 * FT_TILE_BYTES;        // A_hi, A_lo, B_hi, B_lo
-constexpr int FT_OUT_STRIDE = 49;                        // staging row stride (floats): conflict-free
-constexpr int FT_EPI_WARP_BYTES = 32 * FT_OUT_STRIDE * 4;
+constexpr int FT_BHALF_BYTES = 64 * 128;                 // this CTA's half of a basis tile: 64 rows x 128 B
+constexpr int FT_STAGE_BYTES = 2 * FT_TILE_BYTES + 2 * FT_BHALF_BYTES;   // A_hi, A_lo, B_hi half, B_lo half
+constexpr int FT_CHUNK_V = 8;                             // vertices per epilogue chunk (24 accumulator columns)
+constexpr int FT_OUT_STRIDE = 127;                       // staging row stride (floats): odd -> conflict-free
+constexpr int FT_EPI_WARPS = 8;                          // two warps per TMEM lane quarter, alternating chunks
+constexpr int FT_EPI_Q_BYTES = 32 * FT_OUT_STRIDE * 4;    // one TMEM lane quarter (32 frames) x the tile's 126 columns
 constexpr int FT_MISC_BYTES = 2048;                      // barriers, tmem slot, per-tile weights + template
-constexpr int FT_SMEM_BYTES = 1024 + FT_STAGES * FT_STAGE_BYTES + 4 * FT_EPI_WARP_BYTES + FT_MISC_BYTES + 2 * (FT_VERT * 5 + FT_BN + 2) * 4;
-constexpr int FT_THREADS = 192;
+constexpr int FT_SMEM_BYTES = 1024 + FT_STAGES * FT_STAGE_BYTES + 4 * FT_EPI_Q_BYTES + FT_MISC_BYTES + 2 * (FT_VERT * 5 + FT_BN + 2) * 4;
+constexpr int FT_THREADS = 64 + 32 * FT_EPI_WARPS;
 
 struct FlameTcParams {
   CUtensorMap a_hi, a_lo, b_hi, b_lo;
@@ -48,13 +57,20 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
       : "memory");
 }
 
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
+
 __global__ void __launch_bounds__(FT_THREADS, 1) flame_tc_kernel(const __grid_constant__ FlameTcParams p) {
   using namespace tc;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stage_base = smem;
   float* epi_base = reinterpret_cast<float*>(smem + FT_STAGES * FT_STAGE_BYTES);
-  uint8_t* misc = reinterpret_cast<uint8_t*>(epi_base) + 4 * FT_EPI_WARP_BYTES;
+  uint8_t* misc = reinterpret_cast<uint8_t*>(epi_base) + 4 * FT_EPI_Q_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(misc);  // [STAGES]
   uint64_t* empty_bar = full_bar + FT_STAGES;              // [STAGES]
   uint64_t* tfull_bar = empty_bar + FT_STAGES;             // [2]
@@ -65,16 +81,18 @@ __global__ void __launch_bounds__(FT_THREADS, 1) flame_tc_kernel(const __grid_co
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = p.tiles_m * p.tiles_n;
+  const int cta_rank = (int)cluster_ctarank();
+  const int pair = (int)blockIdx.x / 2, npairs = (int)gridDim.x / 2;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&p.a_hi); prefetch_tmap(&p.a_lo); prefetch_tmap(&p.b_hi); prefetch_tmap(&p.b_lo);
     for (int s = 0; s < FT_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 2 * FT_EPI_WARPS); }   // epilogue warps of both CTAs
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  if (warp == 1) tmem_alloc_2sm(tmem_slot, 512);
   tc_fence_before();
-  __syncthreads();
+  cluster_sync();   // the peer's barriers are initialised before anyone signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -82,18 +100,19 @@ __global__ void __launch_bounds__(FT_THREADS, 1) flame_tc_kernel(const __grid_co
     // ---------------------------------------------------------------- TMA producer
     int s = 0;
     uint32_t ph = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const int m0 = (t / p.tiles_n) * FT_BM, n0 = (t % p.tiles_n) * FT_BN;
+    for (int t = pair; t < num_tiles; t += npairs) {
+      const int m0 = (t / p.tiles_n) * 2 * FT_BM + cta_rank * FT_BM, n0 = (t % p.tiles_n) * FT_BN + cta_rank * 64;
       for (int kb = 0; kb < p.num_kb; ++kb) {
         if (lane == 0) {
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* st = stage_base + s * FT_STAGE_BYTES;
-          // the basis boxes are 126 rows: their last two smem rows keep stale data and only feed junk columns
-          mbar_expect_tx(&full_bar[s], 2 * FT_TILE_BYTES + 2 * FT_BN * 128);
-          tma_load_2d(st, &p.a_hi, &full_bar[s], kb * FT_BK, m0);
-          tma_load_2d(st + FT_TILE_BYTES, &p.a_lo, &full_bar[s], kb * FT_BK, m0);
-          tma_load_2d(st + 2 * FT_TILE_BYTES, &p.b_hi, &full_bar[s], kb * FT_BK, n0);
-          tma_load_2d(st + 3 * FT_TILE_BYTES, &p.b_lo, &full_bar[s], kb * FT_BK, n0);
+          // both CTAs' boxes land on the leader's barrier.  Rank 1's basis half covers tile columns 64..127: the
+          // last two rows belong to the next tile (or are zero-filled past the end) and only feed junk columns
+          if (cta_rank == 0) mbar_expect_tx(&full_bar[s], 2 * FT_STAGE_BYTES);
+          tma_load_2d_2sm(st, &p.a_hi, &full_bar[s], kb * FT_BK, m0);
+          tma_load_2d_2sm(st + FT_TILE_BYTES, &p.a_lo, &full_bar[s], kb * FT_BK, m0);
+          tma_load_2d_2sm(st + 2 * FT_TILE_BYTES, &p.b_hi, &full_bar[s], kb * FT_BK, n0);
+          tma_load_2d_2sm(st + 2 * FT_TILE_BYTES + FT_BHALF_BYTES, &p.b_lo, &full_bar[s], kb * FT_BK, n0);
         }
         __syncwarp();
         if (++s == FT_STAGES) { s = 0; ph ^= 1; }
@@ -101,10 +120,10 @@ __global__ void __launch_bounds__(FT_THREADS, 1) flame_tc_kernel(const __grid_co
     }
   } else if (warp == 1) {
     // ---------------------------------------------------------------- MMA issuer
-    constexpr uint32_t idesc = make_idesc(2, FT_BM, FT_UN);
+    constexpr uint32_t idesc = make_idesc(0, 2 * FT_BM, FT_UN);   // fp16 operands, fp32 accumulate
     int s = 0, it = 0;
     uint32_t ph = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+    for (int t = cta_rank == 0 ? pair : num_tiles; t < num_tiles; t += npairs, ++it) {   // leader only
       const int a = it & 1;
       const uint32_t aph = (it >> 1) & 1;
       const uint32_t d_main = tmem_base + a * 256, d_cross = d_main + 128;
@@ -119,37 +138,41 @@ __global__ void __launch_bounds__(FT_THREADS, 1) flame_tc_kernel(const __grid_co
           tc_fence_after();
           const uint32_t sa = smem_u32(stage_base + s * FT_STAGE_BYTES);
           const uint64_t ah = make_smem_desc_sw128(sa), al = make_smem_desc_sw128(sa + FT_TILE_BYTES);
-          const uint64_t bh = make_smem_desc_sw128(sa + 2 * FT_TILE_BYTES), bl = make_smem_desc_sw128(sa + 3 * FT_TILE_BYTES);
+          const uint64_t bh = make_smem_desc_sw128(sa + 2 * FT_TILE_BYTES);
+          const uint64_t bl = make_smem_desc_sw128(sa + 2 * FT_TILE_BYTES + FT_BHALF_BYTES);
 #pragma unroll
-          for (int k = 0; k < FT_BK / 8; ++k) {
+          for (int k = 0; k < FT_BK / 16; ++k) {
             const uint32_t acc = (kb | k) != 0;
-            umma<1>(d_cross, desc_advance(al, k * 32), desc_advance(bh, k * 32), idesc, acc);  // lo * hi
-            umma<1>(d_cross, desc_advance(ah, k * 32), desc_advance(bl, k * 32), idesc, 1u);   // hi * lo
-            umma<1>(d_main, desc_advance(ah, k * 32), desc_advance(bh, k * 32), idesc, acc);   // hi * hi
+            umma_2sm(d_cross, desc_advance(al, k * 32), desc_advance(bh, k * 32), idesc, acc);  // lo * hi
+            umma_2sm(d_cross, desc_advance(ah, k * 32), desc_advance(bl, k * 32), idesc, 1u);   // hi * lo
+            umma_2sm(d_main, desc_advance(ah, k * 32), desc_advance(bh, k * 32), idesc, acc);   // hi * hi
           }
-          umma_commit(&empty_bar[s]);
+          umma_commit_2sm(&empty_bar[s]);
         }
         __syncwarp();
         if (++s == FT_STAGES) { s = 0; ph ^= 1; }
       }
-      if (lane == 0) umma_commit(&tfull_bar[a]);
+      if (lane == 0) umma_commit_2sm(&tfull_bar[a]);
       __syncwarp();
     }
   } else {
     // ---------------------------------------------------------------- epilogue: skinning
-    const int q = warp & 3;
-    float* stage = epi_base + (warp - 2) * (FT_EPI_WARP_BYTES / 4);
+    const int q = warp & 3;                     // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;           // which of the quarter's two warps: chunks half, half+2, ...
+    float* stage = epi_base + q * (FT_EPI_Q_BYTES / 4);   // shared by the quarter's two warps
     const int etid = threadIdx.x - 64;
+    constexpr int EPI_THREADS = 32 * FT_EPI_WARPS;
+    constexpr int NCHUNK = (FT_VERT + FT_CHUNK_V - 1) / FT_CHUNK_V;
     int it = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-      const int m0 = (t / p.tiles_n) * FT_BM, n0 = (t % p.tiles_n) * FT_BN;
+    for (int t = pair; t < num_tiles; t += npairs, ++it) {
+      const int m0 = (t / p.tiles_n) * 2 * FT_BM + cta_rank * FT_BM, n0 = (t % p.tiles_n) * FT_BN;
       const int a = it & 1;
       const uint32_t aph = (it >> 1) & 1;
       const int v0 = n0 / 3;
       // per-tile skinning weights + template slice -> smem (double-buffered by tile parity)
       float* tw = tile_w + a * TILE_W_FLOATS;
-      for (int i = etid; i < FT_VERT * 5; i += 128) tw[i] = (v0 + i / 5 < p.V) ? __ldg(p.weights + (int64_t)v0 * 5 + i) : 0.f;
-      for (int i = etid; i < FT_BN; i += 128) tw[FT_VERT * 5 + i] = (n0 + i < p.N3) ? __ldg(p.tmpl + n0 + i) : 0.f;
+      for (int i = etid; i < FT_VERT * 5; i += EPI_THREADS) tw[i] = (v0 + i / 5 < p.V) ? __ldg(p.weights + (int64_t)v0 * 5 + i) : 0.f;
+      for (int i = etid; i < FT_BN; i += EPI_THREADS) tw[FT_VERT * 5 + i] = (n0 + i < p.N3) ? __ldg(p.tmpl + n0 + i) : 0.f;
       // this thread's frame: 5 joints x (3x3 | t)
       const int row = m0 + q * 32 + lane;
       float xf[60];
@@ -161,27 +184,32 @@ __global__ void __launch_bounds__(FT_THREADS, 1) flame_tc_kernel(const __grid_co
           xf[4 * i] = f.x; xf[4 * i + 1] = f.y; xf[4 * i + 2] = f.z; xf[4 * i + 3] = f.w;
         }
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
       mbar_wait(&tfull_bar[a], aph);
       tc_fence_after();
       const uint32_t t_main = tmem_base + ((uint32_t)(q * 32) << 16) + a * 256, t_cross = t_main + 128;
       const float* tmpl = tw + FT_VERT * 5;
 #pragma unroll 1
-      for (int ck = 0; ck < 3; ++ck) {           // vertex chunks: 16, 16, 10 vertices (48, 48, 30(+2 junk) columns)
-        const int c0 = ck * 48;
-        const int nv = ck < 2 ? 16 : 10;
-        uint32_t m[48], c[48];
-        tmem_ld32(t_main + c0, m);
-        tmem_ld32(t_cross + c0, c);
-        if (ck < 2) { tmem_ld16(t_main + c0 + 32, m + 32); tmem_ld16(t_cross + c0 + 32, c + 32); }
+      for (int ck = half; ck < NCHUNK; ck += 2) {   // 8-vertex chunks (24 columns); the last one holds 2 vertices
+        const int c0 = ck * 3 * FT_CHUNK_V;
+        const int nv = min(FT_CHUNK_V, FT_VERT - ck * FT_CHUNK_V);
+        uint32_t m[24], c[24];
+        if (nv == FT_CHUNK_V) {
+          tmem_ld16(t_main + c0, m); tmem_ld8(t_main + c0 + 16, m + 16);
+          tmem_ld16(t_cross + c0, c); tmem_ld8(t_cross + c0 + 16, c + 16);
+        } else {   // last chunk: 2 vertices = columns 120..125; an x16 load would run past the 128-column accumulator
+          tmem_ld8(t_main + c0, m);
+          tmem_ld8(t_cross + c0, c);
+        }
         tmem_ld_wait();
 #pragma unroll
-        for (int v = 0; v < 16; ++v) {
+        for (int v = 0; v < FT_CHUNK_V; ++v) {
           if (v < nv) {
             const int cc = c0 + 3 * v;
-            const float px = __uint_as_float(m[3 * v]) + __uint_as_float(c[3 * v]) + tmpl[cc];
-            const float py = __uint_as_float(m[3 * v + 1]) + __uint_as_float(c[3 * v + 1]) + tmpl[cc + 1];
-            const float pz = __uint_as_float(m[3 * v + 2]) + __uint_as_float(c[3 * v + 2]) + tmpl[cc + 2];
+            constexpr float kLo = 1.0f / 2048.0f;   // the residual terms were scaled by 2^11 (flame.cuh)
+            const float px = __uint_as_float(m[3 * v]) + fmaf(__uint_as_float(c[3 * v]), kLo, tmpl[cc]);
+            const float py = __uint_as_float(m[3 * v + 1]) + fmaf(__uint_as_float(c[3 * v + 1]), kLo, tmpl[cc + 1]);
+            const float pz = __uint_as_float(m[3 * v + 2]) + fmaf(__uint_as_float(c[3 * v + 2]), kLo, tmpl[cc + 2]);
             const float* w = tw + (cc / 3) * 5;
             float T[12];
 #pragma unroll
@@ -191,34 +219,38 @@ __global__ void __launch_bounds__(FT_THREADS, 1) flame_tc_kernel(const __grid_co
               for (int j = 1; j < 5; ++j) s = fmaf(w[j], xf[j * 12 + e], s);
               T[e] = s;
             }
-            stage[lane * FT_OUT_STRIDE + 3 * v + 0] = T[0] * px + T[1] * py + T[2] * pz + T[9];
-            stage[lane * FT_OUT_STRIDE + 3 * v + 1] = T[3] * px + T[4] * py + T[5] * pz + T[10];
-            stage[lane * FT_OUT_STRIDE + 3 * v + 2] = T[6] * px + T[7] * py + T[8] * pz + T[11];
+            stage[lane * FT_OUT_STRIDE + cc + 0] = T[0] * px + T[1] * py + T[2] * pz + T[9];
+            stage[lane * FT_OUT_STRIDE + cc + 1] = T[3] * px + T[4] * py + T[5] * pz + T[10];
+            stage[lane * FT_OUT_STRIDE + cc + 2] = T[6] * px + T[7] * py + T[8] * pz + T[11];
           }
         }
-        __syncwarp();
-        // coalesced stores: one frame row (nv*3 contiguous floats) per iteration
-        const int ncol = nv * 3;
-        for (int r = 0; r < 32; ++r) {
-          const int grow = m0 + q * 32 + r;
-          if (grow >= p.B) break;
-          float* dst = p.out + (int64_t)grow * p.N3 + n0 + c0;
-          if (lane < ncol && n0 + c0 + lane < p.N3) __stcs(dst + lane, stage[r * FT_OUT_STRIDE + lane]);
-          if (lane + 32 < ncol && n0 + c0 + lane + 32 < p.N3) __stcs(dst + lane + 32, stage[r * FT_OUT_STRIDE + lane + 32]);
-        }
-        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[a]);
+      if (lane == 0) {   // accumulators are consumed: the MMAs of the next tile may overwrite them during the stores
+        if (cta_rank != 0) mbar_arrive_cluster(&tempty_bar[a], 0);   // the leader's MMA warp waits for both CTAs
+        else mbar_arrive(&tempty_bar[a]);
+      }
+      // both warps of the quarter have staged their vertices: store whole 504-byte tile rows, coalesced
+      asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
+      const int ncol = min(FT_BN, p.N3 - n0);
+      for (int r = half; r < 32; r += 2) {
+        const int grow = m0 + q * 32 + r;
+        if (grow >= p.B) break;
+        float* dst = p.out + (int64_t)grow * p.N3 + n0;
+        const float* src = stage + r * FT_OUT_STRIDE;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (lane + 32 * k < ncol) __stcs(dst + lane + 32 * k, src[lane + 32 * k]);
+      }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  cluster_sync();   // the peer may still be reading this CTA's smem / signalling its barriers
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc_2sm(tmem_base, 512);
   }
 }
 
@@ -229,15 +261,15 @@ int flame_decode_tc(msmd_flame* fh, int64_t B, float* verts_out, cudaStream_t st
   memset(&p, 0, sizeof(p));
   const int64_t rows = fh->cap_B;  // workspace rows (multiple of 128)
   int rc;
-  const auto f32 = CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
-  const uint64_t ldk = (uint64_t)fh->Kpad * 4;
+  const auto f32 = CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  const uint64_t ldk = (uint64_t)fh->Kpad * 2;
   if ((rc = make_tmap_2d(&p.a_hi, fh->A_hi, f32, fh->Kpad, rows, ldk, FT_BK, FT_BM, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   if ((rc = make_tmap_2d(&p.a_lo, fh->A_lo, f32, fh->Kpad, rows, ldk, FT_BK, FT_BM, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
-  if ((rc = make_tmap_2d(&p.b_hi, fh->basis_hi, f32, fh->Kpad, fh->N3pad, ldk, FT_BK, FT_BN, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
-  if ((rc = make_tmap_2d(&p.b_lo, fh->basis_lo, f32, fh->Kpad, fh->N3pad, ldk, FT_BK, FT_BN, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if ((rc = make_tmap_2d(&p.b_hi, fh->basis_hi, f32, fh->Kpad, fh->N3pad, ldk, FT_BK, 64, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if ((rc = make_tmap_2d(&p.b_lo, fh->basis_lo, f32, fh->Kpad, fh->N3pad, ldk, FT_BK, 64, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   p.tmpl = fh->v_template; p.weights = fh->weights; p.xf = fh->xf; p.out = verts_out;
   p.B = (int)B; p.V = fh->V; p.N3 = fh->N3; p.num_kb = fh->Kpad / FT_BK;
-  p.tiles_m = cdiv(B, FT_BM);
+  p.tiles_m = cdiv(B, 2 * FT_BM);
   p.tiles_n = cdiv(fh->N3, FT_BN);
   static bool attr = false;
   if (!attr) {
@@ -246,7 +278,18 @@ int flame_decode_tc(msmd_flame* fh, int64_t B, float* verts_out, cudaStream_t st
   }
   const int tiles = p.tiles_m * p.tiles_n;
   ProfileScope prof("flame_fused", st);
-  flame_tc_kernel<<<tiles < kNumSMs ? tiles : kNumSMs, FT_THREADS, FT_SMEM_BYTES, st>>>(p);
+  const int pairs = tiles < kNumSMs / 2 ? tiles : kNumSMs / 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(FT_THREADS);
+  cfg.dynamicSmemBytes = FT_SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr_c[1];
+  attr_c[0].id = cudaLaunchAttributeClusterDimension;
+  attr_c[0].val.clusterDim.x = 2; attr_c[0].val.clusterDim.y = 1; attr_c[0].val.clusterDim.z = 1;
+  cfg.attrs = attr_c;
+  cfg.numAttrs = 1;
+  MSMD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, flame_tc_kernel, p));
   MSMD_CHECK_LAUNCH();
   return MSMD_OK;
 }
