@@ -91,6 +91,8 @@ int msmd_quat_binary(int op, const float* a, const float* b, float* out, int64_t
  *   mode 0: x, w bf16; one tcgen05 kind::f16 pass, fp32 accumulation in TMEM.
  *   mode 1: fp32-grade: x/x_lo and w/w_lo are tf32 hi/lo splits (msmd_split_tf32); three
  *           kind::tf32 passes (hi*hi + hi*lo + lo*hi).  out/aux fp32.
+ *   mode 2: fp32-grade, faster: x/x_lo and w/w_lo are fp16 two-term splits (msmd_split_f16: x = hi + 2^-11 lo,
+ *           22 mantissa bits; |x| < 65504); three kind::f16 passes, cross terms rescaled in the epilogue.
  *   ld* are row strides in elements (rows must be 16-byte multiples apart); act 0 none, 1 GELU(erf);
  *   out_f32 / aux_f32 select fp32 (1) or bf16 (0) for out / aux.
  * ------------------------------------------------------------------------- */
@@ -98,6 +100,7 @@ int msmd_linear(int mode, const void* x, const void* x_lo, const void* w, const 
                 const float* bias, const void* aux, void* out, int M, int N, int K, int64_t ldx,
                 int64_t ldw, int64_t ldo, int64_t ld_aux, int out_f32, int aux_f32, int act, void* stream);
 int msmd_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream);
+int msmd_split_f16(const float* x, void* hi, void* lo, int64_t n, void* stream);   /* hi, lo: __half[n] */
 
 /* ------------------------------------------------------------------------- *
  * Denoiser + sampler — model.py:820-996 (DenoisingNetwork_MSMD), :282-440 (MSMD.sample),

@@ -159,11 +159,12 @@ def cfg_entries(sd, cfg, audio_feat, shape_feat, style_feat, cfg_mode, cfg_cond)
 
 def sample(sd, cfg, audio_feat, shape_feat, style_feat, prev_motion=None, prev_audio=None, x_T=None,
            z=None, indicator=None, cfg_mode=None, cfg_cond=None, cfg_scale=1.15, flexibility=0,
-           ret_traj=False, n_steps=None, denoise_fn=None, dynamic_threshold=None, separate=False):
+           ret_traj=False, n_steps=None, denoise_fn=None, dynamic_threshold=None, separate=False, t_start=None):
     """model.py:282-440 with externally supplied noise.
 
     z: [T+1, N, L, 67] indexed by t (z[t] used at step t > 1; zeros at t == 1), or None -> torch.randn.
     n_steps (< T) stops early after that many steps (tests); returns the state reached.
+    t_start (tests): begin at step t_start with x_T taken as x_{t_start} (teacher-forced single steps).
     Returns (x, x_T, audio_feat) like the reference; with ret_traj a dict {t: x_t}.
     dynamic_threshold = (ratio, min, max): per-sequence quantile clamp of the network output (model.py:396-402).
     separate=True follows MSMD.sample_separate (model.py:442-651, alpah_t_modification=None) and returns
@@ -204,9 +205,10 @@ def sample(sd, cfg, audio_feat, shape_feat, style_feat, prev_motion=None, prev_a
     cum_static = torch.zeros_like(x_T)
     alpha_traj, tgt_dyn = [], None
     x = x_T
-    traj = {T: x_T}
-    last = T - n_steps if n_steps else 0
-    for t in range(T, last, -1):
+    T0 = t_start or T
+    traj = {T0: x_T}
+    last = T0 - n_steps if n_steps else 0
+    for t in range(T0, last, -1):
         zt = (z[t] if z is not None else torch.randn_like(x)) if t > 1 else torch.zeros_like(x)
         alpha, ab, ab_prev = sched['alphas'][t], sched['alpha_bars'][t], sched['alpha_bars'][t - 1]
         sigma = sched['sigmas_flex'][t] * flexibility + sched['sigmas_inflex'][t] * (1 - flexibility)

@@ -24,8 +24,10 @@ def run_linear(mode, x, w, bias=None, aux=None, act=0, out_f32=False):
         p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
     else:
         def split(t):
-            hi, lo = torch.empty_like(t), torch.empty_like(t)
-            _lib.check(_lib.lib().msmd_split_tf32(t.data_ptr(), hi.data_ptr(), lo.data_ptr(), t.numel(), _lib.stream_ptr()))
+            dt = torch.float32 if mode == 1 else torch.float16
+            hi, lo = torch.empty_like(t, dtype=dt), torch.empty_like(t, dtype=dt)
+            fn = _lib.lib().msmd_split_tf32 if mode == 1 else _lib.lib().msmd_split_f16
+            _lib.check(fn(t.data_ptr(), hi.data_ptr(), lo.data_ptr(), t.numel(), _lib.stream_ptr()))
             return hi, lo
         xa, xl = split(x.float().contiguous())
         wa, wl = split(w.float().contiguous())
@@ -116,6 +118,26 @@ def test_gemm_tf32x3(built_lib, M, N, K):
     assert rel_l2(got, ref_linear(1, x, w, b, None, 0)) < tol
     got = run_linear(1, x, w, b, aux, 1, True)
     assert rel_l2(got, ref_linear(1, x, w, b, aux, 1)) < tol
+
+
+@pytest.mark.parametrize('M,N,K', [(128, 128, 64), (333, 512, 512), (1000, 1672, 448), (64, 2048, 512),
+                                   (777, 512, 2048), (2664, 1536, 512), (21312, 512, 512)])
+def test_gemm_fp16x3(built_lib, M, N, K):
+    """fp16 two-term split (x = hi + 2^-11 lo, 22 mantissa bits), three kind::f16 passes: fp32-grade like tf32x3,
+    single-CTA and CTA-pair tiles; also exercised with operands spanning 6 orders of magnitude."""
+    g = torch.Generator(device='cuda').manual_seed(6)
+    x = torch.randn(M, K, device='cuda', generator=g)
+    w = torch.randn(N, K, device='cuda', generator=g) / K ** 0.5
+    b = torch.randn(N, device='cuda', generator=g)
+    aux = torch.randn(M, N, device='cuda', generator=g)
+    tol = 1.5e-6 + 2.5e-9 * K
+    got = run_linear(2, x, w, b, None, 0, True)
+    assert rel_l2(got, ref_linear(1, x, w, b, None, 0)) < tol
+    got = run_linear(2, x, w, b, aux, 1, True)
+    assert rel_l2(got, ref_linear(1, x, w, b, aux, 1)) < tol
+    scale = torch.logspace(-3, 3, K, device='cuda')          # columns from 1e-3 to 1e3: residuals near fp16 subnormals
+    got = run_linear(2, x * scale, w / scale, b, None, 0, True)
+    assert rel_l2(got, ref_linear(1, x * scale, w / scale, b, None, 0)) < 2 * tol
 
 
 def test_gemm_strided_views(built_lib):

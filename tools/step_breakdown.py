@@ -14,6 +14,8 @@ af = torch.randn(clips, 100, 512, device='cuda', generator=g)
 st = torch.randn(clips, 256, device='cuda', generator=g)
 ind = torch.ones(clips, 100, device='cuda')
 m = wl.model
+if os.environ.get('MSMD_PRECISION'):
+    m.precision = m.denoising_net.precision = os.environ['MSMD_PRECISION']
 m.sample(af, d['shape'], st, motion_at_T=d['x_T'], indicator=ind, cfg_scale=1.4, noise=d['z'], n_steps=4)
 eng = m._eng
 torch.cuda.synchronize()

@@ -25,6 +25,7 @@ SIGNATURES = {
     'msmd_quat_binary': (_i, [_i, _vp, _vp, _vp, _i64, _vp]),
     'msmd_linear': (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i64, _i64, _i64, _i, _i, _i, _vp]),
     'msmd_split_tf32': (_i, [_vp, _vp, _vp, _i64, _vp]),
+    'msmd_split_f16': (_i, [_vp, _vp, _vp, _i64, _vp]),
     'msmd_create': (_i, [_vp, _i, C.POINTER(_vp)]),
     'msmd_destroy': (None, [_vp]),
     'msmd_load_weights': (_i, [_vp, C.POINTER(C.c_char_p), C.POINTER(_vp), C.POINTER(_i64), _i]),

@@ -12,6 +12,7 @@
 #include "denoiser_kernels.cuh"
 #include "gemm_tc.cuh"
 #include "profile.cuh"
+#include <cuda_fp16.h>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -27,10 +28,11 @@ struct LayerW {
   float *bqkv = nullptr, *bo = nullptr, *bq0 = nullptr, *bkv = nullptr, *bco = nullptr, *b1 = nullptr, *b2 = nullptr;
   float *g1 = nullptr, *be1 = nullptr, *g2 = nullptr, *be2 = nullptr, *g3 = nullptr, *be3 = nullptr;
   bf16 *kv = nullptr, *ca = nullptr;  // per-window caches
-  // fp32-grade path (precision >= 1): tf32 hi/lo splits of the same weights and fp32 caches
-  float *Wqkv_h = nullptr, *Wqkv_l = nullptr, *Wo_h = nullptr, *Wo_l = nullptr, *Wq0_h = nullptr, *Wq0_l = nullptr,
-        *Wkv_h = nullptr, *Wkv_l = nullptr, *Wco_h = nullptr, *Wco_l = nullptr, *W1_h = nullptr, *W1_l = nullptr,
-        *W2_h = nullptr, *W2_l = nullptr;
+  // fp32-grade path (precision >= 1): fp16 two-term splits (x = hi + 2^-11 lo, gemm_tc.cuh MODE 2) of the same
+  // weights, and fp32 caches
+  __half *Wqkv_h = nullptr, *Wqkv_l = nullptr, *Wo_h = nullptr, *Wo_l = nullptr, *Wq0_h = nullptr, *Wq0_l = nullptr,
+         *Wkv_h = nullptr, *Wkv_l = nullptr, *Wco_h = nullptr, *Wco_l = nullptr, *W1_h = nullptr, *W1_l = nullptr,
+         *W2_h = nullptr, *W2_l = nullptr;
   float *kv32 = nullptr, *ca32 = nullptr;
 };
 
@@ -65,9 +67,10 @@ struct msmd_model {
         *hid = nullptr, *xbuf = nullptr, *mixed = nullptr, *thr = nullptr;
   int* steps = nullptr;
   // fp32-grade path workspaces
-  float *Wd1_h = nullptr, *Wd1_l = nullptr, *Wd2_h = nullptr, *Wd2_l = nullptr;
+  __half *Wd1_h = nullptr, *Wd1_l = nullptr, *Wd2_h = nullptr, *Wd2_l = nullptr;
   float *fx = nullptr, *fqkv = nullptr, *fctx = nullptr, *fh = nullptr, *fy = nullptr, *fdec1 = nullptr, *fmem = nullptr,
-        *fx0c = nullptr, *fq0 = nullptr, *fctx0 = nullptr, *fy0 = nullptr, *ws_hi = nullptr, *ws_lo = nullptr;
+        *fx0c = nullptr, *fq0 = nullptr, *fctx0 = nullptr, *fy0 = nullptr;
+  __half *ws_hi = nullptr, *ws_lo = nullptr;   // split scratch of the current A operand
   bool f32_ready = false, window32 = false;
   const float *w_audio = nullptr, *w_prev_audio = nullptr;   // conditioning kept for the lazy fp32 window pass
   // window state
@@ -110,27 +113,27 @@ int gemm(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const float* bi
   return gemm_tc_launch(d, st);
 }
 
-int up_split(msmd_model* m, float** hi, float** lo, const float* h, size_t n) {
-  std::vector<float> a(n), b(n);
+int up_split(msmd_model* m, __half** hi, __half** lo, const float* h, size_t n) {
+  std::vector<__half> a(n), b(n);
   for (size_t i = 0; i < n; ++i) {
-    uint32_t u;
-    memcpy(&u, &h[i], 4);
-    u &= 0xffffe000u;
-    memcpy(&a[i], &u, 4);
-    b[i] = h[i] - a[i];
+    a[i] = __float2half_rn(h[i]);
+    b[i] = __float2half_rn((h[i] - __half2float(a[i])) * 2048.0f);
   }
-  int rc = up_f32(m, hi, a);
-  return rc ? rc : up_f32(m, lo, b);
+  int rc;
+  if ((rc = dalloc(m, hi, n)) || (rc = dalloc(m, lo, n))) return rc;
+  MSMD_CHECK_CUDA(cudaMemcpy(*hi, a.data(), n * sizeof(__half), cudaMemcpyHostToDevice));
+  MSMD_CHECK_CUDA(cudaMemcpy(*lo, b.data(), n * sizeof(__half), cudaMemcpyHostToDevice));
+  return MSMD_OK;
 }
 
-// fp32-grade linear: split the activations (tf32 hi + remainder), then the 3-pass tcgen05 GEMM
-int gemm32(msmd_model* m, const float* A, int64_t lda, const float* Wh, const float* Wl, int64_t ldw, const float* bias,
+// fp32-grade linear: split the activations (fp16 hi + scaled fp16 residual), then the 3-pass tcgen05 GEMM
+int gemm32(msmd_model* m, const float* A, int64_t lda, const __half* Wh, const __half* Wl, int64_t ldw, const float* bias,
            float* out, int64_t ldo, int M, int N, int K, int act, cudaStream_t st) {
   int rc;
   // the split kernel works on contiguous [M, lda] storage; K <= lda columns are used by the GEMM
-  if ((rc = split_tf32(A, m->ws_hi, m->ws_lo, (int64_t)(M - 1) * lda + K, st))) return rc;
+  if ((rc = split_f16(A, m->ws_hi, m->ws_lo, (int64_t)(M - 1) * lda + K, st))) return rc;
   GemmDesc d;
-  d.mode = 1; d.A = m->ws_hi; d.A_lo = m->ws_lo; d.W = Wh; d.W_lo = Wl; d.bias = bias; d.out = out;
+  d.mode = 2; d.A = m->ws_hi; d.A_lo = m->ws_lo; d.W = Wh; d.W_lo = Wl; d.bias = bias; d.out = out;
   d.M = M; d.N = N; d.K = K; d.lda = lda; d.ldw = ldw; d.ldo = ldo; d.out_f32 = 1; d.aux_f32 = 1; d.act = act;
   return gemm_tc_launch(d, st);
 }
@@ -179,9 +182,9 @@ int window_begin_f32(msmd_model* m, cudaStream_t st) {
   for (auto& w : m->L) {
     if ((rc = gemm32(m, m->fmem, d, w.Wkv_h, w.Wkv_l, d, w.bkv, w.kv32, 2 * d, S * Tk, 2 * d, d, 0, st))) return rc;
     // v half of the kv cache as a strided A operand: row stride 2d, K = d columns starting at column d
-    if ((rc = split_tf32(w.kv32, m->ws_hi, m->ws_lo, (int64_t)S * Tk * 2 * d, st))) return rc;
+    if ((rc = split_f16(w.kv32, m->ws_hi, m->ws_lo, (int64_t)S * Tk * 2 * d, st))) return rc;
     GemmDesc g;
-    g.mode = 1; g.A = m->ws_hi + d; g.A_lo = m->ws_lo + d; g.W = w.Wco_h; g.W_lo = w.Wco_l; g.bias = w.bco; g.out = w.ca32;
+    g.mode = 2; g.A = m->ws_hi + d; g.A_lo = m->ws_lo + d; g.W = w.Wco_h; g.W_lo = w.Wco_l; g.bias = w.bco; g.out = w.ca32;
     g.M = S * Tk; g.N = d; g.K = d; g.lda = 2 * d; g.ldw = d; g.ldo = d; g.out_f32 = 1; g.aux_f32 = 1;
     if ((rc = gemm_tc_launch(g, st))) return rc;
   }
@@ -319,11 +322,11 @@ extern "C" int msmd_load_weights(msmd_model* m, const char* const* names, const 
   auto F32 = [&](const std::string& key, size_t n_, float** dst) { if (!rc && fetch(key, n_, h)) rc = up_f32(m, dst, h); };
   const bool want_bf = c.precision != 1, want_f32 = c.precision >= 1;
   // a GEMM weight: bf16 copy for the bf16 path and/or tf32 hi/lo split for the fp32-grade path
-  auto put_w = [&](const float* src, size_t n_, bf16** dst, float** hi, float** lo) {
+  auto put_w = [&](const float* src, size_t n_, bf16** dst, __half** hi, __half** lo) {
     if (!rc && want_bf) rc = up_bf16(m, dst, src, n_);
     if (!rc && want_f32) rc = up_split(m, hi, lo, src, n_);
   };
-  auto BF = [&](const std::string& key, size_t n_, bf16** dst, float** hi, float** lo) {
+  auto BF = [&](const std::string& key, size_t n_, bf16** dst, __half** hi, __half** lo) {
     if (!rc && fetch(key, n_, h)) put_w(h.data(), n_, dst, hi, lo);
   };
 

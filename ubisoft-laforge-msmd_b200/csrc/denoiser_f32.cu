@@ -4,6 +4,7 @@
 // (<= 1e-5 per sampling step) and to cover the last sampling steps where bf16 rounding of x0_hat is no
 // longer damped by c1(t).
 #include "denoiser_kernels.cuh"
+#include "profile.cuh"
 
 namespace msmd {
 
@@ -83,6 +84,7 @@ __global__ void embed_f32_kernel(EmbedParams p, float* __restrict__ out) {
   }
 }
 int embed_f32_launch(const EmbedParams& p, float* out, cudaStream_t st) {
+  ProfileScope prof("embed_f32", st);
   embed_f32_kernel<<<p.S * (1 + p.Lp + p.L), 128, 0, st>>>(p, out);
   MSMD_CHECK_LAUNCH();
   return MSMD_OK;
@@ -111,6 +113,7 @@ __global__ void __launch_bounds__(256) ln_f32_kernel(const float* __restrict__ y
 }
 int ln_f32_launch(const float* y, const float* resid, const float* g1, const float* b1, const float* add, const float* g2,
                   const float* b2, float* out, float* x0, int M, int T, cudaStream_t st) {
+  ProfileScope prof("ln_f32", st);
   ln_f32_kernel<<<cdiv(M, 8), 256, 0, st>>>(y, resid, g1, b1, add, g2, b2, out, x0, M, T);
   MSMD_CHECK_LAUNCH();
   return MSMD_OK;
@@ -164,12 +167,17 @@ __global__ void __launch_bounds__(128) self_attn_f32_kernel(const float* __restr
     float sc = 0.f;
 #pragma unroll
     for (int c = 0; c < 64; ++c) sc = fmaf(q[c], sK[j * 64 + c], sc);
-    const float mn = fmaxf(m, sc);
-    const float a = expf(m - mn), pj = expf(sc - mn);
-    l = l * a + pj;
+    if (sc > m) {   // new running maximum (rare after the first keys): rescale what has been accumulated
+      const float a = expf(m - sc);
+      l *= a;
 #pragma unroll
-    for (int c = 0; c < 64; ++c) o[c] = fmaf(pj, sV[j * 64 + c], o[c] * a);
-    m = mn;
+      for (int c = 0; c < 64; ++c) o[c] *= a;
+      m = sc;
+    }
+    const float pj = expf(sc - m);
+    l += pj;
+#pragma unroll
+    for (int c = 0; c < 64; ++c) o[c] = fmaf(pj, sV[j * 64 + c], o[c]);
   }
   const float inv = 1.0f / l;
   float* dst = ctx + ((int64_t)s * T + i) * d + h * 64;
@@ -185,6 +193,7 @@ int self_attn_f32_launch(const float* qkv, float* ctx, int S, int T, int H, cuda
     attr = true;
   }
   MSMD_REQUIRE(T <= 128, "self_attn_f32: T %d > 128", T);
+  ProfileScope prof("self_attn_f32", st);
   self_attn_f32_kernel<<<dim3(H, S), 128, smem, st>>>(qkv, ctx, T, H);
   MSMD_CHECK_LAUNCH();
   return MSMD_OK;
@@ -231,6 +240,7 @@ __global__ void __launch_bounds__(256) cross_attn_row0_f32_kernel(const float* _
 }
 int cross_attn_row0_f32_launch(const float* q0, const float* kv, float* ctx0, int S, int Tk, int H, cudaStream_t st) {
   MSMD_REQUIRE(Tk <= 128, "cross_attn_row0_f32: memory length %d > 128", Tk);
+  ProfileScope prof("cross_attn_row0_f32", st);
   cross_attn_row0_f32_kernel<<<cdiv(S * H, 8), 256, 0, st>>>(q0, kv, ctx0, S, Tk, H);
   MSMD_CHECK_LAUNCH();
   return MSMD_OK;

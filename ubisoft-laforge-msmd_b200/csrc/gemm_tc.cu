@@ -1,6 +1,8 @@
 // Host side of the tcgen05 GEMM core: tensor-map construction, config dispatch, C-ABI test entry.
 #include "gemm_tc.cuh"
 #include "profile.cuh"
+#include <cuda_fp16.h>
+#include <algorithm>
 #include <cudaTypedefs.h>
 #include <mutex>
 #include <cstdlib>
@@ -76,7 +78,8 @@ template <class Cfg, int MODE, bool GELU>
 static int launch_cfg2(const GemmDesc& d, cudaStream_t st) {
   GemmParams p;
   memset(&p, 0, sizeof(p));
-  const auto in_dt = MODE == 0 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  const auto in_dt = MODE == 0 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                               : (MODE == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
   const int esz = Cfg::ELT;
   int rc;
   if ((rc = make_tmap_23(&p.a_map, d.A, in_dt, esz, d.K, d.M, d.lda, d.batch, d.sA, Cfg::BK, Cfg::BM))) return rc;
@@ -84,11 +87,11 @@ static int launch_cfg2(const GemmDesc& d, cudaStream_t st) {
     const int wb = (d.batch > 1 && d.wz_mod != 0) ? (d.wz_mod > 0 ? d.wz_mod : d.batch) : 1;
     if ((rc = make_tmap_23(&p.b_map, d.W, in_dt, esz, d.K, d.N, d.ldw, wb, d.sW, Cfg::BK, Cfg::B_ROWS))) return rc;
   }
-  if (MODE == 1) {
-    MSMD_REQUIRE(d.A_lo && d.W_lo, "gemm: tf32x3 mode needs the lo operands");
-    MSMD_REQUIRE(d.batch <= 1, "gemm: batched tf32x3 is not implemented");
+  if (MODE != 0) {
+    MSMD_REQUIRE(d.A_lo && d.W_lo, "gemm: the three-pass modes need the lo operands");
+    MSMD_REQUIRE(d.batch <= 1, "gemm: batched three-pass GEMMs are not implemented");
     if ((rc = make_tmap_23(&p.a_lo_map, d.A_lo, in_dt, esz, d.K, d.M, d.lda, 1, 0, Cfg::BK, Cfg::BM))) return rc;
-    if ((rc = make_tmap_23(&p.b_lo_map, d.W_lo, in_dt, esz, d.K, d.N, d.ldw, 1, 0, Cfg::BK, Cfg::BN))) return rc;
+    if ((rc = make_tmap_23(&p.b_lo_map, d.W_lo, in_dt, esz, d.K, d.N, d.ldw, 1, 0, Cfg::BK, Cfg::B_ROWS))) return rc;
   }
   using OutT = typename Cfg::OutT;
   using AuxT = typename Cfg::AuxT;
@@ -128,7 +131,7 @@ static int launch_cfg2(const GemmDesc& d, cudaStream_t st) {
     MSMD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  ProfileScope prof(MODE == 0 ? "gemm_bf16" : "gemm_tf32x3", st);
+  ProfileScope prof(MODE == 0 ? "gemm_bf16" : (MODE == 1 ? "gemm_tf32x3" : "gemm_fp16x3"), st);
   char shape_name[64];
   snprintf(shape_name, sizeof(shape_name), "gemm_%dx%dx%d%s", d.M, d.N, d.K, Cfg::CTA2 ? "_pair" : "");
   ProfileScope prof2(profiling_on() ? strdup(shape_name) : "", st);
@@ -224,8 +227,15 @@ int gemm_tc_launch(const GemmDesc& d, cudaStream_t st) {
     set_error("gemm: bf16 output with fp32 aux is not instantiated");
     return MSMD_ERR_UNSUPPORTED;
   }
-  MSMD_REQUIRE(d.mode == 1, "gemm: unknown mode %d", d.mode);
-  MSMD_REQUIRE(d.out_f32 && (!aux || d.aux_f32), "gemm: tf32x3 mode is fp32 in / fp32 out");
+  MSMD_REQUIRE(d.mode == 1 || d.mode == 2, "gemm: unknown mode %d", d.mode);
+  MSMD_REQUIRE(d.out_f32 && (!aux || d.aux_f32), "gemm: the three-pass modes are fp32 out");
+  if (d.mode == 2) {
+    static const bool cta2_env2 = [] { const char* e = getenv("MSMD_GEMM_CTA2"); return !e || atoi(e) != 0; }();
+    if (aux) return launch_cfg<GemmCfg<2, 128, 4, true, float, float>, 2>(d, st);
+    if (d.cta2 != 0 && cta2_env2 && d.batch <= 1 && d.N >= 256 && d.M >= 2048)
+      return launch_cfg<GemmCfg<2, 128, 4, false, float, float, true>, 2>(d, st);
+    return launch_cfg<GemmCfg<2, 128, 4, false, float, float>, 2>(d, st);
+  }
   if (aux) return launch_cfg<GemmCfg<1, 128, 4, true, float, float>, 1>(d, st);
   return launch_cfg<GemmCfg<1, 128, 4, false, float, float>, 1>(d, st);
 }
@@ -238,6 +248,24 @@ __global__ void split_tf32_kernel(const float* __restrict__ x, float* __restrict
     hi[i] = h;
     lo[i] = v - h;
   }
+}
+
+// fp16 two-term split: hi = fp16(x), lo = fp16((x - hi) * 2^11); x ~= hi + 2^-11 lo to 22 mantissa bits
+__global__ void split_f16_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    const __half h = __float2half_rn(v);
+    hi[i] = h;
+    lo[i] = __float2half_rn((v - __half2float(h)) * 2048.0f);
+  }
+}
+int split_f16(const float* x, __half* hi, __half* lo, int64_t n, cudaStream_t st) {
+  if (n == 0) return MSMD_OK;
+  ProfileScope prof("split_f16", st);
+  const int blocks = (int)std::min<int64_t>(cdiv(n, 256), kNumSMs * 16);
+  split_f16_kernel<<<blocks, 256, 0, st>>>(x, hi, lo, n);
+  MSMD_CHECK_LAUNCH();
+  return MSMD_OK;
 }
 
 int split_tf32(const float* x, float* hi, float* lo, int64_t n, cudaStream_t st) {
@@ -261,6 +289,12 @@ extern "C" int msmd_linear(int mode, const void* x, const void* x_lo, const void
   d.M = M; d.N = N; d.K = K; d.lda = ldx; d.ldw = ldw; d.ldo = ldo; d.ld_aux = ld_aux;
   d.out_f32 = out_f32; d.aux_f32 = aux_f32; d.act = act & 1; d.gelu_heavy = (act & 1);
   return gemm_tc_launch(d, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int msmd_split_f16(const float* x, void* hi, void* lo, int64_t n, void* stream) {
+  MSMD_REQUIRE(n >= 0, "msmd_split_f16: negative count");
+  MSMD_REQUIRE(n == 0 || (x && hi && lo), "msmd_split_f16: null pointer");
+  return split_f16(x, static_cast<__half*>(hi), static_cast<__half*>(lo), n, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int msmd_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream) {

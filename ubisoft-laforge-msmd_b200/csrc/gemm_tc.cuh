@@ -9,10 +9,15 @@
 // MODE 0: bf16 operands, one pass (kind::f16).
 // MODE 1: fp32-grade "tf32x3": operands pre-split into hi (tf32-exact) + lo (remainder); three
 //         kind::tf32 MMAs per k-step (hi*hi + hi*lo + lo*hi), error ~2^-21 relative.
+// MODE 2: fp32-grade "fp16x3": operands pre-split into fp16 hi + fp16 lo with x = hi + 2^-11 lo (22 mantissa bits,
+//         msmd_split_f16); three kind::f16 MMAs per k-step, the cross terms rescaled in the epilogue.  Half the MMA
+//         instructions and operand bytes of MODE 1 (a K=8 tf32 MMA moves as many bytes as a K=16 fp16 one), but
+//         |x| must stay below the fp16 range (65504).
 #pragma once
 #include "common.cuh"
 #include "tc_common.cuh"
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 namespace msmd {
 
@@ -43,7 +48,7 @@ struct GemmCfg {
   static constexpr int BN = BN_, EPI_WARPS = EPI_WARPS_;
   static constexpr bool HAS_AUX = HAS_AUX_;
   static constexpr int BM = 128;
-  static constexpr int ELT = MODE == 0 ? 2 : 4;
+  static constexpr int ELT = MODE == 1 ? 4 : 2;
   static constexpr int BK = 128 / ELT;  // one 128-byte swizzle atom of K per stage
   static constexpr int UK = 32 / ELT;   // K per tcgen05.mma (32 bytes)
   static constexpr int B_ROWS = CTA2 ? BN / 2 : BN;     // W rows this CTA stages per k-block
@@ -74,7 +79,7 @@ struct GemmCfg {
   static_assert(COLS_PER_WARP % 64 == 0, "the epilogue processes 32-column chunks in pairs");
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
   static_assert(STAGES >= 2, "not enough shared memory for a pipeline");
-  static_assert(!CTA2 || (MODE == 0 && !HAS_AUX && BN % 32 == 0), "CTA-pair variant: bf16, no aux");
+  static_assert(!CTA2 || (MODE != 1 && !HAS_AUX && BN % 32 == 0), "CTA-pair variant: 16-bit operands, no aux");
 };
 
 // erf by Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7): enough for a bf16-rounded GELU, 3x cheaper than erff
@@ -148,7 +153,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_tc_kernel(const __grid_c
     prefetch_tmap(&p.a_map);
     prefetch_tmap(&p.b_map);
     prefetch_tmap(&p.out_map);
-    if (MODE == 1) { prefetch_tmap(&p.a_lo_map); prefetch_tmap(&p.b_lo_map); }
+    if (MODE != 0) { prefetch_tmap(&p.a_lo_map); prefetch_tmap(&p.b_lo_map); }
     if (Cfg::HAS_AUX) prefetch_tmap(&p.aux_map);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], Cfg::EPI_WARPS * (Cfg::CTA2 ? 2 : 1)); }
@@ -194,6 +199,10 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_tc_kernel(const __grid_c
             if (cta_rank == 0) mbar_expect_tx(&full_bar[s], 2 * Cfg::STAGE_BYTES);  // both CTAs' boxes land here
             tma_load_2d_2sm(sa, &p.a_map, &full_bar[s], kb * BK, m0);
             tma_load_2d_2sm(sb, &p.b_map, &full_bar[s], kb * BK, n0 + cta_rank * Cfg::B_ROWS);
+            if (MODE != 0) {
+              tma_load_2d_2sm(sa + Cfg::A_BYTES, &p.a_lo_map, &full_bar[s], kb * BK, m0);
+              tma_load_2d_2sm(sb + Cfg::B_BYTES, &p.b_lo_map, &full_bar[s], kb * BK, n0 + cta_rank * Cfg::B_ROWS);
+            }
           } else if (p.batch > 1) {
             mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
             tma_load_3d(sa, &p.a_map, &full_bar[s], kb * BK, m0, z);
@@ -203,7 +212,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_tc_kernel(const __grid_c
             mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
             tma_load_2d(sa, &p.a_map, &full_bar[s], kb * BK, m0);
             tma_load_2d(sb, &p.b_map, &full_bar[s], kb * BK, n0);
-            if (MODE == 1) {
+            if (MODE != 0) {
               tma_load_2d(sa + Cfg::A_BYTES, &p.a_lo_map, &full_bar[s], kb * BK, m0);
               tma_load_2d(sb + Cfg::B_BYTES, &p.b_lo_map, &full_bar[s], kb * BK, n0);
             }
@@ -215,7 +224,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_tc_kernel(const __grid_c
     }
   } else if (warp == 1) {
     // ------------------------------------------------ MMA issuer (lane 0 issues for the whole CTA)
-    constexpr uint32_t idesc = make_idesc(MODE == 0 ? 1 : 2, Cfg::UMMA_M, BN);
+    constexpr uint32_t idesc = make_idesc(MODE == 0 ? 1 : (MODE == 1 ? 2 : 0), Cfg::UMMA_M, BN);   // bf16 / tf32 / fp16
     int s = 0;
     uint32_t ph = 0;
     int it = 0;
@@ -241,15 +250,21 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_tc_kernel(const __grid_c
 #pragma unroll
           for (int k = 0; k < BK / Cfg::UK; ++k) {
             const uint32_t acc = (kb | k) != 0;
-            if constexpr (Cfg::CTA2) {
-              umma_2sm(d_tmem, desc_advance(da, k * 32), desc_advance(db, k * 32), idesc, acc);
-            } else if constexpr (MODE == 0) {
-              umma<0>(d_tmem, desc_advance(da, k * 32), desc_advance(db, k * 32), idesc, acc);
+            if constexpr (MODE == 0) {
+              if constexpr (Cfg::CTA2) umma_2sm(d_tmem, desc_advance(da, k * 32), desc_advance(db, k * 32), idesc, acc);
+              else umma<0>(d_tmem, desc_advance(da, k * 32), desc_advance(db, k * 32), idesc, acc);
             } else {
               const uint64_t dal = make_smem_desc_sw128(sa + Cfg::A_BYTES), dbl = make_smem_desc_sw128(sb + Cfg::B_BYTES);
-              umma<1>(d_tmem + BN, desc_advance(dal, k * 32), desc_advance(db, k * 32), idesc, acc);  // lo * hi
-              umma<1>(d_tmem + BN, desc_advance(da, k * 32), desc_advance(dbl, k * 32), idesc, 1u);   // hi * lo
-              umma<1>(d_tmem, desc_advance(da, k * 32), desc_advance(db, k * 32), idesc, acc);        // hi * hi
+              constexpr int KIND = MODE == 1 ? 1 : 0;
+              if constexpr (Cfg::CTA2) {
+                umma_2sm(d_tmem + BN, desc_advance(dal, k * 32), desc_advance(db, k * 32), idesc, acc);  // lo * hi
+                umma_2sm(d_tmem + BN, desc_advance(da, k * 32), desc_advance(dbl, k * 32), idesc, 1u);   // hi * lo
+                umma_2sm(d_tmem, desc_advance(da, k * 32), desc_advance(db, k * 32), idesc, acc);        // hi * hi
+              } else {
+                umma<KIND>(d_tmem + BN, desc_advance(dal, k * 32), desc_advance(db, k * 32), idesc, acc);  // lo * hi
+                umma<KIND>(d_tmem + BN, desc_advance(da, k * 32), desc_advance(dbl, k * 32), idesc, 1u);   // hi * lo
+                umma<KIND>(d_tmem, desc_advance(da, k * 32), desc_advance(db, k * 32), idesc, acc);        // hi * hi
+              }
             }
           }
           if constexpr (Cfg::CTA2) umma_commit_2sm(&empty_bar[s]);
@@ -340,7 +355,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_tc_kernel(const __grid_c
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + a * Cfg::ACC_COLS + csplit * CPW;
       const float* sbw = sb + csplit * CPW;
 
-      auto process = [&](uint32_t (&raw)[32], uint32_t (&raw2)[MODE == 1 ? 32 : 1], int c) {
+      auto process = [&](uint32_t (&raw)[32], uint32_t (&raw2)[MODE != 0 ? 32 : 1], int c) {
         const uint8_t* aux_buf = nullptr;
         int aux_off = 0;
         if constexpr (Cfg::HAS_AUX) {
@@ -364,6 +379,10 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_tc_kernel(const __grid_c
         if constexpr (MODE == 1) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(raw2[j]);
+        }
+        if constexpr (MODE == 2) {   // cross terms carry the 2^11 scale of the residual operands
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(raw2[j]), 1.0f / 2048.0f, v[j]);
         }
         if constexpr (GELU) {
 #pragma unroll
@@ -437,7 +456,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_tc_kernel(const __grid_c
           else mbar_arrive(&tempty_bar[a]);
         }
       };
-      if constexpr (MODE == 1) {
+      if constexpr (MODE != 0) {
         // software-pipelined TMEM reads: chunk c+1 is in flight while chunk c is processed
         uint32_t rA[32], rB[32], rA2[32], rB2[32];
         tmem_ld32(t_addr, rA);
@@ -506,7 +525,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_tc_kernel(const __grid_c
 // ---------------------------------------------------------------------------------------------
 // Host-side description of one GEMM call.  Element strides; row-major [rows, K] operands.
 struct GemmDesc {
-  int mode = 0;                 // 0 bf16, 1 tf32x3
+  int mode = 0;                 // 0 bf16, 1 tf32x3, 2 fp16x3 (A/W hi and lo are __half, x = hi + 2^-11 lo)
   const void* A = nullptr;      // [M,K] bf16 (mode 0) / fp32 hi (mode 1)
   const void* A_lo = nullptr;   // mode 1
   const void* W = nullptr;      // [N,K]
@@ -529,5 +548,6 @@ struct GemmDesc {
 };
 
 int gemm_tc_launch(const GemmDesc& d, cudaStream_t st);
+int split_f16(const float* x, __half* hi, __half* lo, int64_t n, cudaStream_t st);
 
 }  // namespace msmd

@@ -83,7 +83,7 @@ class _EngineOwner:
     'fp32' (fp32 activations + 3-pass tf32 tensor-core GEMMs, ~1e-6 of the fp32 reference) or 'hybrid' (both
     resident; ``precise_last_steps`` = the sampler's last k steps run in fp32-grade arithmetic)."""
     precision = 'bf16'
-    precise_last_steps = 0
+    precise_last_steps = 0     # int, or 'auto': every step whose bf16 error could exceed 1e-3 (MSMD.auto_precise_steps)
 
     def _engine_state(self):
         raise NotImplementedError
@@ -243,6 +243,26 @@ class MSMD(nn.Module, _EngineOwner):
             return out
         return (lambda cap: _engine_cfg(net, self.diffusion_sched.num_steps, self.target, cap, self.precision)), sd
 
+    def auto_precise_steps(self, tol=1e-3, bf16_err=1.5e-2):
+        """Number of final sampling steps whose bf16 error could exceed ``tol``: x_{t-1} = c0 x_t + c1(t) x0_hat + sigma z
+        carries the network's bf16 error (``bf16_err`` = the tested bound on x0_hat) scaled by c1(t),
+        which decreases with t; 26 of 500 steps for the cosine schedule."""
+        sch = self.diffusion_sched
+        a, ab = sch.alphas.double().cpu(), sch.alpha_bars.double().cpu()
+        t = torch.arange(1, sch.num_steps + 1)
+        if self.target == 'noise':
+            c1 = (1 - a[t]) / torch.sqrt(1 - ab[t]) / torch.sqrt(a[t])
+        else:
+            c1 = (1 - a[t]) * torch.sqrt(ab[t - 1]) / (1 - ab[t])
+        over = torch.nonzero(c1 * bf16_err > tol)
+        return int(over.max()) + 1 if len(over) else 0
+
+    def _precise_steps(self, override=None):
+        if self.precision != 'hybrid':
+            return 0
+        k = self.precise_last_steps if override is None else override
+        return self.auto_precise_steps() if k == 'auto' else int(k)
+
     @torch.no_grad()
     def extract_audio_feature(self, audio, frame_num=None):
         """model.py:250-264: [N, samples] -> [N, frame_num, feature_dim], all inside the CUDA audio encoder."""
@@ -326,8 +346,7 @@ class MSMD(nn.Module, _EngineOwner):
         res = eng.sample_window(motion_at_T, noise, seed, cfg_mode == 'independent', s0, s1, flexibility,
                                 t_start=T, n_steps=n_steps, want_traj=ret_traj, dynamic_threshold=dynamic_threshold,
                                 separate=_separate,
-                                precise_last_steps=(self.precise_last_steps if precise_last_steps is None
-                                                    else precise_last_steps) if self.precision == 'hybrid' else 0)
+                                precise_last_steps=self._precise_steps(precise_last_steps))
         x0, traj = res[0], res[1]
         if _separate and not ret_traj:
             return x0, motion_at_T, audio_feat, res[2]
