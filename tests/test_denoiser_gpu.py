@@ -216,3 +216,20 @@ def test_hybrid_every_step_within_1e3_at_T500(built_lib):
         if t <= k:
             assert err < F32_TOL, (t, err)
     print(f'hybrid auto (k={k}): worst single-step rel-L2 over the sampled steps = {worst:.2e}')
+
+
+def test_fp32_grade_path_reports_operands_outside_fp16_range(built_lib):
+    """The fp32-grade GEMMs split their operands into two fp16 terms; an activation beyond 65504 cannot be
+    represented and must fail loudly (not return NaNs)."""
+    m, args = make_msmd('cuda')
+    _set_precision(m, 'fp32')
+    i = {k: v.cuda() for k, v in synth.denoiser_inputs(2, 5).items()}
+    ok = m.denoising_net(i['motion'], i['audio'], i['person'], i['style'], i['prev_motion'], i['prev_audio'], i['step'],
+                         i['indicator'])
+    assert torch.isfinite(ok).all()
+    with pytest.raises(Exception, match='fp16 range'):
+        m.denoising_net(i['motion'], i['audio'] * 1e6, i['person'], i['style'], i['prev_motion'], i['prev_audio'],
+                        i['step'], i['indicator'])
+    again = m.denoising_net(i['motion'], i['audio'], i['person'], i['style'], i['prev_motion'], i['prev_audio'], i['step'],
+                            i['indicator'])
+    assert torch.equal(ok, again)        # the flag is cleared: the engine keeps working

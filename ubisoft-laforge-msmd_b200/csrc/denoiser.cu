@@ -71,6 +71,7 @@ struct msmd_model {
   float *fx = nullptr, *fqkv = nullptr, *fctx = nullptr, *fh = nullptr, *fy = nullptr, *fdec1 = nullptr, *fmem = nullptr,
         *fx0c = nullptr, *fq0 = nullptr, *fctx0 = nullptr, *fy0 = nullptr;
   __half *ws_hi = nullptr, *ws_lo = nullptr;   // split scratch of the current A operand
+  int* overflow = nullptr;                     // raised by the operand split when an activation leaves the fp16 range
   bool f32_ready = false, window32 = false;
   const float *w_audio = nullptr, *w_prev_audio = nullptr;   // conditioning kept for the lazy fp32 window pass
   // window state
@@ -131,7 +132,7 @@ int gemm32(msmd_model* m, const float* A, int64_t lda, const __half* Wh, const _
            float* out, int64_t ldo, int M, int N, int K, int act, cudaStream_t st) {
   int rc;
   // the split kernel works on contiguous [M, lda] storage; K <= lda columns are used by the GEMM
-  if ((rc = split_f16(A, m->ws_hi, m->ws_lo, (int64_t)(M - 1) * lda + K, st))) return rc;
+  if ((rc = split_f16(A, m->ws_hi, m->ws_lo, (int64_t)(M - 1) * lda + K, st, m->overflow))) return rc;
   GemmDesc d;
   d.mode = 2; d.A = m->ws_hi; d.A_lo = m->ws_lo; d.W = Wh; d.W_lo = Wl; d.bias = bias; d.out = out;
   d.M = M; d.N = N; d.K = K; d.lda = lda; d.ldw = ldw; d.ldo = ldo; d.out_f32 = 1; d.aux_f32 = 1; d.act = act;
@@ -182,7 +183,7 @@ int window_begin_f32(msmd_model* m, cudaStream_t st) {
   for (auto& w : m->L) {
     if ((rc = gemm32(m, m->fmem, d, w.Wkv_h, w.Wkv_l, d, w.bkv, w.kv32, 2 * d, S * Tk, 2 * d, d, 0, st))) return rc;
     // v half of the kv cache as a strided A operand: row stride 2d, K = d columns starting at column d
-    if ((rc = split_f16(w.kv32, m->ws_hi, m->ws_lo, (int64_t)S * Tk * 2 * d, st))) return rc;
+    if ((rc = split_f16(w.kv32, m->ws_hi, m->ws_lo, (int64_t)S * Tk * 2 * d, st, m->overflow))) return rc;
     GemmDesc g;
     g.mode = 2; g.A = m->ws_hi + d; g.A_lo = m->ws_lo + d; g.W = w.Wco_h; g.W_lo = w.Wco_l; g.bias = w.bco; g.out = w.ca32;
     g.M = S * Tk; g.N = d; g.K = d; g.lda = 2 * d; g.ldw = d; g.ldo = d; g.out_f32 = 1; g.aux_f32 = 1;
@@ -276,11 +277,12 @@ extern "C" int msmd_create(const msmd_config* cfg, int device, msmd_model** out)
   if (c.precision >= 1) {
     A(&m->fx, M * d); A(&m->fqkv, M * 3 * d); A(&m->fctx, M * d); A(&m->fh, M * c.d_ff); A(&m->fy, M * d);
     A(&m->fdec1, M * d / 2); A(&m->fmem, S * (T - 1) * d); A(&m->fx0c, S * d); A(&m->fq0, S * d); A(&m->fctx0, S * d);
-    A(&m->fy0, S * d); A(&m->ws_hi, M * c.d_ff); A(&m->ws_lo, M * c.d_ff);
+    A(&m->fy0, S * d); A(&m->ws_hi, M * c.d_ff); A(&m->ws_lo, M * c.d_ff); A(&m->overflow, 1);
     for (auto& w : m->L) { A(&w.kv32, S * (T - 1) * 2 * d); A(&w.ca32, S * (T - 1) * d); }
   }
   if (rc) { msmd_destroy(m); return rc; }
   cudaMemset(m->dec2, 0, M * m->ldd * sizeof(float));
+  if (m->overflow) cudaMemset(m->overflow, 0, sizeof(int));
   *out = m;
   return MSMD_OK;
 }
@@ -448,6 +450,19 @@ __global__ void steps_from_i64_kernel(const int64_t* in, int* out, int S) {
 }
 
 namespace {
+// fp32-grade path: the fp16 two-term operand split needs |activation| < 65504; fail loudly instead of returning NaNs
+int check_overflow(msmd_model* m, cudaStream_t st, const char* who) {
+  if (!m->overflow) return MSMD_OK;
+  int flag = 0;
+  MSMD_CHECK_CUDA(cudaMemcpyAsync(&flag, m->overflow, sizeof(int), cudaMemcpyDeviceToHost, st));
+  MSMD_CHECK_CUDA(cudaStreamSynchronize(st));
+  if (flag) {
+    cudaMemsetAsync(m->overflow, 0, sizeof(int), st);
+    set_error("%s: an activation left the fp16 range of the fp32-grade GEMM operand split (|x| > 65504 or NaN)", who);
+    return MSMD_ERR_INVALID;
+  }
+  return MSMD_OK;
+}
 int check_precise(const msmd_model* m, int precise, const char* who) {
   if (precise && m->c.precision == 0) {
     set_error("%s: the fp32-grade path needs a model created with precision 1 or 2", who);
@@ -477,6 +492,7 @@ extern "C" int msmd_denoise_ex(msmd_model* m, const float* motion, const int64_t
   int rc = check_precise(m, precise, "msmd_denoise");
   if (rc) return rc;
   if ((rc = precise ? run_forward_f32(m, motion, st) : run_forward(m, motion, st))) return rc;
+  if (precise && (rc = check_overflow(m, st, "msmd_denoise"))) return rc;   // (synchronises; the bf16 path does not)
   return mix_static_launch(m->dec2, m->stat, out, m->S, m->T, m->c.motion_dim, m->c.n_basis, m->ldd, st);
 }
 
@@ -582,6 +598,7 @@ extern "C" int msmd_sample_window_ex(msmd_model* m, const float* x_T, const floa
   }
   for (int i = 0; i < n_hi; ++i)
     if ((rc = one_step(st, true))) return rc;
+  if (n_hi > 0 && (rc = check_overflow(m, st, "msmd_sample_window"))) return rc;
   MSMD_CHECK_CUDA(cudaMemcpyAsync(x_out, m->xbuf, n_el * 4, cudaMemcpyDeviceToDevice, st));
   return MSMD_OK;
 }

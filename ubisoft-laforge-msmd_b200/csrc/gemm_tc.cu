@@ -251,19 +251,23 @@ __global__ void split_tf32_kernel(const float* __restrict__ x, float* __restrict
 }
 
 // fp16 two-term split: hi = fp16(x), lo = fp16((x - hi) * 2^11); x ~= hi + 2^-11 lo to 22 mantissa bits
-__global__ void split_f16_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo, int64_t n) {
+__global__ void split_f16_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo, int64_t n,
+                                 int* __restrict__ overflow) {
+  bool bad = false;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float v = x[i];
     const __half h = __float2half_rn(v);
     hi[i] = h;
     lo[i] = __float2half_rn((v - __half2float(h)) * 2048.0f);
+    bad |= !(fabsf(v) <= 65504.0f);   // outside the fp16 range (or NaN): the split cannot represent it
   }
+  if (bad && overflow) *overflow = 1;
 }
-int split_f16(const float* x, __half* hi, __half* lo, int64_t n, cudaStream_t st) {
+int split_f16(const float* x, __half* hi, __half* lo, int64_t n, cudaStream_t st, int* overflow) {
   if (n == 0) return MSMD_OK;
   ProfileScope prof("split_f16", st);
   const int blocks = (int)std::min<int64_t>(cdiv(n, 256), kNumSMs * 16);
-  split_f16_kernel<<<blocks, 256, 0, st>>>(x, hi, lo, n);
+  split_f16_kernel<<<blocks, 256, 0, st>>>(x, hi, lo, n, overflow);
   MSMD_CHECK_LAUNCH();
   return MSMD_OK;
 }
@@ -294,7 +298,7 @@ extern "C" int msmd_linear(int mode, const void* x, const void* x_lo, const void
 extern "C" int msmd_split_f16(const float* x, void* hi, void* lo, int64_t n, void* stream) {
   MSMD_REQUIRE(n >= 0, "msmd_split_f16: negative count");
   MSMD_REQUIRE(n == 0 || (x && hi && lo), "msmd_split_f16: null pointer");
-  return split_f16(x, static_cast<__half*>(hi), static_cast<__half*>(lo), n, static_cast<cudaStream_t>(stream));
+  return split_f16(x, static_cast<__half*>(hi), static_cast<__half*>(lo), n, static_cast<cudaStream_t>(stream), nullptr);
 }
 
 extern "C" int msmd_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream) {

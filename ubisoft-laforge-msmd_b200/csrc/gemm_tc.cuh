@@ -548,6 +548,7 @@ struct GemmDesc {
 };
 
 int gemm_tc_launch(const GemmDesc& d, cudaStream_t st);
-int split_f16(const float* x, __half* hi, __half* lo, int64_t n, cudaStream_t st);
+// `overflow` (optional, device): set to 1 when a value lies outside the fp16 range, which the split cannot represent
+int split_f16(const float* x, __half* hi, __half* lo, int64_t n, cudaStream_t st, int* overflow = nullptr);
 
 }  // namespace msmd
