@@ -43,6 +43,7 @@ struct AttnParams {
   CUtensorMap out_map;     // ctx rows, box {64 head dims, T rows}: a job's store covers exactly its sequence
   int S, T, H, jobs;
   int early;               // A/B (MSMD_ATTN_EARLY): release S_g right after it is read instead of after O_g is read
+  unsigned long long* trace;   // -DMSMD_ATTN_TRACE builds: clock64 stamps of CTA 0, [role 0..2][job 0..15][8]
 };
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
@@ -53,6 +54,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
         "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr)
       : "memory");
+}
+
+__device__ __forceinline__ void attn_stamp(unsigned long long* tr, int role, int job, int ev) {
+#ifdef MSMD_ATTN_TRACE
+  if (tr != nullptr && blockIdx.x == 0 && job < 16) tr[(role * 16 + job) * 8 + ev] = clock64();
+#endif
 }
 
 template <bool TAIL16>
@@ -127,11 +134,14 @@ __global__ void __launch_bounds__(kThreads, 1) self_attn_tc_kernel(const __grid_
           for (int k = 0; k < 4; ++k)
             umma<0>(tmem_base + g * kGroupCols, desc_advance(dq, k * 32), desc_advance(dk, k * 32), idesc_qk, k != 0);
           umma_commit(&sfull_bar[g]);
+          attn_stamp(p.trace, 0, i, 0);
         }
         if (i >= 1) {      // O_g = P_g V of job i-1
           const int j = i - 1, st = j % kStages, g = j & 1;
+          attn_stamp(p.trace, 0, j, 1);
           mbar_wait(&pfull_bar[g], (j >> 1) & 1);
           tc_fence_after();
+          attn_stamp(p.trace, 0, j, 2);
           const uint32_t sv = smem_u32(stage_base + st * kStageBytes + kQBytes + kKVBytes);
           const uint32_t sp = smem_u32(p_base + g * kPBytes);
 #pragma unroll
@@ -142,6 +152,7 @@ __global__ void __launch_bounds__(kThreads, 1) self_attn_tc_kernel(const __grid_
           }
           umma_commit(&ofull_bar[g]);
           umma_commit(&empty_bar[st]);   // Q, K (read by the earlier MMAs) and V of this stage are free
+          attn_stamp(p.trace, 0, j, 3);
         }
       }
     }
@@ -161,14 +172,18 @@ __global__ void __launch_bounds__(kThreads, 1) self_attn_tc_kernel(const __grid_
       const int job = job0 + i;
       const int s = job / p.H, h = job % p.H;
       const uint32_t ph = it & 1;
+      const bool tr0 = issuer;
+      if (tr0) attn_stamp(p.trace, 1 + g, i, 0);
       mbar_wait(&sfull_bar[g], ph);
       tc_fence_after();
+      if (tr0) attn_stamp(p.trace, 1 + g, i, 1);
       uint32_t v[kKeys];
       tmem_ld32(t_s, v);
       tmem_ld32(t_s + 32, v + 32);
       tmem_ld32(t_s + 64, v + 64);
       tmem_ld16(t_s + 96, v + 96);
       tmem_ld_wait();
+      if (tr0) attn_stamp(p.trace, 1 + g, i, 2);
       if (p.early) {   // S_g is in registers: the next Q K^T of this group may run under this job's softmax
         tc_fence_before();
         __syncwarp();
@@ -205,9 +220,11 @@ __global__ void __launch_bounds__(kThreads, 1) self_attn_tc_kernel(const __grid_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&pfull_bar[g]);
+      if (tr0) attn_stamp(p.trace, 1 + g, i, 3);
 
       mbar_wait(&ofull_bar[g], ph);   // P V done: O_g is complete and P_g is no longer read
       tc_fence_after();
+      if (tr0) attn_stamp(p.trace, 1 + g, i, 4);
       uint32_t o[64];
       tmem_ld32(t_o, o);
       tmem_ld32(t_o + 32, o + 32);
@@ -234,6 +251,7 @@ __global__ void __launch_bounds__(kThreads, 1) self_attn_tc_kernel(const __grid_
       if (issuer) {
         tma_store_2d(&p.out_map, p_base + g * kPBytes, h * 64, s * p.T);
         tma_store_commit();
+        attn_stamp(p.trace, 1 + g, i, 5);
       }
     }
     if (issuer) tma_store_wait<0>();
@@ -267,6 +285,12 @@ int self_attn_tc_launch(const bf16* qkv, bf16* ctx, int S, int T, int H, cudaStr
                          CU_TENSOR_MAP_SWIZZLE_128B)))
     return rc;
   p.S = S; p.T = T; p.H = H; p.jobs = S * H;
+#ifdef MSMD_ATTN_TRACE
+  static unsigned long long* tbuf = nullptr;
+  if (!tbuf) MSMD_CHECK_CUDA(cudaMalloc(&tbuf, 3 * 16 * 8 * 8));
+  MSMD_CHECK_CUDA(cudaMemsetAsync(tbuf, 0, 3 * 16 * 8 * 8, st));
+  p.trace = tbuf;
+#endif
   static const int early_env = [] { const char* e = getenv("MSMD_ATTN_EARLY"); return e ? atoi(e) : 0; }();
   p.early = early_env;
   static bool attr = false;
@@ -280,6 +304,29 @@ int self_attn_tc_launch(const bf16* qkv, bf16* ctx, int S, int T, int H, cudaStr
   if (T > kKeys - 16) MSMD_CHECK_CUDA(launch_pdl(self_attn_tc_kernel<true>, dim3(grid), dim3(kThreads), kSmemBytes, st, p));
   else MSMD_CHECK_CUDA(launch_pdl(self_attn_tc_kernel<false>, dim3(grid), dim3(kThreads), kSmemBytes, st, p));
   MSMD_CHECK_LAUNCH();
+#ifdef MSMD_ATTN_TRACE
+  {
+    static int dumps = 0;
+    unsigned long long h[3 * 16 * 8];
+    MSMD_CHECK_CUDA(cudaStreamSynchronize(st));
+    MSMD_CHECK_CUDA(cudaMemcpy(h, tbuf, sizeof(h), cudaMemcpyDeviceToHost));
+    if (dumps++ == 20) {
+      const unsigned long long t0 = h[0];
+      const char* names[3] = {"mma   [QK issued, wait P, got P, PV issued]", "grp0  [wait S, got S, S in regs, P arrived, got O, store issued]",
+                              "grp1  [same]"};
+      for (int r = 0; r < 3; ++r) {
+        fprintf(stderr, "[attn trace] %s\n", names[r]);
+        for (int j = 0; j < 12; ++j) {
+          const unsigned long long* e = &h[(r * 16 + j) * 8];
+          if (!e[0] && !e[1] && !e[2]) continue;
+          fprintf(stderr, "   job %2d:", j);
+          for (int k = 0; k < 6; ++k) fprintf(stderr, " %7lld", e[k] ? (long long)(e[k] - t0) : -1LL);
+          fprintf(stderr, "\n");
+        }
+      }
+    }
+  }
+#endif
   return MSMD_OK;
 }
 
