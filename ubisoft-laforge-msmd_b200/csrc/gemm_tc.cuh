@@ -99,9 +99,10 @@ __device__ __forceinline__ float erf_fast(float x) {
 // 9 instructions per element instead of ~25 - the bf16 GELU epilogue must stay below the 4096-cycle MMA time
 // of a 128x256x512 tile.
 __device__ __forceinline__ float gelu_tanh3(float x) {
-  const float xc = fminf(fmaxf(x, -8.0f), 8.0f);
-  const float x2 = xc * xc;
-  const float u = xc * fmaf(x2, fmaf(x2, -0.000351516788570472f, 0.037005646019657945f), 0.7975078842869763f);
+  // the fit holds for |x| <= 8; beyond it x^2 is clamped, so u = x * p(64) = 1.726 x >= 13.8 in magnitude and tanh
+  // has long saturated (one FMNMX instead of a two-sided clamp of x)
+  const float x2 = fminf(x * x, 64.0f);
+  const float u = x * fmaf(x2, fmaf(x2, -0.000351516788570472f, 0.037005646019657945f), 0.7975078842869763f);
   float th;
   asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(u));
   const float hx = 0.5f * x;
