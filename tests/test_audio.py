@@ -62,3 +62,19 @@ def test_audio_cuda_matches_golden(built_lib, am):
     assert rel_l2(got_s, g[am + '_short']) < 2e-2
     one = m.extract_audio_feature(x[:1].cuda(), c['frames'])      # clips are independent (GroupNorm is per clip)
     assert rel_l2(one, got[:1]) < 1e-5
+
+
+@pytest.mark.gpu
+def test_audio_cuda_long_clip_wav2vec2(built_lib):
+    """BASELINE configs[4]: wav2vec2 on a 60 s clip -> 3000 encoder frames (the flash-attention path of the audio
+    encoder, 12 heads x 3000 x 3000 scores never materialised) vs the CPU oracle on the same clip."""
+    m = make_msmd_with_audio('wav2vec2', 'cuda')
+    sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    n = 60 * 16000
+    x = torch.stack([synth.clip_audio(7, n)])
+    frames = 60 * 25
+    want = A.extract_audio_feature(sd, x, 25, frames)
+    got = m.extract_audio_feature(x.cuda(), frames)
+    err = rel_l2(got, want)
+    print('wav2vec2 60 s clip: audio feature rel-L2 (bf16 vs fp32 oracle):', err)
+    assert got.shape == (1, frames, 512) and err < 2e-2
