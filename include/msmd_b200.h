@@ -227,6 +227,16 @@ int msmd_audio_encode(msmd_audio* m, const float* wav, int N, int n_samples, int
                       float* hidden_out, int feat_frames, float* feat_out, void* stream);
 
 /* ------------------------------------------------------------------------- *
+ * Clip front-end of the inference driver (the numpy stages between file I/O and the encoders)
+ *   msmd_audio_normalize: inference.py:234   out = (x - mean(x)) / (std(x) + 1e-5) per clip (population std);
+ *                         in/out [n_clips, n_samples] fp32, may alias.
+ *   msmd_resample_linear: inference.py:158-171   scipy interp1d(kind='linear', axis=0) from
+ *                         np.linspace(0,1,rows_in) onto np.linspace(0,1,rows_out); in [rows_in, cols], out [rows_out, cols].
+ * ------------------------------------------------------------------------- */
+int msmd_audio_normalize(const float* in, float* out, int n_clips, int64_t n_samples, void* stream);
+int msmd_resample_linear(const float* in, float* out, int rows_in, int rows_out, int cols, void* stream);
+
+/* ------------------------------------------------------------------------- *
  * FLAME decode — utils/flame.py:180-244 (FLAME.forward) -> utils/lbs.py:141-223 (lbs)
  *
  * msmd_flame_create packs the static bases once:

@@ -41,6 +41,8 @@ SIGNATURES = {
     'msmd_audio_destroy': (None, [_vp]),
     'msmd_audio_load_weights': (_i, [_vp, C.POINTER(C.c_char_p), C.POINTER(_vp), C.POINTER(_i64), _i]),
     'msmd_audio_encode': (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _vp, _vp]),
+    'msmd_audio_normalize': (_i, [_vp, _vp, _i, _i64, _vp]),
+    'msmd_resample_linear': (_i, [_vp, _vp, _i, _i, _i, _vp]),
     'msmd_sample_window_ex': (_i, [_vp, _vp, _vp, C.c_uint64, _i, C.c_float, C.c_float, C.c_float, _i, _i, _vp, _vp, _vp, _vp]),
     'msmd_flame_create': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, C.POINTER(_vp)]),
     'msmd_flame_decode': (_i, [_vp, _vp, _vp, _i, _i64, _vp, _vp, _i, _vp]),

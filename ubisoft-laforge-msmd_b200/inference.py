@@ -87,3 +87,50 @@ def load_model(model_root: str, model_name: str, iter_num: str, device='cuda'):
     model.load_state_dict(ckpt['model'])
     model.eval()
     return model, style_enc, model_args
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Clip front-end: the numpy stages of inference.py between file I/O and the encoders,
+# on the GPU through the C ABI (csrc/frontend.cu).  File decoding itself (librosa.load / pickle) stays with the caller.
+def normalize_audio(audio):
+    """inference.py:234: ``(audio - audio.mean()) / (audio.std() + 1e-5)`` per clip (numpy's population std).
+    audio: CUDA fp32 [n] or [N, n]."""
+    from . import _lib
+    if audio.device.type != 'cuda':
+        raise _lib.MsmdError('msmd_b200.inference.normalize_audio needs a CUDA tensor (no CPU path)')
+    x = audio.detach().to(torch.float32).contiguous()
+    x2 = x.reshape(1, -1) if x.ndim == 1 else x
+    out = torch.empty_like(x2)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().msmd_audio_normalize(_lib.dev_ptr(x2), _lib.dev_ptr(out), x2.shape[0], x2.shape[1],
+                                                   _lib.stream_ptr()))
+    return out.reshape(x.shape)
+
+
+def resample_linear(x, rows_out):
+    """scipy ``interp1d(np.linspace(0, 1, rows_in), x, axis=0)(np.linspace(0, 1, rows_out))`` (inference.py:158-171).
+    x: CUDA fp32 [rows_in, cols]."""
+    from . import _lib
+    if x.device.type != 'cuda':
+        raise _lib.MsmdError('msmd_b200.inference.resample_linear needs a CUDA tensor (no CPU path)')
+    x = x.detach().to(torch.float32).contiguous()
+    if x.ndim != 2 or x.shape[0] < 1:
+        raise ValueError(f'resample_linear expects [rows >= 1, cols], got {tuple(x.shape)}')
+    out = torch.empty((int(rows_out), x.shape[1]), device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().msmd_resample_linear(_lib.dev_ptr(x), _lib.dev_ptr(out), x.shape[0], int(rows_out), x.shape[1],
+                                                   _lib.stream_ptr()))
+    return out
+
+
+def prepare_style_clip(expression_coef, head_rot, coef_stats, device='cuda', original_fps=30, target_fps=25):
+    """The arithmetic of ``query_for_motion_coeff`` (inference.py:108-184) on already-loaded arrays: normalise the
+    expression codes and head rotations with the dataset statistics (eps 1e-9), resample original_fps -> target_fps
+    by linear interpolation, concatenate.  Returns (motion_coeff [1, frames, n_exp + n_rot], shape_coef zeros [1, 100])."""
+    t = lambda a: torch.as_tensor(a, dtype=torch.float32, device=device)
+    exp = (t(expression_coef) - t(coef_stats['exp_mean'])) / (t(coef_stats['exp_std']) + 1e-9)
+    rot = (t(head_rot) - t(coef_stats['pose_mean'])) / (t(coef_stats['pose_std']) + 1e-9)
+    if original_fps is not None and original_fps != target_fps:
+        new_frames = int(round(exp.shape[0] / original_fps * target_fps))
+        exp, rot = resample_linear(exp, new_frames), resample_linear(rot, new_frames)
+    return torch.cat([exp, rot], dim=1).unsqueeze(0), torch.zeros((1, 100), device=device)
