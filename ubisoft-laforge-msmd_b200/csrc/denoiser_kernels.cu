@@ -133,17 +133,26 @@ __global__ void __launch_bounds__(256, 2) embed_x_kernel(EmbedParams p) {
     float a0[kEmbedPitch], a1[kEmbedPitch];
 #pragma unroll
     for (int r = 0; r < kEmbedPitch; ++r) a0[r] = a1[r] = 0.f;
-#pragma unroll 2
-    for (int k = 0; k < p.dm; ++k) {
-      const float2 w = __ldg(reinterpret_cast<const float2*>(p.WfT + (int64_t)k * p.d + c));
-      const float4* xr = reinterpret_cast<const float4*>(xs + k * kEmbedPitch);
+    // weights for 4 k at a time: the 4 loads are issued together, so their (L1/L2) latency is paid once per 224 FMAs
+    const float* wcol = p.WfT + c;
+    for (int k0 = 0; k0 < p.dm; k0 += 4) {
+      float2 w[4];
 #pragma unroll
-      for (int q = 0; q < kEmbedPitch / 4; ++q) {
-        const float4 xv = xr[q];
-        a0[4 * q + 0] = fmaf(xv.x, w.x, a0[4 * q + 0]); a1[4 * q + 0] = fmaf(xv.x, w.y, a1[4 * q + 0]);
-        a0[4 * q + 1] = fmaf(xv.y, w.x, a0[4 * q + 1]); a1[4 * q + 1] = fmaf(xv.y, w.y, a1[4 * q + 1]);
-        a0[4 * q + 2] = fmaf(xv.z, w.x, a0[4 * q + 2]); a1[4 * q + 2] = fmaf(xv.z, w.y, a1[4 * q + 2]);
-        a0[4 * q + 3] = fmaf(xv.w, w.x, a0[4 * q + 3]); a1[4 * q + 3] = fmaf(xv.w, w.y, a1[4 * q + 3]);
+      for (int u = 0; u < 4; ++u)
+        w[u] = k0 + u < p.dm ? __ldg(reinterpret_cast<const float2*>(wcol + (int64_t)(k0 + u) * p.d)) : make_float2(0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (k0 + u < p.dm) {
+          const float4* xr = reinterpret_cast<const float4*>(xs + (k0 + u) * kEmbedPitch);
+#pragma unroll
+          for (int q = 0; q < kEmbedPitch / 4; ++q) {
+            const float4 xv = xr[q];
+            a0[4 * q + 0] = fmaf(xv.x, w[u].x, a0[4 * q + 0]); a1[4 * q + 0] = fmaf(xv.x, w[u].y, a1[4 * q + 0]);
+            a0[4 * q + 1] = fmaf(xv.y, w[u].x, a0[4 * q + 1]); a1[4 * q + 1] = fmaf(xv.y, w[u].y, a1[4 * q + 1]);
+            a0[4 * q + 2] = fmaf(xv.z, w[u].x, a0[4 * q + 2]); a1[4 * q + 2] = fmaf(xv.z, w[u].y, a1[4 * q + 2]);
+            a0[4 * q + 3] = fmaf(xv.w, w[u].x, a0[4 * q + 3]); a1[4 * q + 3] = fmaf(xv.w, w[u].y, a1[4 * q + 3]);
+          }
+        }
       }
     }
     const float2 wi = *reinterpret_cast<const float2*>(p.WfT + (int64_t)p.dm * p.d + c);
