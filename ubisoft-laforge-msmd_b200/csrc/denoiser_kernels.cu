@@ -130,9 +130,17 @@ __global__ void __launch_bounds__(256, 2) embed_x_kernel(EmbedParams p) {
   }
   __syncthreads();
   for (int c = 2 * threadIdx.x; c < p.d; c += 2 * blockDim.x) {
+    // accumulators start from bias + positional encoding: those 25 independent loads overlap the staging above
+    // instead of sitting, one latency each, between the stores of the epilogue
     float a0[kEmbedPitch], a1[kEmbedPitch];
+    const float2 bc = *reinterpret_cast<const float2*>(p.bf + c);
 #pragma unroll
-    for (int r = 0; r < kEmbedPitch; ++r) a0[r] = a1[r] = 0.f;
+    for (int r = 0; r < kEmbedPitch; ++r) {
+      float2 pe = make_float2(0.f, 0.f);
+      if (r < nr) pe = __ldg(reinterpret_cast<const float2*>(p.PE + (int64_t)(1 + p.Lp + l0 + r) * p.d + c));
+      a0[r] = bc.x + pe.x;
+      a1[r] = bc.y + pe.y;
+    }
     // weights for 4 k at a time: the 4 loads are issued together, so their (L1/L2) latency is paid once per 224 FMAs
     const float* wcol = p.WfT + c;
     for (int k0 = 0; k0 < p.dm; k0 += 4) {
@@ -156,18 +164,15 @@ __global__ void __launch_bounds__(256, 2) embed_x_kernel(EmbedParams p) {
       }
     }
     const float2 wi = *reinterpret_cast<const float2*>(p.WfT + (int64_t)p.dm * p.d + c);
-    const float2 bc = *reinterpret_cast<const float2*>(p.bf + c);
 #pragma unroll
     for (int r = 0; r < kEmbedRows; ++r) {
       if (r < nr) {
         const int l = l0 + r;
-        const float2 pe = *reinterpret_cast<const float2*>(p.PE + (int64_t)(1 + p.Lp + l) * p.d + c);
-        const float b0 = a0[r] + bc.x + pe.x, b1 = a1[r] + bc.y + pe.y;
         for (int e = 0; e < p.E; ++e) {
           const float ind = inds[e * kEmbedPitch + r];
           const int s = e * p.NX + n;
           *reinterpret_cast<uint32_t*>(p.out + ((int64_t)s * T + 1 + p.Lp + l) * p.d + c) =
-              pack_bf16(b0 + ind * wi.x, b1 + ind * wi.y);
+              pack_bf16(fmaf(ind, wi.x, a0[r]), fmaf(ind, wi.y, a1[r]));
         }
       }
     }
