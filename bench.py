@@ -90,7 +90,7 @@ class FlameWorkload:
     def setup(self, device, rank):
         from types import SimpleNamespace
         from msmd_b200.utils.flame import FLAME
-        from oracle import synth
+        from tools import synth
         raw = synth.flame_raw(0, synth.FLAME_V, 400)
         self.model = FLAME(SimpleNamespace(n_shape=300, n_exp=100, flame_lmk_embedding_path=None), raw=raw).to(device)
         host = synth.flame_inputs(self.frames, 300, 100, seed=rank)
@@ -182,8 +182,8 @@ class SamplerWorkload:
         from msmd_b200.style_encoder import get_style_encoder
         from msmd_b200.utils import hubert
         from msmd_b200.utils.flame import FLAME
-        from oracle import synth
-        from oracle.ref_shims import pinned_args
+        from tools import synth
+        from tools.synth import pinned_args
         self.args = pinned_args()
         enc = hubert.HubertModel(transformers.HubertConfig())
         m = M.MSMD(self.args, 'cpu', True, use_head_alpha=False, audio_encoder=enc)

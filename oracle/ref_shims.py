@@ -22,17 +22,7 @@ def available():
     return os.path.isfile(os.path.join(REF, 'model.py'))
 
 
-def pinned_args(**over):
-    """SURVEY App. A pinned configuration (the hyper-parameters model.py reads)."""
-    a = dict(audio_model='hubert', style_enc_model_style='vae2', d_style=256, num_of_basis=4,
-             use_indicator=True, n_motions=100, n_prev_motions=10, fps=25,
-             architecture='decoder', feature_dim=512, n_heads=8, n_layers=8, mlp_ratio=4,
-             align_mask_width=1, no_use_learnable_pe=False, n_diff_steps=500,
-             diff_schedule='cosine', target='sample', cfg_mode='incremental',
-             guiding_conditions='audio,style', style_enc_ckpt=None, regularize_alpha='None',
-             dataset_type='ravdess+celebv-text-medium', rot_repr='euler', no_head_pose=False)
-    a.update(over)
-    return argparse.Namespace(**a)
+from tools.synth import pinned_args  # noqa: E402,F401  (SURVEY App. A configuration; shared with bench.py)
 
 
 _ready = False

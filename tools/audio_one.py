@@ -2,8 +2,8 @@ import sys, os, torch, transformers
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from msmd_b200 import model as M
 from msmd_b200.utils import hubert
-from oracle import synth
-from oracle.ref_shims import pinned_args
+from tools import synth
+from tools.synth import pinned_args
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 m = M.MSMD(pinned_args(), 'cpu', True, use_head_alpha=False, audio_encoder=hubert.HubertModel(transformers.HubertConfig()))
 m.load_state_dict(synth.fill_state_dict(synth.param_spec(m, skip=('denoising_net.',)), 1), strict=False)
