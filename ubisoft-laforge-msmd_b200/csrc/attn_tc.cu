@@ -42,7 +42,6 @@ struct AttnParams {
   CUtensorMap q_map, kv_map;
   CUtensorMap out_map;     // ctx rows, box {64 head dims, T rows}: a job's store covers exactly its sequence
   int S, T, H, jobs;
-  int early;               // A/B (MSMD_ATTN_EARLY): release S_g right after it is read instead of after O_g is read
   unsigned long long* trace;   // -DMSMD_ATTN_TRACE builds: clock64 stamps of CTA 0, [role 0..2][job 0..15][8]
 };
 
@@ -184,11 +183,6 @@ __global__ void __launch_bounds__(kThreads, 1) self_attn_tc_kernel(const __grid_
       tmem_ld16(t_s + 96, v + 96);
       tmem_ld_wait();
       if (tr0) attn_stamp(p.trace, 1 + g, i, 2);
-      if (p.early) {   // S_g is in registers: the next Q K^T of this group may run under this job's softmax
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&aempty_bar[g]);
-      }
       float m = -INFINITY;
 #pragma unroll
       for (int c = 0; c < kKeys; ++c) {
@@ -229,11 +223,9 @@ __global__ void __launch_bounds__(kThreads, 1) self_attn_tc_kernel(const __grid_
       tmem_ld32(t_o, o);
       tmem_ld32(t_o + 32, o + 32);
       tmem_ld_wait();
-      if (!p.early) {
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&aempty_bar[g]);
-      }
+      tc_fence_before();   // S_g and O_g are both in registers: hand the group's TMEM slice back (releasing S_g earlier,
+      __syncwarp();        // right after its read, was measured: no change)
+      if (lane == 0) mbar_arrive(&aempty_bar[g]);
       const float inv = 1.0f / l;
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
@@ -291,8 +283,6 @@ int self_attn_tc_launch(const bf16* qkv, bf16* ctx, int S, int T, int H, cudaStr
   MSMD_CHECK_CUDA(cudaMemsetAsync(tbuf, 0, 3 * 16 * 8 * 8, st));
   p.trace = tbuf;
 #endif
-  static const int early_env = [] { const char* e = getenv("MSMD_ATTN_EARLY"); return e ? atoi(e) : 0; }();
-  p.early = early_env;
   static bool attr = false;
   if (!attr) {
     MSMD_CHECK_CUDA(cudaFuncSetAttribute(self_attn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));

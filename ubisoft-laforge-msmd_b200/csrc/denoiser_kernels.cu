@@ -579,75 +579,6 @@ int cross_attn_row0_launch(const bf16* q0, const bf16* kv, bf16* ctx0, int S, in
   return MSMD_OK;
 }
 
-// ------------------------------------------------------------------------------------------- small-M linear
-// out[r, f] = bias[f] + sum_k x[r,k] W[f,k] for a handful of rows (the person-token projections, M = S):
-// a 128-row tcgen05 tile would idle 87% of the tensor pipe and pay a 6 us kernel prologue, so this runs on
-// mma.sync m16n8k16: CTA = 16 rows x 64 features, 4 warps x 16 features, W fragments straight from L2.
-__global__ void __launch_bounds__(128) rowgemm_kernel(const bf16* __restrict__ x, const bf16* __restrict__ W,
-                                                      const float* __restrict__ bias, bf16* __restrict__ out, int R,
-                                                      int F, int K, int gelu) {
-  extern __shared__ __align__(16) bf16 rg_x[];    // [16][K + 8]
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  const int r0 = blockIdx.y * 16, f0 = blockIdx.x * 64 + warp * 16;
-  const int pitch = K + 8;
-  for (int idx = tid; idx < 16 * (K / 8); idx += 128) {
-    const int row = idx / (K / 8), ch = idx % (K / 8);
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (r0 + row < R) v = *reinterpret_cast<const uint4*>(x + (int64_t)(r0 + row) * K + ch * 8);
-    *reinterpret_cast<uint4*>(rg_x + row * pitch + ch * 8) = v;
-  }
-  __syncthreads();
-  float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-  const bf16* w0 = W + (int64_t)(f0 + g) * K + 2 * t;
-  const bf16* w1 = w0 + (int64_t)8 * K;
-  for (int k0 = 0; k0 < K; k0 += 128) {          // 8 k-steps per batch: 32 independent loads in flight per lane
-    uint32_t b[8][4];
-#pragma unroll
-    for (int ks = 0; ks < 8; ++ks) {
-      const int k = k0 + ks * 16;
-      b[ks][0] = __ldg(reinterpret_cast<const uint32_t*>(w0 + k));
-      b[ks][1] = __ldg(reinterpret_cast<const uint32_t*>(w0 + k + 8));
-      b[ks][2] = __ldg(reinterpret_cast<const uint32_t*>(w1 + k));
-      b[ks][3] = __ldg(reinterpret_cast<const uint32_t*>(w1 + k + 8));
-    }
-#pragma unroll
-    for (int ks = 0; ks < 8; ++ks) {
-      const int k = k0 + ks * 16;
-      uint32_t a[4];
-      a[0] = *reinterpret_cast<const uint32_t*>(rg_x + g * pitch + k + 2 * t);
-      a[1] = *reinterpret_cast<const uint32_t*>(rg_x + (g + 8) * pitch + k + 2 * t);
-      a[2] = *reinterpret_cast<const uint32_t*>(rg_x + g * pitch + k + 8 + 2 * t);
-      a[3] = *reinterpret_cast<const uint32_t*>(rg_x + (g + 8) * pitch + k + 8 + 2 * t);
-      mma_bf16_16816(acc[0], a, b[ks][0], b[ks][1]);
-      mma_bf16_16816(acc[1], a, b[ks][2], b[ks][3]);
-    }
-  }
-#pragma unroll
-  for (int nt = 0; nt < 2; ++nt) {
-    const int f = f0 + nt * 8 + 2 * t;
-    const float b0 = bias ? bias[f] : 0.f, b1 = bias ? bias[f + 1] : 0.f;
-    float v0 = acc[nt][0] + b0, v1 = acc[nt][1] + b1, v2 = acc[nt][2] + b0, v3 = acc[nt][3] + b1;
-    if (gelu) { v0 = gelu_exact(v0); v1 = gelu_exact(v1); v2 = gelu_exact(v2); v3 = gelu_exact(v3); }
-    if (r0 + g < R) *reinterpret_cast<uint32_t*>(out + (int64_t)(r0 + g) * F + f) = pack_bf16(v0, v1);
-    if (r0 + g + 8 < R) *reinterpret_cast<uint32_t*>(out + (int64_t)(r0 + g + 8) * F + f) = pack_bf16(v2, v3);
-  }
-}
-int rowgemm_launch(const bf16* x, const bf16* W, const float* bias, bf16* out, int R, int F, int K, int gelu,
-                   cudaStream_t st) {
-  MSMD_REQUIRE(F % 64 == 0 && K % 128 == 0, "rowgemm: F %% 64 and K %% 128 required (got %d, %d)", F, K);
-  ProfileScope prof("rowgemm", st);
-  const int smem = 16 * (K + 8) * (int)sizeof(bf16);
-  static bool attr = false;
-  if (!attr) {
-    MSMD_CHECK_CUDA(cudaFuncSetAttribute(rowgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * (4096 + 8) * 2));
-    attr = true;
-  }
-  MSMD_REQUIRE(K <= 4096, "rowgemm: K %d > 4096", K);
-  rowgemm_kernel<<<dim3(F / 64, cdiv(R, 16)), 128, smem, st>>>(x, W, bias, out, R, F, K, gelu);
-  MSMD_CHECK_LAUNCH();
-  return MSMD_OK;
-}
-
 // ------------------------------------------------------------------------------------------- sampler update
 // Philox4x32-10 + Box-Muller for the in-kernel noise path (z == null); keyed by (seed, t, element)
 __device__ __forceinline__ float philox_normal(unsigned long long seed, uint32_t t, uint32_t idx) {

@@ -58,9 +58,6 @@ int self_attn_launch(const bf16* qkv, bf16* ctx, int S, int T, int H, cudaStream
 // row-0 cross attention: q0 [S,d]; kv [S*Tk, 2d] (k|v) -> ctx0 [S,d]
 int cross_attn_row0_launch(const bf16* q0, const bf16* kv, bf16* ctx0, int S, int Tk, int H, cudaStream_t st);
 
-// out[R,F] = x[R,K] W[F,K]^T + bias for small R (mma.sync; the person-token projections)
-int rowgemm_launch(const bf16* x, const bf16* W, const float* bias, bf16* out, int R, int F, int K, int gelu,
-                   cudaStream_t st);
 
 struct UpdateParams {
   const float* dec;       // [S, T, ldd] fp32: motion_dec output (dm dynamic + nb alphas)
