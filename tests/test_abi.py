@@ -67,3 +67,19 @@ def test_convention_errors_match_reference(built_lib):
         rc.matrix_to_quaternion(torch.zeros(2, 3, 4))
     with pytest.raises(ValueError, match='Points are not in 3D'):
         rc.quaternion_apply(torch.zeros(2, 4), torch.zeros(2, 4))
+
+
+def test_plain_c_consumer_compiles_links_and_runs(built_lib, tmp_path):
+    """include/msmd_b200.h is a C header (extern "C", plain pointers and sizes): a C99 translation unit binds the
+    library directly, which is what a cgo / JNI / N-API stub of the reference would do."""
+    import shutil
+    import subprocess
+    gcc = shutil.which('gcc')
+    assert gcc, 'gcc is part of the image'
+    exe = str(tmp_path / 'c_abi_consumer')
+    libdir = os.path.dirname(built_lib)
+    subprocess.run([gcc, '-std=c99', '-Wall', '-Werror', '-I', os.path.join(ROOT, 'include'),
+                    os.path.join(ROOT, 'tests', 'c_abi_consumer.c'), '-o', exe, '-L', libdir, '-lmsmd_b200',
+                    '-Wl,-rpath,' + libdir, '-Wl,-rpath,/usr/local/cuda/lib64'], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.startswith('ok '), (r.returncode, r.stdout, r.stderr)
