@@ -133,6 +133,21 @@ def gen_sampler():
     print('sampler.npz', res['incremental'].shape)
 
 
+def gen_sampler_noise():
+    """args.target == 'noise' (model.py:421-424: the network predicts eps, x_{t-1} = (x_t - c1 eps) / sqrt(alpha) + sigma z),
+    with dynamic thresholding off; same inputs as gen_sampler."""
+    c = SAMP_GOLD
+    model, args = ref_msmd(c['weight_seed'], n_diff_steps=c['T'], target='noise')
+    assert model.target == 'noise'
+    i = synth.sampler_inputs(c['N'], c['T'], c['seed'])
+    with ref_shims.inject_randn_like([i['z'][t] for t in range(c['T'], 1, -1)]):
+        traj, _, _ = model.sample(i['audio_feat'], i['shape'], i['style'], motion_at_T=i['x_T'], indicator=i['indicator'],
+                                  cfg_mode='incremental', cfg_scale=list(c['scales']), ret_traj=True)
+    out = torch.stack([traj[t] for t in range(c['T'] + 1)]).numpy()
+    np.savez_compressed(os.path.join(OUT, 'sampler_noise.npz'), incremental=out)
+    print('sampler_noise.npz', out.shape, float(np.abs(out[0]).max()))
+
+
 STYLE_GOLD = dict(N=5, L=100, seed=31, weight_seed=77)
 
 
@@ -254,7 +269,7 @@ def gen_separate():
 
 
 SECTIONS = dict(rot=gen_rot, flame=gen_flame, denoiser=gen_denoiser, sampler=gen_sampler, style=gen_style,
-                audio=gen_audio, infer=gen_infer, separate=gen_separate)
+                audio=gen_audio, infer=gen_infer, separate=gen_separate, sampler_noise=gen_sampler_noise)
 
 
 def main(argv):

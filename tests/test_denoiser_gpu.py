@@ -233,3 +233,32 @@ def test_fp32_grade_path_reports_operands_outside_fp16_range(built_lib):
     again = m.denoising_net(i['motion'], i['audio'], i['person'], i['style'], i['prev_motion'], i['prev_audio'], i['step'],
                             i['indicator'])
     assert torch.equal(ok, again)        # the flag is cleared: the engine keeps working
+
+
+def test_sampler_noise_target_teacher_forced(built_lib):
+    """args.target == 'noise' (the update kernel's other branch, model.py:421-424) against the reference trajectory:
+    fp32-grade arithmetic to 1e-5 on every step; bf16 within the c0*c1-scaled network error."""
+    c = SAMP_GOLD
+    gold = np.load(os.path.join(GOLDEN, 'sampler_noise.npz'))['incremental']
+    i = synth.sampler_inputs(c['N'], c['T'], c['seed'])
+    sched = D.cosine_schedule(c['T'])
+    for precision, tol in (('fp32', F32_TOL), ('bf16', None)):
+        m, args = make_msmd('cuda', n_diff_steps=c['T'], target='noise')
+        assert m.target == 'noise'
+        _set_precision(m, precision)
+        worst = 0.0
+        for t in range(c['T'], 0, -1):
+            x_prev, _, _ = m.sample(i['audio_feat'].cuda(), i['shape'].cuda(), i['style'].cuda(),
+                                    motion_at_T=torch.from_numpy(gold[t]).cuda(), indicator=i['indicator'].cuda(),
+                                    cfg_mode='incremental', cfg_scale=list(c['scales']), noise=i['z'].cuda(), t_start=t,
+                                    n_steps=1)
+            err = rel_l2(x_prev, gold[t - 1])
+            if tol is None:      # eps_hat carries X0_TOL; it enters x_{t-1} through c0 * c1 relative to |x_{t-1}| ~ c0 |x_t|
+                a, ab = float(sched['alphas'][t]), float(sched['alpha_bars'][t])
+                bound = 1e-3 + X0_TOL * (1 - a) / (1 - ab) ** 0.5 * float(np.linalg.norm(gold[t - 1]) ** -1) * \
+                    float(np.linalg.norm(gold[t])) * 4
+                assert err < max(bound, 2e-2), (t, err, bound)
+            else:
+                assert err < tol, (precision, t, err)
+            worst = max(worst, err)
+        print(f'noise target, {precision}: worst teacher-forced step rel-L2 = {worst:.2e}')

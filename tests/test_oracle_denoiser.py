@@ -92,3 +92,18 @@ def test_no_cpu_path_for_model(msmd):
         m.sample(i['audio_feat'], i['shape'], i['style'], motion_at_T=i['x_T'], indicator=i['indicator'])
     with pytest.raises(_lib.MsmdError):
         m(i['x_T'], i['audio_feat'], i['shape'])
+
+
+def test_oracle_sampler_noise_target_matches_golden():
+    """args.target == 'noise' (model.py:421-424): the posterior step with the network read as eps."""
+    c = SAMP_GOLD
+    m, args = make_msmd('cpu', n_diff_steps=c['T'], target='noise')
+    sd = cpu_state_dict(m)
+    i = synth.sampler_inputs(c['N'], c['T'], c['seed'])
+    gold = np.load(os.path.join(GOLDEN, 'sampler_noise.npz'))['incremental']
+    x = torch.from_numpy(gold[c['T']])
+    for t in range(c['T'], 0, -1):       # teacher-forced: the random-weight eps recursion amplifies any difference
+        nxt, _, _ = D.sample(sd, args, i['audio_feat'], i['shape'], i['style'], x_T=torch.from_numpy(gold[t]), z=i['z'],
+                             indicator=i['indicator'], cfg_mode='incremental', cfg_scale=list(c['scales']), t_start=t,
+                             n_steps=1)
+        assert rel_l2(nxt, gold[t - 1]) < 5e-6, t
