@@ -262,3 +262,25 @@ def test_sampler_noise_target_teacher_forced(built_lib):
                 assert err < tol, (precision, t, err)
             worst = max(worst, err)
         print(f'noise target, {precision}: worst teacher-forced step rel-L2 = {worst:.2e}')
+
+
+@pytest.mark.parametrize('use_indicator', [True, False])
+def test_sampler_guidance_variants_vs_oracle(built_lib, use_indicator):
+    """No guidance (E = 1), audio-only / style-only guidance (E = 2), 'independent' with both, flexibility > 0, and a
+    model built without the indicator input: 4 free-running fp32-grade steps against the oracle (which
+    test_oracle_sampler_variants_match_reference pins to the reference), and the bf16 path within its usual bound."""
+    from test_oracle_denoiser import VARIANTS
+    T = 4
+    i = synth.sampler_inputs(2, T, 5)
+    ind = i['indicator'] if use_indicator else None
+    for precision, tol in (('fp32', 2e-5), ('bf16', 5e-2)):
+        m, args = make_msmd('cuda', n_diff_steps=T, use_indicator=use_indicator)
+        _set_precision(m, precision)
+        sd = cpu_state_dict(m)
+        for v in VARIANTS:
+            kw = dict(cfg_mode=v.get('cfg_mode', 'incremental'), cfg_cond=v['cfg_cond'],
+                      cfg_scale=[1.3, 1.6][:len(v['cfg_cond'])], flexibility=v['flexibility'])
+            want, _, _ = D.sample(sd, args, i['audio_feat'], i['shape'], i['style'], x_T=i['x_T'], z=i['z'], indicator=ind, **kw)
+            got, _, _ = m.sample(i['audio_feat'].cuda(), i['shape'].cuda(), i['style'].cuda(), motion_at_T=i['x_T'].cuda(),
+                                 indicator=None if ind is None else ind.cuda(), noise=i['z'].cuda(), **kw)
+            assert rel_l2(got, want) < tol, (precision, v, rel_l2(got, want))

@@ -107,3 +107,27 @@ def test_oracle_sampler_noise_target_matches_golden():
                              indicator=i['indicator'], cfg_mode='incremental', cfg_scale=list(c['scales']), t_start=t,
                              n_steps=1)
         assert rel_l2(nxt, gold[t - 1]) < 5e-6, t
+
+
+VARIANTS = [dict(cfg_cond=[], flexibility=0.3), dict(cfg_cond=['audio'], flexibility=0.0),
+            dict(cfg_cond=['style'], flexibility=0.5), dict(cfg_cond=['audio', 'style'], flexibility=1.0, cfg_mode='independent')]
+
+
+@pytest.mark.skipif(not ref_shims.available(), reason='needs /root/reference (build container)')
+@pytest.mark.parametrize('use_indicator', [True, False])
+def test_oracle_sampler_variants_match_reference(use_indicator):
+    """Guidance sets other than the default (none / audio only / style only), sigma 'flexibility' > 0 and a model built
+    without the indicator input: the oracle against the unmodified reference, 4 sampling steps each."""
+    from oracle.make_golden import ref_msmd
+    T = 4
+    ref, args = ref_msmd(1234, n_diff_steps=T, use_indicator=use_indicator)
+    sd = {k: v.detach() for k, v in ref.state_dict().items()}
+    i = synth.sampler_inputs(2, T, 5)
+    ind = i['indicator'] if use_indicator else None
+    for v in VARIANTS:
+        kw = dict(cfg_mode=v.get('cfg_mode', 'incremental'), cfg_cond=v['cfg_cond'], cfg_scale=[1.3, 1.6][:len(v['cfg_cond'])],
+                  flexibility=v['flexibility'])
+        with ref_shims.inject_randn_like([i['z'][t] for t in range(T, 1, -1)]):
+            want, _, _ = ref.sample(i['audio_feat'], i['shape'], i['style'], motion_at_T=i['x_T'], indicator=ind, **kw)
+        got, _, _ = D.sample(sd, args, i['audio_feat'], i['shape'], i['style'], x_T=i['x_T'], z=i['z'], indicator=ind, **kw)
+        assert rel_l2(got, want) < 5e-6, v
