@@ -93,6 +93,7 @@ int msmd_quat_binary(int op, const float* a, const float* b, float* out, int64_t
  *           kind::tf32 passes (hi*hi + hi*lo + lo*hi).  out/aux fp32.
  *   mode 2: fp32-grade, faster: x/x_lo and w/w_lo are fp16 two-term splits (msmd_split_f16: x = hi + 2^-11 lo,
  *           22 mantissa bits; |x| < 65504); three kind::f16 passes, cross terms rescaled in the epilogue.
+ *   mode 3: x, w and (16-bit) out IEEE fp16; one kind::f16 pass - the cost of mode 0 with 11 mantissa bits.
  *   ld* are row strides in elements (rows must be 16-byte multiples apart); act 0 none, 1 GELU(erf);
  *   out_f32 / aux_f32 select fp32 (1) or bf16 (0) for out / aux.
  * ------------------------------------------------------------------------- */
@@ -127,9 +128,10 @@ typedef struct {
   int target_noise;     /* 0: network predicts the sample (args.target == 'sample'), 1: the noise */
   int max_seqs;         /* capacity in sequences (E * clips); workspaces are sized for it at create */
   int precision;        /* 0: bf16 tensor-core GEMMs (fp32 accumulate, fp32 LayerNorm/softmax statistics);
-                         * 1: fp32-grade only — fp32 activations, 3-pass tf32 tcgen05 GEMMs (error ~1e-6), exact erf GELU;
-                         * 2: both sets of weights/workspaces resident, selectable per call (msmd_denoise_ex) or per
-                         *    step (msmd_sample_extras.precise_last_steps) */
+                         * 1: fp32-grade only — fp32 activations, 3-pass fp16-split tcgen05 GEMMs (error ~1e-6), exact erf GELU;
+                         * 2: hybrid — bf16, one-pass fp16 and fp32-grade weights/workspaces all resident, selectable per
+                         *    call (msmd_denoise_ex) or per step (msmd_sample_extras.fp16_last_steps / precise_last_steps);
+                         * 3: one-pass fp16 only (bf16's cost, x0_hat error 8e-4 instead of 6.5e-3; |activation| < 65504) */
 } msmd_config;
 
 typedef struct msmd_model msmd_model;
@@ -148,8 +150,8 @@ int msmd_load_weights(msmd_model* m, const char* const* names, const void* const
  * mask), person_proj, previous-motion projection, static-basis MLPs.
  * Arguments are exactly the conditioning tensors of DenoisingNetwork_MSMD.forward (model.py:914):
  *   audio [S,L,d], person [S,d_shape+d_style], style [S,d_style], prev_motion [S,Lp,dm],
- *   prev_audio [S,Lp,d], indicator [S,L] or NULL.  S = E*NX.  `indicator` must stay valid until the
- * window's last msmd_denoise / msmd_sample_window call. */
+ *   prev_audio [S,Lp,d], indicator [S,L] or NULL.  S = E*NX.  Everything later calls need is copied or projected
+ * into the handle in stream order: the caller may release its tensors when the call returns. */
 int msmd_window_begin(msmd_model* m, const float* audio, const float* person, const float* style,
                       const float* prev_motion, const float* prev_audio, const float* indicator,
                       int S, int NX, int E, void* stream);
@@ -157,12 +159,19 @@ int msmd_window_begin(msmd_model* m, const float* audio, const float* person, co
 /* One forward of the denoising network (model.py:914-996) for module-level parity.
  * Needs msmd_window_begin(..., S, NX=S, E=1).  motion [S,L,dm]; steps [S] int64; out [S,Lp+L,dm]. */
 int msmd_denoise(msmd_model* m, const float* motion, const int64_t* steps, float* out, void* stream);
-/* Same, choosing the arithmetic: precise != 0 runs the fp32-grade path (needs precision >= 1), 0 the bf16 path
- * (needs precision 0 or 2).  msmd_denoise == msmd_denoise_ex(..., precise = (precision == 1)). */
+/* Same, choosing the arithmetic: precise = 0 bf16 (precision 0/2), 1 fp32-grade (precision 1/2), 2 one-pass fp16
+ * (precision 2/3).  msmd_denoise picks the model's main arithmetic.  Step indices are clamped to [0, n_diff_steps].
+ * precise = 1 synchronises `stream` to report an fp16-range overflow of the operand split at the call site. */
 int msmd_denoise_ex(msmd_model* m, const float* motion, const int64_t* steps, float* out, int precise, void* stream);
+/* keep_separate=True of DenoisingNetwork_MSMD.forward (model.py:914,972-973): the un-mixed parts
+ *   dyn [S,Lp+L,dm], stat [S,Lp+L,n_basis,dm] (static-basis MLP outputs tiled over the rows), alphas [S,Lp+L,n_basis]. */
+int msmd_denoise_parts(msmd_model* m, const float* motion, const int64_t* steps, float* dyn, float* stat, float* alphas,
+                       int precise, void* stream);
 
 /* Ancestral sampling loop of MSMD.sample (model.py:377-435) for the current window, steps
- * t = t_start .. t_start-n_steps+1, captured once as a CUDA graph and replayed per step.
+ * t = t_start .. t_start-n_steps+1.  One step is captured as a CUDA graph the first time a (format, S, NX, E) shape
+ * is seen and the instantiated graph is kept in the handle: later calls only enqueue launches (no capture, no
+ * instantiation, no stream creation, no synchronisation) and return before the stream has drained.
  *   x_T [NX,L,dm] start state (state at t_start);  z [T+1,NX,L,dm] noise indexed by t or NULL
  *   (-> in-kernel Philox keyed by `seed`); cfg_independent selects 'independent' vs 'incremental';
  *   scale0/scale1 = guidance scales of entries 1 and 2; x_out [NX,L,dm];
@@ -186,13 +195,20 @@ typedef struct {
   float* cumulative_static;
   float* alpha_traj;
   int precise_last_steps; /* hybrid schedule (precision 2): steps with t <= precise_last_steps run the fp32-grade
-                           * path, earlier (noisier) steps the bf16 path; < 0 = every step.  Ignored (all steps
-                           * precise) when precision == 1; must be 0 when precision == 0. */
+                           * path, earlier (noisier) steps a 16-bit path; < 0 = every step.  Ignored (all steps
+                           * precise) when precision == 1; must be 0 when precision == 0 or 3.  An fp16-range overflow
+                           * of the operand split poisons x_out with NaN and is reported by the NEXT call on the
+                           * handle (or msmd_check) - this call does not synchronise. */
+  int fp16_last_steps;    /* hybrid schedule (precision 2): steps with precise_last_steps < t <= fp16_last_steps run the
+                           * one-pass fp16 path, earlier steps bf16; < 0 = every step.  Must be 0 when precision == 0. */
 } msmd_sample_extras;
 
 int msmd_sample_window_ex(msmd_model* m, const float* x_T, const float* z, uint64_t seed, int cfg_independent,
                           float scale0, float scale1, float flexibility, int t_start, int n_steps,
                           float* x_out, float* traj, const msmd_sample_extras* extras, void* stream);
+
+/* Synchronise `stream` and report a pending fp32-grade operand-split overflow of an earlier call on this handle. */
+int msmd_check(msmd_model* m, void* stream);
 
 /* ------------------------------------------------------------------------- *
  * Style encoder — style_encoder.py:119-213 (StyleEncoder_VAE2.forward / .sample)

@@ -268,7 +268,70 @@ def gen_separate():
     print('separate.npz', {k: v.shape for k, v in res.items()})
 
 
-SECTIONS = dict(rot=gen_rot, flame=gen_flame, denoiser=gen_denoiser, sampler=gen_sampler, style=gen_style,
+DECODE_GOLD = dict(N=2, F=4, seed=41)
+
+
+def decode_inputs():
+    """Shared by the generator and the tests: 54-d DiffPoseTalk-layout coefficients + statistics, and 67-d MSMD codes
+    (normalised) + their de-normalisation statistics (head rotation in Euler 'YXZ' degrees)."""
+    c = DECODE_GOLD
+    g = torch.Generator().manual_seed(c['seed'])
+    r = lambda *s: torch.randn(*s, generator=g)
+    motion54 = torch.cat([r(c['N'], c['F'], 50), 0.2 * r(c['N'], c['F'], 4)], -1)
+    shape = r(c['N'], 100)
+    stats54 = dict(exp_mean=0.1 * r(50), exp_std=0.5 + torch.rand(50, generator=g), pose_mean=0.05 * r(6),
+                   pose_std=0.5 + torch.rand(6, generator=g), shape_mean=0.1 * r(100), shape_std=0.5 + torch.rand(100, generator=g))
+    codes67 = r(c['N'], c['F'], 67)
+    stats67 = dict(exp_mean=0.1 * r(64), exp_std=0.5 + torch.rand(64, generator=g), rot_mean=5.0 * r(3),
+                   rot_std=10.0 + 10.0 * torch.rand(3, generator=g))
+    return motion54, shape, stats54, codes67, stats67
+
+
+def gen_decode():
+    """(a) utils/common.py:140-196 get_coef_dict + coef_dict_to_vertices on the reference FLAME(100, 50);
+    (b) the 67-d decode chain out of reference functions: inference.py:274-275 de-normalisation, Euler 'YXZ' degrees
+    (Step2*.py:556-566) -> rotation_conversions.euler_angles_to_matrix -> matrix_to_axis_angle -> FLAME(300, 100)."""
+    import math
+    m = ref_shims.ref_modules()
+    import utils.common as ref_common
+    motion54, shape, stats54, codes67, stats67 = decode_inputs()
+    raw = synth.flame_raw(0, synth.FLAME_V, 400)
+    res = {}
+    fl = ref_shims.ref_flame(raw, 100, 50)
+    for name, kw in (('global', dict(with_global_pose=True)), ('noglobal', dict(with_global_pose=False))):
+        cd = ref_common.get_coef_dict(motion54.clone(), shape, stats54, **kw)
+        for k, v in cd.items():
+            res[f'cd_{name}_{k}'] = v.numpy().copy()
+        res[f'verts54_{name}'] = ref_common.coef_dict_to_vertices(cd, fl, flame_batch_size=5).numpy()
+    cd = ref_common.get_coef_dict(motion54.clone(), shape, stats54, with_global_pose=True)   # (no stats: .view fails on the expanded shape, common.py:178)
+    res['verts54_ignore_global'] = ref_common.coef_dict_to_vertices(cd, fl, ignore_global_rot=True).numpy()
+    fl2 = ref_shims.ref_flame(raw, 300, 100)
+    N, Fr, _ = codes67.shape
+    exp = codes67[..., :-3] * stats67['exp_std'] + stats67['exp_mean']
+    rot = codes67[..., -3:] * stats67['rot_std'] + stats67['rot_mean']
+    aa = m.rc.matrix_to_axis_angle(m.rc.euler_angles_to_matrix(rot.reshape(-1, 3) * (math.pi / 180.0), 'YXZ'))
+    expression = torch.zeros(N * Fr, 100)
+    expression[:, :64] = exp.reshape(N * Fr, 64)
+    v, _, _ = fl2(torch.zeros(N * Fr, 300), expression, torch.cat([aa, torch.zeros_like(aa)], 1), None,
+                  return_lm2d=False, return_lm3d=False)
+    res['verts67'] = v.view(N, Fr, -1, 3).numpy()
+    res['aa67'] = aa.numpy()
+    np.savez_compressed(os.path.join(OUT, 'decode.npz'), **res)
+    print('decode.npz', {k: v.shape for k, v in res.items()})
+
+
+def gen_denoiser_parts():
+    """DenoisingNetwork_MSMD.forward(keep_separate=True) (model.py:972-973), same inputs as gen_denoiser."""
+    c = DEN_GOLD
+    model, args = ref_msmd(c['weight_seed'])
+    i = synth.denoiser_inputs(c['N'], c['seed'])
+    dyn, sta, alp = model.denoising_net(i['motion'], i['audio'], i['person'], i['style'], i['prev_motion'], i['prev_audio'],
+                                        i['step'], i['indicator'], keep_separate=True)
+    np.savez_compressed(os.path.join(OUT, 'denoiser_parts.npz'), dyn=dyn.numpy(), static=sta.numpy(), alphas=alp.numpy())
+    print('denoiser_parts.npz', dyn.shape, sta.shape, alp.shape)
+
+
+SECTIONS = dict(decode=gen_decode, denoiser_parts=gen_denoiser_parts, rot=gen_rot, flame=gen_flame, denoiser=gen_denoiser, sampler=gen_sampler, style=gen_style,
                 audio=gen_audio, infer=gen_infer, separate=gen_separate, sampler_noise=gen_sampler_noise)
 
 

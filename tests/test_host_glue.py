@@ -24,10 +24,29 @@ def test_args_round_trip(tmp_path):
     assert c.new_flag == 7 and c.n_motions == 100
 
 
-def test_load_model_from_reference_layout_checkpoint(tmp_path):
+def test_pretrained_audio_encoder_is_not_silently_random(monkeypatch):
+    """model.py:94-101 downloads the released HuBERT / wav2vec2 weights.  Without network or cache the drop-in raises
+    instead of silently returning a random encoder; the random-init fallback is an explicit opt-in and warns."""
+    import pytest
+    from msmd_b200.utils import hubert, wav2vec2
+    monkeypatch.setenv('HF_HUB_OFFLINE', '1')
+    monkeypatch.delenv('MSMD_ALLOW_RANDOM_AUDIO_ENCODER', raising=False)
+    with pytest.raises(OSError):
+        hubert.HubertModel.from_pretrained('facebook/hubert-base-ls960', cache_dir='/nonexistent-cache')
+    with pytest.warns(RuntimeWarning, match='RANDOMLY'):
+        m = wav2vec2.Wav2Vec2Model.from_pretrained('facebook/wav2vec2-base-960h', allow_random_init=True)
+    assert isinstance(m, wav2vec2.Wav2Vec2Model)
+    monkeypatch.setenv('MSMD_ALLOW_RANDOM_AUDIO_ENCODER', '1')
+    with pytest.warns(RuntimeWarning):
+        assert isinstance(hubert.HubertModel.from_pretrained('facebook/hubert-base-ls960'), hubert.HubertModel)
+
+
+def test_load_model_from_reference_layout_checkpoint(tmp_path, monkeypatch):
     """A checkpoint in the reference's layout ({'model', 'style_enc', 'iter'}, training_script.py:227-233) loads
     through load_model unchanged."""
     import transformers
+    monkeypatch.setenv('HF_HUB_OFFLINE', '1')
+    monkeypatch.setenv('MSMD_ALLOW_RANDOM_AUDIO_ENCODER', '1')     # no HF cache here; the checkpoint overwrites every weight
     from msmd_b200.inference import load_model
     from msmd_b200.style_encoder import get_style_encoder
     from msmd_b200.utils import hubert

@@ -16,10 +16,11 @@ class MsmdConfig(C.Structure):
 class SampleExtras(C.Structure):
     _fields_ = [('use_dynamic_threshold', C.c_int), ('dt_ratio', C.c_float), ('dt_min', C.c_float), ('dt_max', C.c_float),
                 ('target_dynamic', C.c_void_p), ('cumulative_static', C.c_void_p), ('alpha_traj', C.c_void_p),
-                ('precise_last_steps', C.c_int)]
+                ('precise_last_steps', C.c_int), ('fp16_last_steps', C.c_int)]
 
 
-PRECISIONS = {'bf16': 0, 'fp32': 1, 'hybrid': 2}
+PRECISIONS = {'bf16': 0, 'fp32': 1, 'hybrid': 2, 'fp16': 3}
+PATHS = {'bf16': 0, 'fp32': 1, 'fp16': 2}          # msmd_denoise_ex's `precise` argument
 
 
 class DenoiserEngine:
@@ -55,7 +56,6 @@ class DenoiserEngine:
         audio, person, style, prev_motion, prev_audio, indicator = map(f, (audio, person, style, prev_motion,
                                                                           prev_audio, indicator))
         S = audio.shape[0]
-        self._keep = (audio, person, style, prev_motion, prev_audio, indicator)  # indicator must outlive the window
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().msmd_window_begin(self._h, _lib.dev_ptr(audio), _lib.dev_ptr(person),
                                                     _lib.dev_ptr(style), _lib.dev_ptr(prev_motion),
@@ -63,23 +63,56 @@ class DenoiserEngine:
                                                     _lib.stream_ptr()))
         self.S, self.NX, self.E = S, NX, E
 
-    def denoise(self, motion, steps, precise=None):
-        """precise: None = the engine's native arithmetic (fp32-grade iff precision == 'fp32'); True/False picks
-        the path on a 'hybrid' engine."""
+    def _path(self, precise):
+        """precise: None = the most accurate arithmetic the engine holds (fp32-grade on 'fp32' / 'hybrid' engines);
+        True / False = fp32-grade / the engine's 16-bit arithmetic; or a name from PATHS."""
+        p = self.cfg.precision
+        if isinstance(precise, str):
+            return PATHS[precise]
         if precise is None:
-            precise = self.cfg.precision == 1
+            precise = p in (1, 2)
+        return 1 if precise else (2 if p == 3 else 0)
+
+    def _steps(self, steps):
+        steps = steps.detach().to(torch.int64)
+        if not steps.is_cuda:   # host-side step indices are range-checked before they index the embedding table
+            if steps.numel() and (int(steps.min()) < 0 or int(steps.max()) > self.cfg.n_diff_steps):
+                raise IndexError(f'diffusion step outside [0, {self.cfg.n_diff_steps}]')
+        return steps.to(self.device).contiguous()
+
+    def denoise(self, motion, steps, precise=None):
         motion = motion.detach().to(self.device, torch.float32).contiguous()
-        steps = steps.detach().to(self.device, torch.int64).contiguous()
+        steps = self._steps(steps)
         c = self.cfg
         out = torch.empty((self.S, c.n_prev_motions + c.n_motions, c.motion_dim), device=self.device)
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().msmd_denoise_ex(self._h, _lib.dev_ptr(motion), _lib.dev_ptr(steps, torch.int64),
-                                                  _lib.dev_ptr(out), int(bool(precise)), _lib.stream_ptr()))
+                                                  _lib.dev_ptr(out), self._path(precise), _lib.stream_ptr()))
         return out
+
+    def denoise_parts(self, motion, steps, precise=None):
+        """keep_separate=True outputs (model.py:972-973): (dynamic [S,Lp+L,dm], static [S,Lp+L,nb,dm], alphas [S,Lp+L,nb])."""
+        motion = motion.detach().to(self.device, torch.float32).contiguous()
+        steps = self._steps(steps)
+        c = self.cfg
+        R = c.n_prev_motions + c.n_motions
+        dyn = torch.empty((self.S, R, c.motion_dim), device=self.device)
+        sta = torch.empty((self.S, R, c.n_basis, c.motion_dim), device=self.device)
+        alp = torch.empty((self.S, R, c.n_basis), device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().msmd_denoise_parts(self._h, _lib.dev_ptr(motion), _lib.dev_ptr(steps, torch.int64),
+                                                     _lib.dev_ptr(dyn), _lib.dev_ptr(sta), _lib.dev_ptr(alp),
+                                                     self._path(precise), _lib.stream_ptr()))
+        return dyn, sta, alp
+
+    def check(self):
+        """Synchronise and raise if an earlier fp32-grade call overflowed its operand split."""
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().msmd_check(self._h, _lib.stream_ptr()))
 
     def sample_window(self, x_T, z=None, seed=0, cfg_independent=False, scale0=0.0, scale1=0.0, flexibility=0.0,
                       t_start=None, n_steps=None, want_traj=False, dynamic_threshold=None, separate=False,
-                      precise_last_steps=0):
+                      precise_last_steps=0, fp16_last_steps=0):
         c = self.cfg
         x_T = x_T.detach().to(self.device, torch.float32).contiguous()
         t_start = c.n_diff_steps if t_start is None else t_start
@@ -92,6 +125,7 @@ class DenoiserEngine:
         traj = torch.zeros((c.n_diff_steps + 1,) + tuple(x_T.shape), device=self.device) if want_traj else None
         ex = SampleExtras()
         ex.precise_last_steps = int(precise_last_steps)
+        ex.fp16_last_steps = int(fp16_last_steps)
         sep = None
         if dynamic_threshold:
             ex.use_dynamic_threshold = 1

@@ -32,6 +32,8 @@ SIGNATURES = {
     'msmd_window_begin': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     'msmd_denoise': (_i, [_vp, _vp, _vp, _vp, _vp]),
     'msmd_denoise_ex': (_i, [_vp, _vp, _vp, _vp, _i, _vp]),
+    'msmd_denoise_parts': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
+    'msmd_check': (_i, [_vp, _vp]),
     'msmd_sample_window': (_i, [_vp, _vp, _vp, C.c_uint64, _i, C.c_float, C.c_float, C.c_float, _i, _i, _vp, _vp, _vp]),
     'msmd_style_create': (_i, [_i, _i, _i, _i, _i, _i, C.POINTER(_vp)]),
     'msmd_style_destroy': (None, [_vp]),

@@ -55,13 +55,24 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
       : "memory");
 }
 
+template <bool F16>
+__device__ __forceinline__ uint32_t pack16(float a, float b) {
+  if constexpr (F16) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  } else {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+}
+
 __device__ __forceinline__ void attn_stamp(unsigned long long* tr, int role, int job, int ev) {
 #ifdef MSMD_ATTN_TRACE
   if (tr != nullptr && blockIdx.x == 0 && job < 16) tr[(role * 16 + job) * 8 + ev] = clock64();
 #endif
 }
 
-template <bool TAIL16>
+template <bool TAIL16, bool F16>
 __global__ void __launch_bounds__(kThreads, 1) self_attn_tc_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -118,8 +129,8 @@ __global__ void __launch_bounds__(kThreads, 1) self_attn_tc_kernel(const __grid_
     __syncwarp();
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    constexpr uint32_t idesc_qk = make_idesc(1, 128, kKeys);                 // bf16, K-major A and B
-    constexpr uint32_t idesc_pv = make_idesc(1, 128, 64) | (1u << 16);       // B (= V) is MN-major
+    constexpr uint32_t idesc_qk = make_idesc(F16 ? 0 : 1, 128, kKeys);                 // bf16 / fp16, K-major A and B
+    constexpr uint32_t idesc_pv = make_idesc(F16 ? 0 : 1, 128, 64) | (1u << 16);       // B (= V) is MN-major
     if (lane == 0) {
       for (int i = 0; i <= njobs; ++i) {
         if (i < njobs) {   // S_g = Q K^T of job i
@@ -205,8 +216,7 @@ __global__ void __launch_bounds__(kThreads, 1) self_attn_tc_kernel(const __grid_
           const float e0 = exp2f(fmaf(__uint_as_float(v[kc * 8 + 2 * u]), kScale, -ms));
           const float e1 = exp2f(fmaf(__uint_as_float(v[kc * 8 + 2 * u + 1]), kScale, -ms));
           l += e0 + e1;
-          __nv_bfloat162 hb = __floats2bfloat162_rn(e0, e1);
-          w[u] = *reinterpret_cast<uint32_t*>(&hb);
+          w[u] = pack16<F16>(e0, e1);
         }
         *reinterpret_cast<uint4*>(prow + (kc >> 3) * (128 * 128) + (((kc & 7) ^ swz) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
       }
@@ -232,9 +242,7 @@ __global__ void __launch_bounds__(kThreads, 1) self_attn_tc_kernel(const __grid_
         uint32_t w[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          __nv_bfloat162 hb = __floats2bfloat162_rn(__uint_as_float(o[c * 8 + 2 * u]) * inv,
-                                                    __uint_as_float(o[c * 8 + 2 * u + 1]) * inv);
-          w[u] = *reinterpret_cast<uint32_t*>(&hb);
+          w[u] = pack16<F16>(__uint_as_float(o[c * 8 + 2 * u]) * inv, __uint_as_float(o[c * 8 + 2 * u + 1]) * inv);
         }
         *reinterpret_cast<uint4*>(prow + ((c ^ swz) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);   // first 64-key block of P_g
       }
@@ -259,21 +267,22 @@ __global__ void __launch_bounds__(kThreads, 1) self_attn_tc_kernel(const __grid_
 
 }  // namespace
 
-int self_attn_tc_launch(const bf16* qkv, bf16* ctx, int S, int T, int H, cudaStream_t st) {
+int self_attn_tc_launch(const bf16* qkv, bf16* ctx, int S, int T, int H, int fp16, cudaStream_t st) {
   MSMD_REQUIRE(T >= 1 && T <= kKeys, "self_attn: sequence length %d exceeds the %d-token tile", T, kKeys);
   MSMD_REQUIRE(H >= 1 && S >= 1, "self_attn: empty problem");
   AttnParams p;
   memset(&p, 0, sizeof(p));
   const int d = H * 64;
   int rc;
+  const auto dt16 = fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   const uint64_t rows = (uint64_t)S * T;
-  if ((rc = make_tmap_2d(&p.q_map, qkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3 * d, rows, (uint64_t)3 * d * 2, 64, 128,
+  if ((rc = make_tmap_2d(&p.q_map, qkv, dt16, 3 * d, rows, (uint64_t)3 * d * 2, 64, 128,
                          CU_TENSOR_MAP_SWIZZLE_128B)))
     return rc;
-  if ((rc = make_tmap_2d(&p.kv_map, qkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3 * d, rows, (uint64_t)3 * d * 2, 64, kKeys,
+  if ((rc = make_tmap_2d(&p.kv_map, qkv, dt16, 3 * d, rows, (uint64_t)3 * d * 2, 64, kKeys,
                          CU_TENSOR_MAP_SWIZZLE_128B)))
     return rc;
-  if ((rc = make_tmap_2d(&p.out_map, ctx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, d, rows, (uint64_t)d * 2, 64, T,
+  if ((rc = make_tmap_2d(&p.out_map, ctx, dt16, d, rows, (uint64_t)d * 2, 64, T,
                          CU_TENSOR_MAP_SWIZZLE_128B)))
     return rc;
   p.S = S; p.T = T; p.H = H; p.jobs = S * H;
@@ -285,14 +294,17 @@ int self_attn_tc_launch(const bf16* qkv, bf16* ctx, int S, int T, int H, cudaStr
 #endif
   static bool attr = false;
   if (!attr) {
-    MSMD_CHECK_CUDA(cudaFuncSetAttribute(self_attn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    MSMD_CHECK_CUDA(cudaFuncSetAttribute(self_attn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    MSMD_CHECK_CUDA(cudaFuncSetAttribute(self_attn_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    MSMD_CHECK_CUDA(cudaFuncSetAttribute(self_attn_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    MSMD_CHECK_CUDA(cudaFuncSetAttribute(self_attn_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    MSMD_CHECK_CUDA(cudaFuncSetAttribute(self_attn_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     attr = true;
   }
   ProfileScope prof("self_attn", st);
   const int grid = p.jobs < kNumSMs ? p.jobs : kNumSMs;
-  if (T > kKeys - 16) MSMD_CHECK_CUDA(launch_pdl(self_attn_tc_kernel<true>, dim3(grid), dim3(kThreads), kSmemBytes, st, p));
-  else MSMD_CHECK_CUDA(launch_pdl(self_attn_tc_kernel<false>, dim3(grid), dim3(kThreads), kSmemBytes, st, p));
+  auto kern = T > kKeys - 16 ? (fp16 ? self_attn_tc_kernel<true, true> : self_attn_tc_kernel<true, false>)
+                             : (fp16 ? self_attn_tc_kernel<false, true> : self_attn_tc_kernel<false, false>);
+  MSMD_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(kThreads), kSmemBytes, st, p));
   MSMD_CHECK_LAUNCH();
 #ifdef MSMD_ATTN_TRACE
   {

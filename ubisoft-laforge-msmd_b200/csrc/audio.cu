@@ -37,7 +37,8 @@ uint16_t f2bf(float f) {
 struct msmd_audio {
   int device = 0, max_clips = 0, max_samples = 0, d_out = 512, n_layers = 12, n_heads = 12;
   bool loaded = false;
-  std::vector<void*> owned;
+  std::vector<void*> owned;   // workspaces first (allocated by create), then the packed weights
+  size_t n_workspace = (size_t)-1;   // owned[n_workspace..] are weights: released and re-packed by every load_weights
   // weights
   float *w0 = nullptr, *gn_w = nullptr, *gn_b = nullptr, *fp_g = nullptr, *fp_b = nullptr, *fp_bias = nullptr,
         *pos_bias = nullptr, *enc_g = nullptr, *enc_b = nullptr, *map_b = nullptr;
@@ -115,6 +116,12 @@ extern "C" int msmd_audio_load_weights(msmd_audio* m, const char* const* names, 
                                        const int64_t* numel, int n) {
   MSMD_REQUIRE(m && names && data && numel, "msmd_audio_load_weights: null argument");
   MSMD_CHECK_CUDA(cudaSetDevice(m->device));
+  // a reload replaces the previous packed copies instead of accumulating them until destroy
+  MSMD_CHECK_CUDA(cudaDeviceSynchronize());
+  if (m->n_workspace == (size_t)-1) m->n_workspace = m->owned.size();
+  for (size_t i = m->n_workspace; i < m->owned.size(); ++i) cudaFree(m->owned[i]);
+  m->owned.resize(m->n_workspace);
+  m->loaded = false;
   std::map<std::string, int> idx;
   for (int i = 0; i < n; ++i) idx[names[i]] = i;
   std::string missing;

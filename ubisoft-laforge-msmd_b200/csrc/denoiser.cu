@@ -17,6 +17,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <tuple>
 #include <vector>
 
 using namespace msmd;
@@ -27,7 +28,8 @@ struct LayerW {
   bf16 *Wqkv = nullptr, *Wo = nullptr, *Wq0 = nullptr, *Wkv = nullptr, *Wco = nullptr, *W1 = nullptr, *W2 = nullptr;
   float *bqkv = nullptr, *bo = nullptr, *bq0 = nullptr, *bkv = nullptr, *bco = nullptr, *b1 = nullptr, *b2 = nullptr;
   float *g1 = nullptr, *be1 = nullptr, *g2 = nullptr, *be2 = nullptr, *g3 = nullptr, *be3 = nullptr;
-  bf16 *kv = nullptr, *ca = nullptr;  // per-window caches
+  bf16 *kv = nullptr, *ca = nullptr;  // per-window caches (bf16 steps)
+  bf16 *kvh = nullptr, *cah = nullptr;  // same in fp16 storage (one-pass fp16 steps)
   // fp32-grade path (precision >= 1): fp16 two-term splits (x = hi + 2^-11 lo, gemm_tc.cuh MODE 2) of the same
   // weights, and fp32 caches
   __half *Wqkv_h = nullptr, *Wqkv_l = nullptr, *Wo_h = nullptr, *Wo_l = nullptr, *Wq0_h = nullptr, *Wq0_l = nullptr,
@@ -52,7 +54,9 @@ struct msmd_model {
   bool loaded = false, window = false;
   int T = 0, dp = 0, ldd = 80;
   std::vector<LayerW> L;
-  std::vector<void*> owned;  // every device allocation, freed in destroy
+  std::vector<void*> owned;   // workspaces, freed in destroy
+  std::vector<void*> wowned;  // packed weights: released and re-packed by every msmd_load_weights
+  bool packing = false;       // dalloc target: wowned while load_weights runs
   // fp32 parameters
   float *PE = nullptr, *temb = nullptr, *Wp = nullptr, *bp = nullptr, *Wf = nullptr, *WfT = nullptr, *bf_ = nullptr;
   std::vector<float*> Ws0, bs0, Ws2, bs2;
@@ -62,7 +66,7 @@ struct msmd_model {
   // workspaces
   bf16 *x = nullptr, *qkv = nullptr, *ctx = nullptr, *h = nullptr, *dec1 = nullptr, *mem = nullptr, *x0c = nullptr,
        *q0 = nullptr, *ctx0 = nullptr;
-  bf16 *y = nullptr, *y0 = nullptr;
+  bf16 *y = nullptr, *y0 = nullptr, *memh = nullptr;
   float *dec2 = nullptr, *pp = nullptr, *pmproj = nullptr, *stat = nullptr,
         *hid = nullptr, *xbuf = nullptr, *mixed = nullptr, *thr = nullptr;
   int* steps = nullptr;
@@ -72,11 +76,25 @@ struct msmd_model {
         *fx0c = nullptr, *fq0 = nullptr, *fctx0 = nullptr, *fy0 = nullptr;
   __half *ws_hi = nullptr, *ws_lo = nullptr;   // split scratch of the current A operand
   int* overflow = nullptr;                     // raised by the operand split when an activation leaves the fp16 range
-  bool f32_ready = false, window32 = false;
-  const float *w_audio = nullptr, *w_prev_audio = nullptr;   // conditioning kept for the lazy fp32 window pass
+  int *h_overflow = nullptr;                   // pinned mirror, filled asynchronously after fp32-grade steps
+  cudaEvent_t ovf_event = nullptr;
+  bool ovf_pending = false;
+  bool window16[2] = {false, false}, window32 = false;   // per-window caches built for [bf16, fp16] / fp32-grade
+  float *w_audio = nullptr, *w_prev_audio = nullptr, *w_ind = nullptr;   // engine-owned copies of the window's conditioning
   // window state
   int S = 0, NX = 0, E = 0;
-  const float* indicator = nullptr;
+  const float* indicator = nullptr;            // = w_ind, or null when the model has no indicator column
+  // sampling loop: device-resident parameter block of the update kernel + instantiated step graphs, keyed by
+  // (format, S, NX, E, thresholding).  Nothing caller-owned is baked into a graph, so it is reused by every later
+  // window / call of the same shape; the capture stream is created once here.
+  UpdateParams* d_up = nullptr;
+  cudaStream_t cap_stream = nullptr;
+  typedef std::tuple<int, int, int, int, int, float, float, float> GraphKey;
+  std::map<GraphKey, cudaGraphExec_t> graphs;
+  void drop_graphs() {
+    for (auto& g : graphs) cudaGraphExecDestroy(g.second);
+    graphs.clear();
+  }
 };
 
 namespace {
@@ -85,7 +103,7 @@ template <class Tp>
 int dalloc(msmd_model* m, Tp** p, size_t n) {
   void* q = nullptr;
   MSMD_CHECK_CUDA(cudaMalloc(&q, n * sizeof(Tp)));
-  m->owned.push_back(q);
+  (m->packing ? m->wowned : m->owned).push_back(q);
   *p = static_cast<Tp*>(q);
   return MSMD_OK;
 }
@@ -105,25 +123,31 @@ int up_bf16(msmd_model* m, bf16** dst, const float* h, size_t n) {
   return MSMD_OK;
 }
 
-int gemm(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const float* bias, const bf16* aux, int64_t ld_aux,
+// one-pass 16-bit GEMM: fmt 0 = bf16 operands (gemm_tc MODE 0), 1 = fp16 operands (MODE 3); W is the matching copy
+int gemm(int fmt, const bf16* A, int64_t lda, const void* W, int64_t ldw, const float* bias, const bf16* aux, int64_t ld_aux,
          void* out, int64_t ldo, int out_f32, int M, int N, int K, int act, cudaStream_t st) {
   GemmDesc d;
-  d.mode = 0; d.A = A; d.W = W; d.bias = bias; d.aux = aux; d.out = out;
+  d.mode = fmt ? 3 : 0; d.A = A; d.W = W; d.bias = bias; d.aux = aux; d.out = out;
   d.M = M; d.N = N; d.K = K; d.lda = lda; d.ldw = ldw; d.ldo = ldo; d.ld_aux = ld_aux;
   d.out_f32 = out_f32; d.aux_f32 = 0; d.act = act; d.gelu_heavy = act;
   return gemm_tc_launch(d, st);
 }
 
-int up_split(msmd_model* m, __half** hi, __half** lo, const float* h, size_t n) {
-  std::vector<__half> a(n), b(n);
+// fp16 copies of a weight: hi = fp16(w) (also the operand of the one-pass fp16 steps) and, for the fp32-grade path,
+// lo = fp16((w - hi) * 2^11)
+int up_split(msmd_model* m, __half** hi, __half** lo, const float* h, size_t n, bool want_lo) {
+  std::vector<__half> a(n), b(want_lo ? n : 0);
   for (size_t i = 0; i < n; ++i) {
     a[i] = __float2half_rn(h[i]);
-    b[i] = __float2half_rn((h[i] - __half2float(a[i])) * 2048.0f);
+    if (want_lo) b[i] = __float2half_rn((h[i] - __half2float(a[i])) * 2048.0f);
   }
   int rc;
-  if ((rc = dalloc(m, hi, n)) || (rc = dalloc(m, lo, n))) return rc;
+  if ((rc = dalloc(m, hi, n))) return rc;
   MSMD_CHECK_CUDA(cudaMemcpy(*hi, a.data(), n * sizeof(__half), cudaMemcpyHostToDevice));
-  MSMD_CHECK_CUDA(cudaMemcpy(*lo, b.data(), n * sizeof(__half), cudaMemcpyHostToDevice));
+  if (want_lo) {
+    if ((rc = dalloc(m, lo, n))) return rc;
+    MSMD_CHECK_CUDA(cudaMemcpy(*lo, b.data(), n * sizeof(__half), cudaMemcpyHostToDevice));
+  }
   return MSMD_OK;
 }
 
@@ -193,51 +217,100 @@ int window_begin_f32(msmd_model* m, cudaStream_t st) {
   return MSMD_OK;
 }
 
-// One forward of the network on the current window context: x rows [NX,L,dm] -> dec2 [M, ldd]
-int run_forward(msmd_model* m, const float* xrows, cudaStream_t st) {
+// One forward of the network on the current window context: x rows [NX,L,dm] -> dec2 [M, ldd].
+// fmt 0: bf16 storage + bf16 tensor-core GEMMs; fmt 1: fp16 storage + one-pass fp16 GEMMs (same kernels, same cost,
+// 11 mantissa bits instead of 8: x0_hat error 8e-4 instead of 6.5e-3).
+int run_forward(msmd_model* m, const float* xrows, cudaStream_t st, int fmt) {
   const msmd_config& c = m->c;
   const int S = m->S, T = m->T, d = c.d_model, M = S * T;
   int rc;
-  EmbedParams ep;
+  EmbedParams ep{};
   ep.pp = m->pp; ep.temb = m->temb; ep.pmproj = m->pmproj; ep.PE = m->PE; ep.steps = m->steps;
   ep.x = xrows; ep.indicator = c.use_indicator ? m->indicator : nullptr; ep.WfT = m->WfT; ep.bf = m->bf_;
   ep.out = m->x; ep.S = S; ep.NX = m->NX; ep.E = m->E; ep.Lp = c.n_prev_motions; ep.L = c.n_motions; ep.d = d;
-  ep.dm = c.motion_dim;
+  ep.dm = c.motion_dim; ep.fp16 = fmt;
   if ((rc = embed_launch(ep, st))) return rc;
   for (int l = 0; l < c.n_layers; ++l) {
     LayerW& w = m->L[l];
+    const void *Wqkv = fmt ? (const void*)w.Wqkv_h : w.Wqkv, *Wo = fmt ? (const void*)w.Wo_h : w.Wo,
+               *Wq0 = fmt ? (const void*)w.Wq0_h : w.Wq0, *Wco = fmt ? (const void*)w.Wco_h : w.Wco,
+               *W1 = fmt ? (const void*)w.W1_h : w.W1, *W2 = fmt ? (const void*)w.W2_h : w.W2;
+    const bf16 *kv = fmt ? w.kvh : w.kv, *ca = fmt ? w.cah : w.ca;
     // self-attention block (nn.TransformerDecoderLayer._sa_block) + norm1, then the cached cross-attention
     // rows + norm2 for motion tokens
-    if ((rc = gemm(m->x, d, w.Wqkv, d, w.bqkv, nullptr, 0, m->qkv, 3 * d, 0, M, 3 * d, d, 0, st))) return rc;
-    static const bool attn_mma_sync = [] { const char* e = getenv("MSMD_ATTN_MMA_SYNC"); return e && atoi(e) != 0; }();  // A/B
-    if ((rc = attn_mma_sync ? self_attn_launch(m->qkv, m->ctx, S, T, c.n_heads, st)
-                            : self_attn_tc_launch(m->qkv, m->ctx, S, T, c.n_heads, st)))
-      return rc;
-    if ((rc = gemm(m->ctx, d, w.Wo, d, w.bo, nullptr, 0, m->y, d, 0, M, d, d, 0, st))) return rc;
-    LnParams lp;
+    if ((rc = gemm(fmt, m->x, d, Wqkv, d, w.bqkv, nullptr, 0, m->qkv, 3 * d, 0, M, 3 * d, d, 0, st))) return rc;
+    if ((rc = self_attn_tc_launch(m->qkv, m->ctx, S, T, c.n_heads, fmt, st))) return rc;
+    if ((rc = gemm(fmt, m->ctx, d, Wo, d, w.bo, nullptr, 0, m->y, d, 0, M, d, d, 0, st))) return rc;
+    LnParams lp{};
     lp.resid = m->x;
-    lp.y = m->y; lp.g1 = w.g1; lp.b1 = w.be1; lp.add = w.ca; lp.g2 = w.g2; lp.b2 = w.be2; lp.out = m->x;
-    lp.x0 = m->x0c; lp.skip_tok0 = 0; lp.M = M; lp.T = T; lp.d = d;
+    lp.y = m->y; lp.g1 = w.g1; lp.b1 = w.be1; lp.add = ca; lp.g2 = w.g2; lp.b2 = w.be2; lp.out = m->x;
+    lp.x0 = m->x0c; lp.skip_tok0 = 0; lp.M = M; lp.T = T; lp.d = d; lp.fp16 = fmt;
     if ((rc = ln_launch(lp, st))) return rc;
     // person token (row 0): real cross attention over the memory (_mha_block) + norm2
-    if ((rc = gemm(m->x0c, d, w.Wq0, d, w.bq0, nullptr, 0, m->q0, d, 0, S, d, d, 0, st))) return rc;
-    if ((rc = cross_attn_row0_launch(m->q0, w.kv, m->ctx0, S, T - 1, c.n_heads, st))) return rc;
-    if ((rc = gemm(m->ctx0, d, w.Wco, d, w.bco, nullptr, 0, m->y0, d, 0, S, d, d, 0, st))) return rc;
-    if ((rc = ln_row0_launch(m->y0, m->x0c, w.g2, w.be2, m->x, nullptr, S, T, d, st))) return rc;
+    if ((rc = gemm(fmt, m->x0c, d, Wq0, d, w.bq0, nullptr, 0, m->q0, d, 0, S, d, d, 0, st))) return rc;
+    if ((rc = cross_attn_row0_launch(m->q0, kv, m->ctx0, S, T - 1, c.n_heads, fmt, st))) return rc;
+    if ((rc = gemm(fmt, m->ctx0, d, Wco, d, w.bco, nullptr, 0, m->y0, d, 0, S, d, d, 0, st))) return rc;
+    if ((rc = ln_row0_launch(m->y0, m->x0c, w.g2, w.be2, m->x, nullptr, S, T, d, fmt, st))) return rc;
     // feed-forward block (_ff_block) + norm3
-    if ((rc = gemm(m->x, d, w.W1, d, w.b1, nullptr, 0, m->h, c.d_ff, 0, M, c.d_ff, d, 1, st))) return rc;
-    if ((rc = gemm(m->h, c.d_ff, w.W2, c.d_ff, w.b2, nullptr, 0, m->y, d, 0, M, d, c.d_ff, 0, st))) return rc;
-    LnParams l3;
+    if ((rc = gemm(fmt, m->x, d, W1, d, w.b1, nullptr, 0, m->h, c.d_ff, 0, M, c.d_ff, d, 1, st))) return rc;
+    if ((rc = gemm(fmt, m->h, c.d_ff, W2, c.d_ff, w.b2, nullptr, 0, m->y, d, 0, M, d, c.d_ff, 0, st))) return rc;
+    LnParams l3{};
     l3.resid = m->x;
     l3.y = m->y; l3.g1 = w.g3; l3.b1 = w.be3; l3.add = nullptr; l3.g2 = nullptr; l3.b2 = nullptr; l3.out = m->x;
-    l3.x0 = nullptr; l3.skip_tok0 = 0; l3.M = M; l3.T = T; l3.d = d;
+    l3.x0 = nullptr; l3.skip_tok0 = 0; l3.M = M; l3.T = T; l3.d = d; l3.fp16 = fmt;
     if ((rc = ln_launch(l3, st))) return rc;
   }
   // motion_dec (model.py:961): Linear(d, d/2) + GELU + Linear(d/2, dm + n_basis)
-  if ((rc = gemm(m->x, d, m->Wd1, d, m->bd1, nullptr, 0, m->dec1, d / 2, 0, M, d / 2, d, 1, st))) return rc;
-  if ((rc = gemm(m->dec1, d / 2, m->Wd2, d / 2, m->bd2, nullptr, 0, m->dec2, m->ldd, 1, M, c.motion_dim + c.n_basis,
+  const void *Wd1 = fmt ? (const void*)m->Wd1_h : m->Wd1, *Wd2 = fmt ? (const void*)m->Wd2_h : m->Wd2;
+  if ((rc = gemm(fmt, m->x, d, Wd1, d, m->bd1, nullptr, 0, m->dec1, d / 2, 0, M, d / 2, d, 1, st))) return rc;
+  if ((rc = gemm(fmt, m->dec1, d / 2, Wd2, d / 2, m->bd2, nullptr, 0, m->dec2, m->ldd, 1, M, c.motion_dim + c.n_basis,
                  d / 2, 0, st)))
     return rc;
+  return MSMD_OK;
+}
+
+// per-window caches of a 16-bit path (fmt 0 bf16 / 1 fp16): memory K|V projection of every layer, then the motion rows'
+// cross-attention output out_proj(v_proj(mem)) (softmax over a single visible key is 1, so the query drops out:
+// SURVEY section 0).  Built on first use in the window: a pure-bf16 call never pays for the fp16 copies.
+int window_begin_16(msmd_model* m, int fmt, cudaStream_t st) {
+  const msmd_config& c = m->c;
+  const int S = m->S, d = c.d_model, Tk = m->T - 1;
+  int rc;
+  bf16* mem = fmt ? m->memh : m->mem;
+  if ((rc = build_memory_h16(m->w_prev_audio, m->w_audio, mem, S, c.n_prev_motions, c.n_motions, d, fmt, st))) return rc;
+  for (auto& w : m->L) {
+    bf16 *kv = fmt ? w.kvh : w.kv, *ca = fmt ? w.cah : w.ca;
+    const void *Wkv = fmt ? (const void*)w.Wkv_h : w.Wkv, *Wco = fmt ? (const void*)w.Wco_h : w.Wco;
+    if ((rc = gemm(fmt, mem, d, Wkv, d, w.bkv, nullptr, 0, kv, 2 * d, 0, S * Tk, 2 * d, d, 0, st))) return rc;
+    if ((rc = gemm(fmt, kv + d, 2 * d, Wco, d, w.bco, nullptr, 0, ca, d, 0, S * Tk, d, d, 0, st))) return rc;
+  }
+  m->window16[fmt] = true;
+  return MSMD_OK;
+}
+
+// which arithmetic a model created with `precision` holds
+bool has_bf16(const msmd_config& c) { return c.precision == 0 || c.precision == 2; }
+bool has_fp16(const msmd_config& c) { return c.precision == 2 || c.precision == 3; }
+bool has_f32(const msmd_config& c) { return c.precision == 1 || c.precision == 2; }
+
+// The fp32-grade path reports operand-split overflow without synchronising the call that hit it: the flag is copied
+// to pinned memory behind the work, and inspected here at the NEXT entry (the state itself was poisoned with NaN).
+int poll_overflow(msmd_model* m, const char* who) {
+  if (!m->ovf_pending || cudaEventQuery(m->ovf_event) != cudaSuccess) return MSMD_OK;
+  m->ovf_pending = false;
+  if (*m->h_overflow) {
+    *m->h_overflow = 0;
+    cudaMemset(m->overflow, 0, sizeof(int));
+    set_error("%s: an earlier fp32-grade call left the fp16 range of its GEMM operand split (|activation| > 65504 or NaN); "
+              "its output was poisoned with NaN", who);
+    return MSMD_ERR_INVALID;
+  }
+  return MSMD_OK;
+}
+int post_overflow(msmd_model* m, cudaStream_t st) {
+  MSMD_CHECK_CUDA(cudaMemcpyAsync(m->h_overflow, m->overflow, sizeof(int), cudaMemcpyDeviceToHost, st));
+  MSMD_CHECK_CUDA(cudaEventRecord(m->ovf_event, st));
+  m->ovf_pending = true;
   return MSMD_OK;
 }
 
@@ -246,17 +319,20 @@ int run_forward(msmd_model* m, const float* xrows, cudaStream_t st) {
 extern "C" int msmd_create(const msmd_config* cfg, int device, msmd_model** out) {
   MSMD_REQUIRE(cfg && out, "msmd_create: null argument");
   const msmd_config& c = *cfg;
+  // supported shape envelope: the kernels are specialised for the released architecture
   MSMD_REQUIRE(c.d_model == 512 && c.n_heads * 64 == c.d_model, "msmd_create: only d_model=512 / 8 heads x 64 is built (got %d / %d)",
                c.d_model, c.n_heads);
-  MSMD_REQUIRE(1 + c.n_prev_motions + c.n_motions <= 112, "msmd_create: sequence %d exceeds the 112-token attention tile",
-               1 + c.n_prev_motions + c.n_motions);
-  MSMD_REQUIRE(c.n_layers > 0 && c.d_ff % 8 == 0 && c.max_seqs > 0 && c.n_diff_steps > 0, "msmd_create: bad sizes");
-  MSMD_REQUIRE(c.motion_dim + c.n_basis <= 80, "msmd_create: motion_dim + n_basis > 80");
+  MSMD_REQUIRE(c.n_motions > 0 && c.n_prev_motions >= 0 && 1 + c.n_prev_motions + c.n_motions <= 112,
+               "msmd_create: sequence 1 + n_prev_motions + n_motions = %d exceeds the 112-token attention tile "
+               "(the released configuration is 1 + 10 + 100)", 1 + c.n_prev_motions + c.n_motions);
+  MSMD_REQUIRE(c.n_layers > 0 && c.d_ff > 0 && c.d_ff % 8 == 0 && c.max_seqs > 0 && c.n_diff_steps > 0, "msmd_create: bad sizes");
+  MSMD_REQUIRE(c.motion_dim > 3 && c.n_basis >= 0 && c.motion_dim + c.n_basis <= 80, "msmd_create: motion_dim + n_basis > 80");
   if (c.align_mask_width != 1) {
     set_error("msmd_create: align_mask_width=%d: only width 1 (step-invariant cross attention) is implemented", c.align_mask_width);
     return MSMD_ERR_UNSUPPORTED;
   }
-  MSMD_REQUIRE(c.precision >= 0 && c.precision <= 2, "msmd_create: precision %d (0 bf16, 1 fp32-grade, 2 both/hybrid)", c.precision);
+  MSMD_REQUIRE(c.precision >= 0 && c.precision <= 3,
+               "msmd_create: precision %d (0 bf16, 1 fp32-grade, 2 hybrid: bf16 + fp16 + fp32-grade, 3 fp16)", c.precision);
   MSMD_CHECK_CUDA(cudaSetDevice(device));
   msmd_model* m = new msmd_model();
   m->c = c;
@@ -267,18 +343,40 @@ extern "C" int msmd_create(const msmd_config* cfg, int device, msmd_model** out)
   const size_t S = c.max_seqs, T = m->T, M = S * T, d = c.d_model;
   int rc = MSMD_OK;
   auto A = [&](auto** p, size_t n) { if (!rc) rc = dalloc(m, p, n); };
-  A(&m->x, M * d); A(&m->qkv, M * 3 * d); A(&m->ctx, M * d); A(&m->h, M * c.d_ff); A(&m->dec1, M * d / 2);
-  A(&m->mem, S * (T - 1) * d); A(&m->x0c, S * d); A(&m->q0, S * d); A(&m->ctx0, S * d);
-  A(&m->y, M * d); A(&m->y0, S * d); A(&m->dec2, M * m->ldd); A(&m->pp, S * d);
+  A(&m->dec2, M * m->ldd); A(&m->pp, S * d);
   A(&m->pmproj, S * c.n_prev_motions * d); A(&m->stat, S * c.n_basis * c.motion_dim); A(&m->hid, S * d);
   A(&m->thr, S);
   A(&m->xbuf, S * c.n_motions * c.motion_dim); A(&m->mixed, S * (T - 1) * c.motion_dim); A(&m->steps, S);
-  for (auto& w : m->L) { A(&w.kv, S * (T - 1) * 2 * d); A(&w.ca, S * (T - 1) * d); }
-  if (c.precision >= 1) {
+  A(&m->w_audio, S * c.n_motions * d); A(&m->w_prev_audio, S * c.n_prev_motions * d); A(&m->w_ind, S * c.n_motions);
+  A(&m->d_up, 1);
+  if (has_bf16(c) || has_fp16(c)) {
+    A(&m->x, M * d); A(&m->qkv, M * 3 * d); A(&m->ctx, M * d); A(&m->h, M * c.d_ff); A(&m->dec1, M * d / 2);
+    A(&m->x0c, S * d); A(&m->q0, S * d); A(&m->ctx0, S * d); A(&m->y, M * d); A(&m->y0, S * d);
+  }
+  if (has_bf16(c)) {
+    A(&m->mem, S * (T - 1) * d);
+    for (auto& w : m->L) { A(&w.kv, S * (T - 1) * 2 * d); A(&w.ca, S * (T - 1) * d); }
+  }
+  if (has_fp16(c)) {
+    A(&m->memh, S * (T - 1) * d);
+    for (auto& w : m->L) { A(&w.kvh, S * (T - 1) * 2 * d); A(&w.cah, S * (T - 1) * d); }
+  }
+  if (has_f32(c)) {
     A(&m->fx, M * d); A(&m->fqkv, M * 3 * d); A(&m->fctx, M * d); A(&m->fh, M * c.d_ff); A(&m->fy, M * d);
     A(&m->fdec1, M * d / 2); A(&m->fmem, S * (T - 1) * d); A(&m->fx0c, S * d); A(&m->fq0, S * d); A(&m->fctx0, S * d);
-    A(&m->fy0, S * d); A(&m->ws_hi, M * c.d_ff); A(&m->ws_lo, M * c.d_ff); A(&m->overflow, 1);
+    A(&m->fy0, S * d);
+    // split scratch of the current A operand: the widest is FF2's [M, d_ff] or the window pass's kv cache [S*Tk, 2d]
+    const size_t ws = std::max(M * (size_t)c.d_ff, S * (T - 1) * 2 * d);
+    A(&m->ws_hi, ws); A(&m->ws_lo, ws); A(&m->overflow, 1);
     for (auto& w : m->L) { A(&w.kv32, S * (T - 1) * 2 * d); A(&w.ca32, S * (T - 1) * d); }
+  }
+  if (!rc && cudaStreamCreateWithFlags(&m->cap_stream, cudaStreamNonBlocking) != cudaSuccess) rc = MSMD_ERR_CUDA;
+  if (!rc && m->overflow) {
+    if (cudaMallocHost(&m->h_overflow, sizeof(int)) != cudaSuccess ||
+        cudaEventCreateWithFlags(&m->ovf_event, cudaEventDisableTiming) != cudaSuccess)
+      rc = MSMD_ERR_CUDA;
+    else
+      *m->h_overflow = 0;
   }
   if (rc) { msmd_destroy(m); return rc; }
   cudaMemset(m->dec2, 0, M * m->ldd * sizeof(float));
@@ -289,7 +387,14 @@ extern "C" int msmd_create(const msmd_config* cfg, int device, msmd_model** out)
 
 extern "C" void msmd_destroy(msmd_model* m) {
   if (!m) return;
+  cudaSetDevice(m->device);
+  cudaDeviceSynchronize();   // graph launches / async copies of earlier calls may still be in flight
+  m->drop_graphs();
+  if (m->cap_stream) cudaStreamDestroy(m->cap_stream);
+  if (m->ovf_event) cudaEventDestroy(m->ovf_event);
+  if (m->h_overflow) cudaFreeHost(m->h_overflow);
   for (void* p : m->owned) cudaFree(p);
+  for (void* p : m->wowned) cudaFree(p);
   delete m;
 }
 
@@ -298,6 +403,15 @@ extern "C" int msmd_load_weights(msmd_model* m, const char* const* names, const 
   MSMD_REQUIRE(m && names && data && numel, "msmd_load_weights: null argument");
   const msmd_config& c = m->c;
   MSMD_CHECK_CUDA(cudaSetDevice(m->device));
+  // a reload replaces the previous packed copies (they used to accumulate until msmd_destroy) and invalidates the
+  // step graphs, which hold their addresses
+  MSMD_CHECK_CUDA(cudaDeviceSynchronize());
+  m->drop_graphs();
+  for (void* p : m->wowned) cudaFree(p);
+  m->wowned.clear();
+  m->loaded = false;
+  m->window = false;
+  struct PackScope { msmd_model* m; PackScope(msmd_model* mm) : m(mm) { m->packing = true; } ~PackScope() { m->packing = false; } } scope(m);
   std::map<std::string, int> idx;
   for (int i = 0; i < n; ++i) idx[names[i]] = i;
   std::string missing;
@@ -322,11 +436,11 @@ extern "C" int msmd_load_weights(msmd_model* m, const char* const* names, const 
   const std::string P = "denoising_net.";
   std::vector<float> h, h2;
   auto F32 = [&](const std::string& key, size_t n_, float** dst) { if (!rc && fetch(key, n_, h)) rc = up_f32(m, dst, h); };
-  const bool want_bf = c.precision != 1, want_f32 = c.precision >= 1;
-  // a GEMM weight: bf16 copy for the bf16 path and/or tf32 hi/lo split for the fp32-grade path
+  const bool want_bf = has_bf16(c), want_hi = has_fp16(c) || has_f32(c), want_lo = has_f32(c);
+  // a GEMM weight: bf16 copy for the bf16 path and/or fp16 hi (+ lo) for the one-pass fp16 / fp32-grade paths
   auto put_w = [&](const float* src, size_t n_, bf16** dst, __half** hi, __half** lo) {
     if (!rc && want_bf) rc = up_bf16(m, dst, src, n_);
-    if (!rc && want_f32) rc = up_split(m, hi, lo, src, n_);
+    if (!rc && want_hi) rc = up_split(m, hi, lo, src, n_, want_lo);
   };
   auto BF = [&](const std::string& key, size_t n_, bf16** dst, __half** hi, __half** lo) {
     if (!rc && fetch(key, n_, h)) put_w(h.data(), n_, dst, hi, lo);
@@ -416,21 +530,19 @@ extern "C" int msmd_window_begin(msmd_model* m, const float* audio, const float*
   MSMD_REQUIRE(E <= 3, "msmd_window_begin: at most 2 guidance conditions (3 entries)");
   MSMD_REQUIRE(audio && person && style && prev_motion && prev_audio, "msmd_window_begin: null conditioning tensor");
   MSMD_REQUIRE(!c.use_indicator || indicator, "Missing indicator: the model was built with use_indicator");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int d = c.d_model, Tk = m->T - 1, Lp = c.n_prev_motions, dm = c.motion_dim;
   int rc;
+  if ((rc = poll_overflow(m, "msmd_window_begin"))) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int d = c.d_model, Lp = c.n_prev_motions, dm = c.motion_dim;
   m->S = S; m->NX = NX; m->E = E;
-  m->w_audio = audio; m->w_prev_audio = prev_audio;
-  m->window32 = false;
-  if (c.precision == 1 && (rc = window_begin_f32(m, st))) return rc;  // precision 2 builds these on first use
-  if (c.precision != 1 && (rc = build_memory_bf16(prev_audio, audio, m->mem, S, Lp, c.n_motions, d, st))) return rc;
-  for (auto& w : m->L) {
-    if (c.precision == 1) break;
-    // memory K|V projection, then the motion rows' cross-attention output out_proj(v_proj(mem)) (softmax over
-    // a single visible key is 1, so the query drops out: SURVEY section 0)
-    if ((rc = gemm(m->mem, d, w.Wkv, d, w.bkv, nullptr, 0, w.kv, 2 * d, 0, S * Tk, 2 * d, d, 0, st))) return rc;
-    if ((rc = gemm(w.kv + d, 2 * d, w.Wco, d, w.bco, nullptr, 0, w.ca, d, 0, S * Tk, d, d, 0, st))) return rc;
-  }
+  // the conditioning the later (lazy) cache passes and every step read is copied into the handle: the caller's tensors
+  // may be released as soon as this call returns, and the step graph only ever sees engine-owned addresses
+  MSMD_CHECK_CUDA(cudaMemcpyAsync(m->w_audio, audio, (size_t)S * c.n_motions * d * 4, cudaMemcpyDeviceToDevice, st));
+  MSMD_CHECK_CUDA(cudaMemcpyAsync(m->w_prev_audio, prev_audio, (size_t)S * Lp * d * 4, cudaMemcpyDeviceToDevice, st));
+  if (c.use_indicator)
+    MSMD_CHECK_CUDA(cudaMemcpyAsync(m->w_ind, indicator, (size_t)S * c.n_motions * 4, cudaMemcpyDeviceToDevice, st));
+  m->indicator = c.use_indicator ? m->w_ind : nullptr;
+  m->window16[0] = m->window16[1] = m->window32 = false;
   if ((rc = linear_simt(person, m->dp, m->Wp, m->dp, m->bp, m->pp, d, S, d, m->dp, 0, st))) return rc;
   const int fin = dm + (c.use_indicator ? 1 : 0);
   if ((rc = linear_simt(prev_motion, dm, m->Wf, fin, m->bf_, m->pmproj, d, S * Lp, d, dm, 0, st))) return rc;
@@ -439,46 +551,42 @@ extern "C" int msmd_window_begin(msmd_model* m, const float* audio, const float*
     if ((rc = linear_simt(m->hid, d, m->Ws2[b], d, m->bs2[b], m->stat + b * dm, (int64_t)c.n_basis * dm, S, dm, d, 0, st)))
       return rc;
   }
-  m->indicator = indicator;
+  // the cross-attention caches of the model's main arithmetic now; the other formats of a hybrid model on first use
+  if (c.precision == 1) { if ((rc = window_begin_f32(m, st))) return rc; }
+  else if ((rc = window_begin_16(m, c.precision == 3 ? 1 : 0, st))) return rc;
   m->window = true;
   return MSMD_OK;
 }
 
-__global__ void steps_from_i64_kernel(const int64_t* in, int* out, int S) {
+// int64 step indices of the module-level forward -> int32, clamped to the timestep-embedding table [0, n_diff_steps]
+__global__ void steps_from_i64_kernel(const int64_t* in, int* out, int S, int t_max) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < S) out[i] = (int)in[i];
+  if (i < S) out[i] = (int)min((int64_t)t_max, max((int64_t)0, in[i]));
 }
 
 namespace {
-// fp32-grade path: the fp16 two-term operand split needs |activation| < 65504; fail loudly instead of returning NaNs
-int check_overflow(msmd_model* m, cudaStream_t st, const char* who) {
-  if (!m->overflow) return MSMD_OK;
-  int flag = 0;
-  MSMD_CHECK_CUDA(cudaMemcpyAsync(&flag, m->overflow, sizeof(int), cudaMemcpyDeviceToHost, st));
-  MSMD_CHECK_CUDA(cudaStreamSynchronize(st));
-  if (flag) {
-    cudaMemsetAsync(m->overflow, 0, sizeof(int), st);
-    set_error("%s: an activation left the fp16 range of the fp32-grade GEMM operand split (|x| > 65504 or NaN)", who);
-    return MSMD_ERR_INVALID;
+// path: 0 bf16, 1 fp32-grade, 2 one-pass fp16
+int check_path(const msmd_model* m, int path, const char* who) {
+  const bool ok = path == 0 ? has_bf16(m->c) : (path == 1 ? has_f32(m->c) : (path == 2 ? has_fp16(m->c) : false));
+  if (!ok) {
+    set_error("%s: arithmetic %d (0 bf16, 1 fp32-grade, 2 fp16) is not resident in a model created with precision %d", who,
+              path, m->c.precision);
+    return MSMD_ERR_STATE;
   }
   return MSMD_OK;
 }
-int check_precise(const msmd_model* m, int precise, const char* who) {
-  if (precise && m->c.precision == 0) {
-    set_error("%s: the fp32-grade path needs a model created with precision 1 or 2", who);
-    return MSMD_ERR_STATE;
-  }
-  if (!precise && m->c.precision == 1) {
-    set_error("%s: the bf16 path needs a model created with precision 0 or 2", who);
-    return MSMD_ERR_STATE;
-  }
-  return MSMD_OK;
+int forward_path(msmd_model* m, const float* xrows, int path, cudaStream_t st) {
+  int rc;
+  if (path == 1) return run_forward_f32(m, xrows, st);
+  const int fmt = path == 2 ? 1 : 0;
+  if (!m->window16[fmt] && (rc = window_begin_16(m, fmt, st))) return rc;
+  return run_forward(m, xrows, st, fmt);
 }
 }  // namespace
 
 extern "C" int msmd_denoise(msmd_model* m, const float* motion, const int64_t* steps, float* out, void* stream) {
   MSMD_REQUIRE(m, "msmd_denoise: null argument");
-  return msmd_denoise_ex(m, motion, steps, out, m->c.precision == 1, stream);
+  return msmd_denoise_ex(m, motion, steps, out, m->c.precision == 1 ? 1 : (m->c.precision == 3 ? 2 : 0), stream);
 }
 
 extern "C" int msmd_denoise_ex(msmd_model* m, const float* motion, const int64_t* steps, float* out, int precise,
@@ -486,14 +594,38 @@ extern "C" int msmd_denoise_ex(msmd_model* m, const float* motion, const int64_t
   MSMD_REQUIRE(m && motion && steps && out, "msmd_denoise: null argument");
   if (!m->window) { set_error("msmd_denoise: call msmd_window_begin first"); return MSMD_ERR_STATE; }
   MSMD_REQUIRE(m->E == 1 && m->NX == m->S, "msmd_denoise: window must be opened with NX == S, E == 1");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  steps_from_i64_kernel<<<cdiv(m->S, 256), 256, 0, st>>>(steps, m->steps, m->S);
-  MSMD_CHECK_LAUNCH();
-  int rc = check_precise(m, precise, "msmd_denoise");
+  int rc = check_path(m, precise, "msmd_denoise");
   if (rc) return rc;
-  if ((rc = precise ? run_forward_f32(m, motion, st) : run_forward(m, motion, st))) return rc;
-  if (precise && (rc = check_overflow(m, st, "msmd_denoise"))) return rc;   // (synchronises; the bf16 path does not)
-  return mix_static_launch(m->dec2, m->stat, out, m->S, m->T, m->c.motion_dim, m->c.n_basis, m->ldd, st);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  steps_from_i64_kernel<<<cdiv(m->S, 256), 256, 0, st>>>(steps, m->steps, m->S, m->c.n_diff_steps);
+  MSMD_CHECK_LAUNCH();
+  if ((rc = forward_path(m, motion, precise, st))) return rc;
+  if ((rc = mix_static_launch(m->dec2, m->stat, out, m->S, m->T, m->c.motion_dim, m->c.n_basis, m->ldd, st))) return rc;
+  if (precise == 1) {   // module-level parity entry: report an operand-split overflow right away (this one synchronises)
+    int flag = 0;
+    MSMD_CHECK_CUDA(cudaMemcpyAsync(&flag, m->overflow, sizeof(int), cudaMemcpyDeviceToHost, st));
+    MSMD_CHECK_CUDA(cudaStreamSynchronize(st));
+    if (flag) {
+      cudaMemsetAsync(m->overflow, 0, sizeof(int), st);
+      set_error("msmd_denoise: an activation left the fp16 range of the fp32-grade GEMM operand split (|x| > 65504 or NaN)");
+      return MSMD_ERR_INVALID;
+    }
+  }
+  return MSMD_OK;
+}
+
+extern "C" int msmd_denoise_parts(msmd_model* m, const float* motion, const int64_t* steps, float* dyn, float* stat,
+                                  float* alphas, int precise, void* stream) {
+  MSMD_REQUIRE(m && motion && steps && dyn && stat && alphas, "msmd_denoise_parts: null argument");
+  if (!m->window) { set_error("msmd_denoise_parts: call msmd_window_begin first"); return MSMD_ERR_STATE; }
+  MSMD_REQUIRE(m->E == 1 && m->NX == m->S, "msmd_denoise_parts: window must be opened with NX == S, E == 1");
+  int rc = check_path(m, precise, "msmd_denoise_parts");
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  steps_from_i64_kernel<<<cdiv(m->S, 256), 256, 0, st>>>(steps, m->steps, m->S, m->c.n_diff_steps);
+  MSMD_CHECK_LAUNCH();
+  if ((rc = forward_path(m, motion, precise, st))) return rc;
+  return split_parts_launch(m->dec2, m->stat, dyn, stat, alphas, m->S, m->T, m->c.motion_dim, m->c.n_basis, m->ldd, st);
 }
 
 extern "C" int msmd_sample_window(msmd_model* m, const float* x_T, const float* z, uint64_t seed, int cfg_independent,
@@ -512,27 +644,36 @@ extern "C" int msmd_sample_window_ex(msmd_model* m, const float* x_T, const floa
   MSMD_REQUIRE(t_start >= 1 && t_start <= c.n_diff_steps && n_steps >= 1 && n_steps <= t_start,
                "msmd_sample_window: steps %d..%d outside 1..%d", t_start, t_start - n_steps + 1, c.n_diff_steps);
   MSMD_REQUIRE(flexibility >= 0.f && flexibility <= 1.f, "msmd_sample_window: flexibility outside [0,1]");
+  int rc;
+  if ((rc = poll_overflow(m, "msmd_sample_window"))) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t n_el = (size_t)m->NX * c.n_motions * c.motion_dim;
   MSMD_CHECK_CUDA(cudaMemcpyAsync(m->xbuf, x_T, n_el * 4, cudaMemcpyDeviceToDevice, st));
-  int rc;
   if ((rc = steps_set(m->steps, m->S, t_start, st))) return rc;
 
-  UpdateParams up;
+  // step schedule: t <= k32 fp32-grade, k32 < t <= k16 one-pass fp16, t > k16 the model's main 16-bit arithmetic
+  int k32 = c.precision == 1 ? c.n_diff_steps : 0;
+  int k16 = c.precision == 3 ? c.n_diff_steps : 0;
+  if (ex && c.precision != 1) {
+    k32 = ex->precise_last_steps < 0 ? c.n_diff_steps : ex->precise_last_steps;
+    MSMD_REQUIRE(k32 == 0 || has_f32(c), "msmd_sample_window: precise_last_steps needs a model created with precision 2");
+  }
+  if (ex && c.precision != 3 && c.precision != 1) {
+    k16 = ex->fp16_last_steps < 0 ? c.n_diff_steps : ex->fp16_last_steps;
+    MSMD_REQUIRE(k16 == 0 || has_fp16(c), "msmd_sample_window: fp16_last_steps needs a model created with precision 2");
+  }
+  if (k16 < k32) k16 = k32;
+
+  UpdateParams up{};
   up.dec = m->dec2; up.stat = m->stat; up.x = m->xbuf; up.z = z; up.traj = traj; up.steps = m->steps;
   up.alphas = m->alphas; up.alpha_bars = m->alpha_bars; up.sig_flex = m->sig_flex; up.sig_inflex = m->sig_inflex;
   up.scale0 = scale0; up.scale1 = scale1; up.flexibility = flexibility; up.seed = seed;
   up.NX = m->NX; up.E = m->E; up.T = m->T; up.L = c.n_motions; up.Lp = c.n_prev_motions; up.dm = c.motion_dim;
   up.nb = c.n_basis; up.ldd = m->ldd; up.cfg_independent = cfg_independent; up.target_noise = c.target_noise;
   up.thr = nullptr; up.tgt_dyn = nullptr; up.cum_static = nullptr; up.alpha_traj = nullptr; up.t_start = t_start;
+  up.overflow = k32 > 0 ? m->overflow : nullptr;
   bool use_dt = false;
   float dt_ratio = 0.f, dt_min = 0.f, dt_max = 0.f;
-  int k_precise = c.precision == 1 ? c.n_diff_steps : 0;   // steps with t <= k_precise run the fp32-grade path
-  if (ex && c.precision != 1) {
-    k_precise = ex->precise_last_steps < 0 ? c.n_diff_steps : ex->precise_last_steps;
-    MSMD_REQUIRE(k_precise == 0 || c.precision == 2,
-                 "msmd_sample_window: precise_last_steps needs a model created with precision 2");
-  }
   if (ex) {
     use_dt = ex->use_dynamic_threshold != 0;
     dt_ratio = ex->dt_ratio; dt_min = ex->dt_min; dt_max = ex->dt_max;
@@ -541,64 +682,81 @@ extern "C" int msmd_sample_window_ex(msmd_model* m, const float* x_T, const floa
     up.tgt_dyn = ex->target_dynamic; up.cum_static = ex->cumulative_static; up.alpha_traj = ex->alpha_traj;
     if (up.cum_static) MSMD_CHECK_CUDA(cudaMemsetAsync(up.cum_static, 0, n_el * 4, st));
   }
+  if ((rc = update_params_set(m->d_up, up, st))) return rc;
 
-  auto one_step = [&](cudaStream_t s, bool precise = false) -> int {
+  // path: 0 bf16, 1 fp32-grade, 2 fp16
+  auto one_step = [&](cudaStream_t s, int path) -> int {
     int r;
-    if ((r = precise ? run_forward_f32(m, m->xbuf, s) : run_forward(m, m->xbuf, s))) return r;
+    if ((r = forward_path(m, m->xbuf, path, s))) return r;
     if (use_dt && (r = threshold_launch(m->dec2, m->stat, m->thr, m->S, m->T, c.n_motions, c.n_prev_motions, c.motion_dim,
                                         c.n_basis, m->ldd, dt_ratio, dt_min, dt_max, s)))
       return r;
-    if ((r = update_launch(up, s))) return r;
+    if ((r = update_launch(m->d_up, m->NX, c.n_motions, c.motion_dim, s))) return r;
     return steps_advance(m->steps, m->S, s);
   };
 
-  // executed steps are t = t_start .. t_end; the last n_hi of them (t <= k_precise) run the fp32-grade path,
-  // eagerly: each is ~5x a bf16 step, so launch latency is hidden and a second graph buys nothing
-  const int t_end = t_start - n_steps + 1;
-  const int n_hi = k_precise >= t_start ? n_steps : (k_precise >= t_end ? k_precise - t_end + 1 : 0);
-  n_steps -= n_hi;
-  if (profiling_on() || n_steps < 3) {  // event timing cannot live inside a graph: plain launches
-    for (int i = 0; i < n_steps; ++i)
-      if ((rc = one_step(st))) return rc;
-  } else {
-    // first step eagerly (one-time function attributes, launch validation), the rest as graph replays
-    if ((rc = one_step(st))) return rc;
-    n_steps -= 1;
-    // capture ONE step (the step index lives in device memory) and replay it
-    cudaStream_t cs;
-    MSMD_CHECK_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
-    cudaGraph_t graph = nullptr;
-    cudaGraphExec_t exec = nullptr;
-    MSMD_CHECK_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
-    rc = one_step(cs);
-    cudaError_t ce = cudaStreamEndCapture(cs, &graph);
-    if (rc || ce != cudaSuccess) {
-      if (graph) cudaGraphDestroy(graph);
-      cudaStreamDestroy(cs);
-      if (!rc) { set_error("msmd_sample_window: graph capture failed: %s", cudaGetErrorString(ce)); rc = MSMD_ERR_CUDA; }
-      return rc;
+  // n consecutive steps of one 16-bit path: replays of ONE captured step (the step index lives in device memory, the
+  // update parameters in m->d_up).  The instantiated graph is kept in the handle: only the first call of a given
+  // (format, S, NX, E, thresholding) captures and instantiates; later calls just enqueue launches - no stream
+  // creation, instantiation or synchronisation (include/msmd_b200.h: "no hidden synchronisation after *_create").
+  auto run_16 = [&](int path, int n) -> int {
+    if (n <= 0) return MSMD_OK;
+    int r;
+    const int fmt = path == 2 ? 1 : 0;
+    if ((r = check_path(m, path, "msmd_sample_window"))) return r;
+    if (!m->window16[fmt] && (r = window_begin_16(m, fmt, st))) return r;
+    if (profiling_on() || n < 3) {  // event timing cannot live inside a graph: plain launches
+      for (int i = 0; i < n; ++i)
+        if ((r = one_step(st, path))) return r;
+      return MSMD_OK;
     }
-    ce = cudaGraphInstantiate(&exec, graph, 0);
-    if (ce != cudaSuccess) {
+    const msmd_model::GraphKey key(fmt, m->S, m->NX, m->E, use_dt ? 1 : 0, dt_ratio, dt_min, dt_max);
+    auto it = m->graphs.find(key);
+    if (it == m->graphs.end()) {
+      // first step eagerly (one-time function attributes, launch validation), then capture one step
+      if ((r = one_step(st, path))) return r;
+      n -= 1;
+      cudaGraph_t graph = nullptr;
+      cudaGraphExec_t exec = nullptr;
+      MSMD_CHECK_CUDA(cudaStreamBeginCapture(m->cap_stream, cudaStreamCaptureModeThreadLocal));
+      r = one_step(m->cap_stream, path);
+      cudaError_t ce = cudaStreamEndCapture(m->cap_stream, &graph);
+      if (r || ce != cudaSuccess) {
+        if (graph) cudaGraphDestroy(graph);
+        if (!r) { set_error("msmd_sample_window: graph capture failed: %s", cudaGetErrorString(ce)); r = MSMD_ERR_CUDA; }
+        return r;
+      }
+      ce = cudaGraphInstantiate(&exec, graph, 0);
       cudaGraphDestroy(graph);
-      cudaStreamDestroy(cs);
-      set_error("msmd_sample_window: cudaGraphInstantiate failed: %s", cudaGetErrorString(ce));
-      return MSMD_ERR_CUDA;
+      if (ce != cudaSuccess) {
+        set_error("msmd_sample_window: cudaGraphInstantiate failed: %s", cudaGetErrorString(ce));
+        return MSMD_ERR_CUDA;
+      }
+      it = m->graphs.emplace(key, exec).first;
     }
-    for (int i = 0; i < n_steps && ce == cudaSuccess; ++i) ce = cudaGraphLaunch(exec, st);
-    // the exec must outlive its launches: destroy after the stream has drained them
-    cudaError_t se = cudaStreamSynchronize(st);
-    cudaGraphExecDestroy(exec);
-    cudaGraphDestroy(graph);
-    cudaStreamDestroy(cs);
-    if (ce != cudaSuccess || se != cudaSuccess) {
-      set_error("msmd_sample_window: graph launch failed: %s", cudaGetErrorString(ce != cudaSuccess ? ce : se));
-      return MSMD_ERR_CUDA;
-    }
-  }
+    for (int i = 0; i < n; ++i) MSMD_CHECK_CUDA(cudaGraphLaunch(it->second, st));
+    return MSMD_OK;
+  };
+
+  // executed steps are t = t_start .. t_end
+  const int t_end = t_start - n_steps + 1;
+  auto count = [&](int hi, int lo) { hi = std::min(hi, t_start); lo = std::max(lo, t_end); return hi >= lo ? hi - lo + 1 : 0; };
+  const int n_main = count(c.n_diff_steps, k16 + 1), n_f16 = count(k16, k32 + 1), n_hi = count(k32, 1);
+  if ((rc = run_16(has_bf16(c) ? 0 : 2, n_main))) return rc;
+  if ((rc = run_16(2, n_f16))) return rc;
+  // the last n_hi steps (t <= k32) run the fp32-grade path eagerly: each is several bf16 steps long, so launch latency
+  // is hidden and a graph buys nothing
+  if (n_hi > 0 && (rc = check_path(m, 1, "msmd_sample_window"))) return rc;
   for (int i = 0; i < n_hi; ++i)
-    if ((rc = one_step(st, true))) return rc;
-  if (n_hi > 0 && (rc = check_overflow(m, st, "msmd_sample_window"))) return rc;
+    if ((rc = one_step(st, 1))) return rc;
+  if (n_hi > 0 && (rc = post_overflow(m, st))) return rc;
   MSMD_CHECK_CUDA(cudaMemcpyAsync(x_out, m->xbuf, n_el * 4, cudaMemcpyDeviceToDevice, st));
   return MSMD_OK;
+}
+
+// Synchronise the stream and report a pending fp32-grade overflow (tests / callers that want the error at the call site).
+extern "C" int msmd_check(msmd_model* m, void* stream) {
+  MSMD_REQUIRE(m, "msmd_check: null model");
+  MSMD_CHECK_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+  return poll_overflow(m, "msmd_check");
 }

@@ -22,6 +22,27 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+// 16-bit activation storage comes in two formats: bf16 (F16 = false) and fp16 (F16 = true, the sampler's
+// intermediate-precision steps).  Buffers are typed bf16* either way; these helpers do the (un)packing.
+template <bool F16>
+__device__ __forceinline__ uint32_t pack_h(float lo, float hi) {
+  if constexpr (F16) {
+    __half2 h = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&h);
+  } else {
+    return pack_bf16(lo, hi);
+  }
+}
+template <bool F16>
+__device__ __forceinline__ float2 unpack_h(uint32_t w) {
+  if constexpr (F16) return __half22float2(*reinterpret_cast<const __half2*>(&w));
+  else return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
+template <bool F16>
+__device__ __forceinline__ void store_h1(bf16* dst, float v) {
+  if constexpr (F16) *reinterpret_cast<__half*>(dst) = __float2half_rn(v);
+  else *dst = __float2bfloat16_rn(v);
+}
 __device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 
 // ------------------------------------------------------------------------------------------- small fp32 linear
@@ -70,6 +91,7 @@ int cast_rows_bf16(const float* src, int64_t lds, bf16* dst, int64_t ldd, int64_
   return MSMD_OK;
 }
 
+template <bool F16>
 __global__ void build_memory_kernel(const float* __restrict__ prev_audio, const float* __restrict__ audio,
                                     bf16* __restrict__ mem, int S, int Lp, int L, int d) {
   const int64_t n = (int64_t)S * (Lp + L) * d;
@@ -79,19 +101,22 @@ __global__ void build_memory_kernel(const float* __restrict__ prev_audio, const 
     const int tok = (int)(row % (Lp + L));
     const int64_t s = row / (Lp + L);
     const float v = tok < Lp ? prev_audio[(s * Lp + tok) * d + c] : audio[(s * L + tok - Lp) * d + c];
-    mem[i] = __float2bfloat16_rn(v);
+    store_h1<F16>(mem + i, v);
   }
 }
-int build_memory_bf16(const float* prev_audio, const float* audio, bf16* mem, int S, int Lp, int L, int d,
-                      cudaStream_t st) {
+int build_memory_h16(const float* prev_audio, const float* audio, bf16* mem, int S, int Lp, int L, int d, int fp16,
+                     cudaStream_t st) {
   const int64_t n = (int64_t)S * (Lp + L) * d;
-  build_memory_kernel<<<(int)std::min<int64_t>(cdiv(n, 256), kNumSMs * 16), 256, 0, st>>>(prev_audio, audio, mem, S, Lp, L, d);
+  const int grid = (int)std::min<int64_t>(cdiv(n, 256), kNumSMs * 16);
+  if (fp16) build_memory_kernel<true><<<grid, 256, 0, st>>>(prev_audio, audio, mem, S, Lp, L, d);
+  else build_memory_kernel<false><<<grid, 256, 0, st>>>(prev_audio, audio, mem, S, Lp, L, d);
   MSMD_CHECK_LAUNCH();
   return MSMD_OK;
 }
 
 // ------------------------------------------------------------------------------------------- embeddings
 // rows 0..Lp: person token (+ timestep embedding) and the projected previous-motion context
+template <bool F16>
 __global__ void embed_ctx_kernel(EmbedParams p) {
   griddep_launch();
   griddep_wait();
@@ -103,13 +128,14 @@ __global__ void embed_ctx_kernel(EmbedParams p) {
     float v = p.PE[i * p.d + c];
     v += (i == 0) ? (p.pp[(int64_t)s * p.d + c] + p.temb[(int64_t)t * p.d + c])
                   : p.pmproj[((int64_t)s * p.Lp + (i - 1)) * p.d + c];
-    p.out[((int64_t)s * T + i) * p.d + c] = __float2bfloat16_rn(v);
+    store_h1<F16>(p.out + ((int64_t)s * T + i) * p.d + c, v);
   }
 }
 // rows Lp+1..: feature_proj([x_t, indicator]) + PE, computed once per x row and written to its E sequences.
 // CTA = 25 frames x 512 features; the x rows sit in shared memory k-major ([k][28]) so one 128-bit broadcast
 // load feeds 4 frames' FMAs (the scalar-load version was LDS-bound at 65 us; this one is FMA-issue-bound).
 constexpr int kEmbedRows = 25, kEmbedPitch = 28;
+template <bool F16>
 __global__ void __launch_bounds__(256, 2) embed_x_kernel(EmbedParams p) {
   griddep_launch();
   griddep_wait();
@@ -172,7 +198,7 @@ __global__ void __launch_bounds__(256, 2) embed_x_kernel(EmbedParams p) {
           const float ind = inds[e * kEmbedPitch + r];
           const int s = e * p.NX + n;
           *reinterpret_cast<uint32_t*>(p.out + ((int64_t)s * T + 1 + p.Lp + l) * p.d + c) =
-              pack_bf16(fmaf(ind, wi.x, a0[r]), fmaf(ind, wi.y, a1[r]));
+              pack_h<F16>(fmaf(ind, wi.x, a0[r]), fmaf(ind, wi.y, a1[r]));
         }
       }
     }
@@ -180,10 +206,11 @@ __global__ void __launch_bounds__(256, 2) embed_x_kernel(EmbedParams p) {
 }
 int embed_launch(const EmbedParams& p, cudaStream_t st) {
   ProfileScope prof("embed", st);
-  MSMD_CHECK_CUDA(launch_pdl(embed_ctx_kernel, dim3(p.S * (p.Lp + 1)), dim3(128), 0, st, p));
+  MSMD_CHECK_CUDA(launch_pdl(p.fp16 ? embed_ctx_kernel<true> : embed_ctx_kernel<false>, dim3(p.S * (p.Lp + 1)), dim3(128), 0, st, p));
   MSMD_CHECK_LAUNCH();
   const int blocks = p.NX * ((p.L + kEmbedRows - 1) / kEmbedRows);
-  MSMD_CHECK_CUDA(launch_pdl(embed_x_kernel, dim3(blocks), dim3(256), (p.dm + 3) * kEmbedPitch * sizeof(float), st, p));
+  MSMD_CHECK_CUDA(launch_pdl(p.fp16 ? embed_x_kernel<true> : embed_x_kernel<false>, dim3(blocks), dim3(256),
+                             (p.dm + 3) * kEmbedPitch * sizeof(float), st, p));
   MSMD_CHECK_LAUNCH();
   return MSMD_OK;
 }
@@ -212,15 +239,23 @@ __device__ __forceinline__ void ln_row(float (&v)[D / 32], const float* __restri
     v[4 * i + 3] = (v[4 * i + 3] - mean) * rstd * gg.w + bb.w;
   }
 }
-__device__ __forceinline__ void store_bf16x4(bf16* dst, float a, float b, float c, float d) {
-  __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+template <bool F16>
+__device__ __forceinline__ void store_h4(bf16* dst, float a, float b, float c, float d) {
   uint2 u;
-  u.x = *reinterpret_cast<uint32_t*>(&lo);
-  u.y = *reinterpret_cast<uint32_t*>(&hi);
+  u.x = pack_h<F16>(a, b);
+  u.y = pack_h<F16>(c, d);
   *reinterpret_cast<uint2*>(dst) = u;
 }
+// 4 consecutive 16-bit values -> v[0..3] (ADD: accumulate)
+template <bool F16, bool ADD>
+__device__ __forceinline__ void load_h4(const bf16* src, float* v) {
+  const uint2 u = *reinterpret_cast<const uint2*>(src);
+  const float2 a = unpack_h<F16>(u.x), b = unpack_h<F16>(u.y);
+  if (ADD) { v[0] += a.x; v[1] += a.y; v[2] += b.x; v[3] += b.y; }
+  else { v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; }
+}
 
-template <int D>
+template <int D, bool F16>
 __global__ void __launch_bounds__(256) ln_kernel(LnParams p) {
   griddep_launch();
   griddep_wait();
@@ -232,58 +267,40 @@ __global__ void __launch_bounds__(256) ln_kernel(LnParams p) {
   float v[NV];
   const bf16* y = p.y + (int64_t)row * D;
 #pragma unroll
-  for (int i = 0; i < NV / 4; ++i) {
-    const uint2 u = *reinterpret_cast<const uint2*>(y + i * 128 + lane * 4);
-    v[4 * i + 0] = __uint_as_float(u.x << 16);
-    v[4 * i + 1] = __uint_as_float(u.x & 0xffff0000u);
-    v[4 * i + 2] = __uint_as_float(u.y << 16);
-    v[4 * i + 3] = __uint_as_float(u.y & 0xffff0000u);
-  }
+  for (int i = 0; i < NV / 4; ++i) load_h4<F16, false>(y + i * 128 + lane * 4, v + 4 * i);
   if (p.resid != nullptr) {  // x + sublayer(x): the residual add of the post-LN layer (model.py:874-878)
     const bf16* r = p.resid + (int64_t)row * D;
 #pragma unroll
-    for (int i = 0; i < NV / 4; ++i) {
-      const uint2 u = *reinterpret_cast<const uint2*>(r + i * 128 + lane * 4);
-      v[4 * i + 0] += __uint_as_float(u.x << 16);
-      v[4 * i + 1] += __uint_as_float(u.x & 0xffff0000u);
-      v[4 * i + 2] += __uint_as_float(u.y << 16);
-      v[4 * i + 3] += __uint_as_float(u.y & 0xffff0000u);
-    }
+    for (int i = 0; i < NV / 4; ++i) load_h4<F16, true>(r + i * 128 + lane * 4, v + 4 * i);
   }
   if (tok == 0 && p.skip_tok0) return;
   ln_row<D>(v, p.g1, p.b1, lane);
   if (tok == 0 && p.x0 != nullptr) {
 #pragma unroll
     for (int i = 0; i < NV / 4; ++i)
-      store_bf16x4(p.x0 + (int64_t)s * D + i * 128 + lane * 4, v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      store_h4<F16>(p.x0 + (int64_t)s * D + i * 128 + lane * 4, v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
     return;
   }
   if (p.add != nullptr && tok > 0) {
     // x1 is rounded to bf16 where the reference's next sub-layer reads it; keep the same rounding point
     const bf16* a = p.add + ((int64_t)s * (p.T - 1) + (tok - 1)) * D;
 #pragma unroll
-    for (int i = 0; i < NV / 4; ++i) {
-      const uint2 u = *reinterpret_cast<const uint2*>(a + i * 128 + lane * 4);
-      v[4 * i + 0] += __uint_as_float(u.x << 16);
-      v[4 * i + 1] += __uint_as_float(u.x & 0xffff0000u);
-      v[4 * i + 2] += __uint_as_float(u.y << 16);
-      v[4 * i + 3] += __uint_as_float(u.y & 0xffff0000u);
-    }
+    for (int i = 0; i < NV / 4; ++i) load_h4<F16, true>(a + i * 128 + lane * 4, v + 4 * i);
     ln_row<D>(v, p.g2, p.b2, lane);
   }
   bf16* o = p.out + (int64_t)row * D;
 #pragma unroll
-  for (int i = 0; i < NV / 4; ++i) store_bf16x4(o + i * 128 + lane * 4, v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  for (int i = 0; i < NV / 4; ++i) store_h4<F16>(o + i * 128 + lane * 4, v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
 }
 int ln_launch(const LnParams& p, cudaStream_t st) {
   MSMD_REQUIRE(p.d == 512, "ln: only d_model = 512 is instantiated (got %d)", p.d);
   ProfileScope prof(p.add ? "ln1_ln2" : "ln3", st);
-  MSMD_CHECK_CUDA(launch_pdl(ln_kernel<512>, dim3(cdiv(p.M, 8)), dim3(256), 0, st, p));
+  MSMD_CHECK_CUDA(launch_pdl(p.fp16 ? ln_kernel<512, true> : ln_kernel<512, false>, dim3(cdiv(p.M, 8)), dim3(256), 0, st, p));
   MSMD_CHECK_LAUNCH();
   return MSMD_OK;
 }
 
-template <int D>
+template <int D, bool F16>
 __global__ void __launch_bounds__(256) ln_row0_kernel(const bf16* __restrict__ y0, const bf16* __restrict__ resid0,
                                                       const float* __restrict__ g, const float* __restrict__ b,
                                                       bf16* __restrict__ out, bf16* __restrict__ out_c, int S, int T) {
@@ -296,31 +313,22 @@ __global__ void __launch_bounds__(256) ln_row0_kernel(const bf16* __restrict__ y
   float v[NV];
 #pragma unroll
   for (int i = 0; i < NV / 4; ++i) {
-    const uint2 uy = *reinterpret_cast<const uint2*>(y0 + (int64_t)s * D + i * 128 + lane * 4);
-    v[4 * i + 0] = __uint_as_float(uy.x << 16);
-    v[4 * i + 1] = __uint_as_float(uy.x & 0xffff0000u);
-    v[4 * i + 2] = __uint_as_float(uy.y << 16);
-    v[4 * i + 3] = __uint_as_float(uy.y & 0xffff0000u);
-    if (resid0 != nullptr) {
-      const uint2 u = *reinterpret_cast<const uint2*>(resid0 + (int64_t)s * D + i * 128 + lane * 4);
-      v[4 * i + 0] += __uint_as_float(u.x << 16);
-      v[4 * i + 1] += __uint_as_float(u.x & 0xffff0000u);
-      v[4 * i + 2] += __uint_as_float(u.y << 16);
-      v[4 * i + 3] += __uint_as_float(u.y & 0xffff0000u);
-    }
+    load_h4<F16, false>(y0 + (int64_t)s * D + i * 128 + lane * 4, v + 4 * i);
+    if (resid0 != nullptr) load_h4<F16, true>(resid0 + (int64_t)s * D + i * 128 + lane * 4, v + 4 * i);
   }
   ln_row<D>(v, g, b, lane);
 #pragma unroll
   for (int i = 0; i < NV / 4; ++i) {
-    if (out) store_bf16x4(out + (int64_t)s * T * D + i * 128 + lane * 4, v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-    if (out_c) store_bf16x4(out_c + (int64_t)s * D + i * 128 + lane * 4, v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    if (out) store_h4<F16>(out + (int64_t)s * T * D + i * 128 + lane * 4, v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    if (out_c) store_h4<F16>(out_c + (int64_t)s * D + i * 128 + lane * 4, v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
   }
 }
 int ln_row0_launch(const bf16* y0, const bf16* resid0, const float* g, const float* b, bf16* out, bf16* out_c, int S,
-                   int T, int d, cudaStream_t st) {
+                   int T, int d, int fp16, cudaStream_t st) {
   MSMD_REQUIRE(d == 512, "ln_row0: only d_model = 512 is instantiated");
   ProfileScope prof("ln_row0", st);
-  MSMD_CHECK_CUDA(launch_pdl(ln_row0_kernel<512>, dim3(cdiv(S, 8)), dim3(256), 0, st, y0, resid0, g, b, out, out_c, S, T));
+  MSMD_CHECK_CUDA(launch_pdl(fp16 ? ln_row0_kernel<512, true> : ln_row0_kernel<512, false>, dim3(cdiv(S, 8)), dim3(256), 0, st,
+                             y0, resid0, g, b, out, out_c, S, T));
   MSMD_CHECK_LAUNCH();
   return MSMD_OK;
 }
@@ -489,6 +497,7 @@ int self_attn_launch(const bf16* qkv, bf16* ctx, int S, int T, int H, cudaStream
 // owns 2 of the 64 head dims, so a key's V slice is one coalesced 128-byte warp load, prefetched 28 keys ahead.
 // HBM-bound: 2 x Tk x d x 2 B per sequence per layer.
 constexpr int kCaBatch = 28;
+template <bool F16>
 __global__ void __launch_bounds__(128, 3) cross_attn_row0_kernel(const bf16* __restrict__ q0, const bf16* __restrict__ kv,
                                                                  bf16* __restrict__ ctx0, int Tk, int H) {
   griddep_launch();
@@ -519,8 +528,9 @@ __global__ void __launch_bounds__(128, 3) cross_attn_row0_kernel(const bf16* __r
       const uint32_t ww[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        q[i * 8 + 2 * k] = __uint_as_float(ww[k] << 16);
-        q[i * 8 + 2 * k + 1] = __uint_as_float(ww[k] & 0xffff0000u);
+        const float2 f = unpack_h<F16>(ww[k]);
+        q[i * 8 + 2 * k] = f.x;
+        q[i * 8 + 2 * k + 1] = f.y;
       }
     }
   }
@@ -540,8 +550,9 @@ __global__ void __launch_bounds__(128, 3) cross_attn_row0_kernel(const bf16* __r
         const uint32_t ww[4] = {kr[i].x, kr[i].y, kr[i].z, kr[i].w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          acc = fmaf(q[i * 8 + 2 * k], __uint_as_float(ww[k] << 16), acc);
-          acc = fmaf(q[i * 8 + 2 * k + 1], __uint_as_float(ww[k] & 0xffff0000u), acc);
+          const float2 f = unpack_h<F16>(ww[k]);
+          acc = fmaf(q[i * 8 + 2 * k], f.x, acc);
+          acc = fmaf(q[i * 8 + 2 * k + 1], f.y, acc);
         }
       }
       dot = acc * 0.125f;
@@ -559,8 +570,9 @@ __global__ void __launch_bounds__(128, 3) cross_attn_row0_kernel(const bf16* __r
     for (int u = 0; u < kCaBatch; ++u) {
       const int j = b * kCaBatch + u;            // compile-time after unrolling: sc[] stays in registers
       const float p = __shfl_sync(0xffffffffu, sc[j >> 5], j & 31);
-      oa = fmaf(p, __uint_as_float(src[u] << 16), oa);
-      ob = fmaf(p, __uint_as_float(src[u] & 0xffff0000u), ob);
+      const float2 f = unpack_h<F16>(src[u]);
+      oa = fmaf(p, f.x, oa);
+      ob = fmaf(p, f.y, ob);
     }
   };
   load_v(1, vb[1]); consume(0, vb[0]);
@@ -568,13 +580,14 @@ __global__ void __launch_bounds__(128, 3) cross_attn_row0_kernel(const bf16* __r
   load_v(3, vb[1]); consume(2, vb[0]);
   consume(3, vb[1]);
   const float inv = 1.0f / l;
-  *reinterpret_cast<uint32_t*>(ctx0 + (int64_t)s * d + h * 64 + 2 * lane) = pack_bf16(oa * inv, ob * inv);
+  *reinterpret_cast<uint32_t*>(ctx0 + (int64_t)s * d + h * 64 + 2 * lane) = pack_h<F16>(oa * inv, ob * inv);
 }
-int cross_attn_row0_launch(const bf16* q0, const bf16* kv, bf16* ctx0, int S, int Tk, int H, cudaStream_t st) {
+int cross_attn_row0_launch(const bf16* q0, const bf16* kv, bf16* ctx0, int S, int Tk, int H, int fp16, cudaStream_t st) {
   MSMD_REQUIRE(Tk <= 4 * kCaBatch && H == 8, "cross_attn_row0: built for 8 heads x 64 and <= %d memory tokens (got %d, %d)",
                4 * kCaBatch, H, Tk);
   ProfileScope prof("cross_attn_row0", st);
-  MSMD_CHECK_CUDA(launch_pdl(cross_attn_row0_kernel, dim3(S * H / 4), dim3(128), 0, st, q0, kv, ctx0, Tk, H));
+  MSMD_CHECK_CUDA(launch_pdl(fp16 ? cross_attn_row0_kernel<true> : cross_attn_row0_kernel<false>, dim3(S * H / 4), dim3(128), 0, st,
+                             q0, kv, ctx0, Tk, H));
   MSMD_CHECK_LAUNCH();
   return MSMD_OK;
 }
@@ -608,9 +621,13 @@ __device__ __forceinline__ void split_target(const float* dec, const float* stat
   sta = v;
 }
 
-__global__ void __launch_bounds__(256) update_kernel(UpdateParams p) {
+// The parameter block lives in device memory (msmd_model::d_up, rewritten by every msmd_sample_window call with a
+// stream-ordered copy): the captured step graph never bakes a caller pointer or scalar, so one instantiated graph
+// serves every window / call of the same shape.
+__global__ void __launch_bounds__(256) update_kernel(const UpdateParams* __restrict__ pp) {
   griddep_launch();
   griddep_wait();
+  const UpdateParams p = *pp;
   const int64_t n_el = (int64_t)p.NX * p.L * p.dm;
   const int t = p.steps[0];
   // model.py:383-386, :421-428 - 0-dim fp32 tensor arithmetic, same operation order
@@ -652,7 +669,10 @@ __global__ void __launch_bounds__(256) update_kernel(UpdateParams p) {
     float zt = 0.f;
     if (t > 1) zt = p.z ? p.z[(int64_t)t * n_el + i] : philox_normal(p.seed, (uint32_t)t, (uint32_t)i);
     const float xo = p.x[i];
-    const float xn = p.target_noise ? (c0 * (xo - c1 * tgt) + sigma * zt) : (c0 * xo + c1 * tgt + sigma * zt);
+    float xn = p.target_noise ? (c0 * (xo - c1 * tgt) + sigma * zt) : (c0 * xo + c1 * tgt + sigma * zt);
+    // fp32-grade steps: an activation left the fp16 range of the operand split -> poison the state instead of
+    // returning a silently wrong sample (the host reports it at the next call, without synchronising this one)
+    if (p.overflow != nullptr && *p.overflow != 0) xn = __int_as_float(0x7fc00000);
     p.x[i] = xn;
     if (p.traj) p.traj[(int64_t)(t - 1) * n_el + i] = xn;
     if (p.tgt_dyn) p.tgt_dyn[i] = td;
@@ -732,10 +752,16 @@ int threshold_launch(const float* dec, const float* stat, float* thr, int S, int
   return MSMD_OK;
 }
 
-int update_launch(const UpdateParams& p, cudaStream_t st) {
-  const int64_t n = (int64_t)p.NX * p.L * p.dm;
+__global__ void update_params_set_kernel(UpdateParams* dst, const UpdateParams src) { *dst = src; }
+int update_params_set(UpdateParams* d_dst, const UpdateParams& p, cudaStream_t st) {
+  update_params_set_kernel<<<1, 1, 0, st>>>(d_dst, p);   // by-value kernel argument: stream-ordered, no host staging buffer to keep alive
+  MSMD_CHECK_LAUNCH();
+  return MSMD_OK;
+}
+int update_launch(const UpdateParams* d_p, int NX, int L, int dm, cudaStream_t st) {
+  const int64_t n = (int64_t)NX * L * dm;
   ProfileScope prof("update", st);
-  MSMD_CHECK_CUDA(launch_pdl(update_kernel, dim3((int)std::min<int64_t>(cdiv(n, 256), kNumSMs * 8)), dim3(256), 0, st, p));
+  MSMD_CHECK_CUDA(launch_pdl(update_kernel, dim3((int)std::min<int64_t>(cdiv(n, 256), kNumSMs * 8)), dim3(256), 0, st, d_p));
   MSMD_CHECK_LAUNCH();
   return MSMD_OK;
 }
@@ -779,6 +805,33 @@ int mix_static_launch(const float* dec, const float* stat, float* out, int S, in
                       cudaStream_t st) {
   const int64_t n = (int64_t)S * (T - 1) * dm;
   mix_static_kernel<<<(int)std::min<int64_t>(cdiv(n, 256), kNumSMs * 8), 256, 0, st>>>(dec, stat, out, S, T, dm, nb, ldd);
+  MSMD_CHECK_LAUNCH();
+  return MSMD_OK;
+}
+
+
+// keep_separate=True outputs of DenoisingNetwork_MSMD.forward (model.py:964-983): the dynamic features, the raw
+// static-basis outputs tiled over the Lp+L rows, and the alphas - no mixing.
+__global__ void split_parts_kernel(const float* __restrict__ dec, const float* __restrict__ stat, float* __restrict__ dyn,
+                                   float* __restrict__ sta, float* __restrict__ alphas, int S, int T, int dm, int nb, int ldd) {
+  const int64_t rows = (int64_t)S * (T - 1);
+  const int per_row = dm + nb * dm + nb;
+  const int64_t n = rows * per_row;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / per_row;
+    const int k = (int)(i % per_row);
+    const int s = (int)(r / (T - 1)), tok = (int)(r % (T - 1));
+    const float* row = dec + ((int64_t)s * T + 1 + tok) * ldd;
+    if (k < dm) dyn[r * dm + k] = row[k];
+    else if (k < dm + nb * dm) sta[r * nb * dm + (k - dm)] = stat[(int64_t)s * nb * dm + (k - dm)];
+    else alphas[r * nb + (k - dm - nb * dm)] = row[dm + (k - dm - nb * dm)];
+  }
+}
+int split_parts_launch(const float* dec, const float* stat, float* dyn, float* sta, float* alphas, int S, int T, int dm,
+                       int nb, int ldd, cudaStream_t st) {
+  const int64_t n = (int64_t)S * (T - 1) * (dm + nb * dm + nb);
+  split_parts_kernel<<<(int)std::min<int64_t>(cdiv(n, 256), kNumSMs * 8), 256, 0, st>>>(dec, stat, dyn, sta, alphas, S, T, dm,
+                                                                                        nb, ldd);
   MSMD_CHECK_LAUNCH();
   return MSMD_OK;
 }

@@ -14,8 +14,11 @@ int linear_simt(const float* x, int64_t ldx, const float* W, int64_t ldw, const 
 // fp32 -> bf16 cast of a [rows, cols] block into a strided destination
 int cast_rows_bf16(const float* src, int64_t lds, bf16* dst, int64_t ldd, int64_t rows, int cols, cudaStream_t st);
 
-// memory = cat(prev_audio [S,Lp,d], audio [S,L,d]) -> bf16 [S, Lp+L, d]
-int build_memory_bf16(const float* prev_audio, const float* audio, bf16* mem, int S, int Lp, int L, int d, cudaStream_t st);
+// 16-bit activation buffers are typed bf16* whatever their storage format; `fp16` != 0 selects IEEE half storage
+// (the sampler's intermediate-precision steps), 0 bfloat16.
+// memory = cat(prev_audio [S,Lp,d], audio [S,L,d]) -> 16-bit [S, Lp+L, d]
+int build_memory_h16(const float* prev_audio, const float* audio, bf16* mem, int S, int Lp, int L, int d, int fp16,
+                     cudaStream_t st);
 
 struct EmbedParams {
   // rows 0..Lp of every sequence (step-dependent only through the timestep embedding)
@@ -31,6 +34,7 @@ struct EmbedParams {
   const float* bf;        // [d]
   bf16* out;              // [S, 1+Lp+L, d]
   int S, NX, E, Lp, L, d, dm;
+  int fp16;               // storage format of `out`
 };
 int embed_launch(const EmbedParams& p, cudaStream_t st);
 
@@ -46,17 +50,18 @@ struct LnParams {
   bf16* x0;                 // [S, d] or null
   int skip_tok0;            // do not write token-0 rows at all (they are produced by the person-token stream)
   int M, T, d;
+  int fp16;                 // storage format of y / resid / add / out / x0
 };
 int ln_launch(const LnParams& p, cudaStream_t st);
 // row-0 finish: LayerNorm(y0 [S,d]; g,b) -> out[s*T + 0]
 // LayerNorm(y0 + resid0) of the S person-token rows -> out[s*T + 0] (if out) and compact out_c[s] (if out_c)
 int ln_row0_launch(const bf16* y0, const bf16* resid0, const float* g, const float* b, bf16* out, bf16* out_c, int S,
-                   int T, int d, cudaStream_t st);
+                   int T, int d, int fp16, cudaStream_t st);
 
 // self-attention over T <= 112 tokens, head dim 64: qkv [S*T, 3*d] bf16 (q|k|v) -> ctx [S*T, d] bf16
 int self_attn_launch(const bf16* qkv, bf16* ctx, int S, int T, int H, cudaStream_t st);
 // row-0 cross attention: q0 [S,d]; kv [S*Tk, 2d] (k|v) -> ctx0 [S,d]
-int cross_attn_row0_launch(const bf16* q0, const bf16* kv, bf16* ctx0, int S, int Tk, int H, cudaStream_t st);
+int cross_attn_row0_launch(const bf16* q0, const bf16* kv, bf16* ctx0, int S, int Tk, int H, int fp16, cudaStream_t st);
 
 
 struct UpdateParams {
@@ -78,19 +83,26 @@ struct UpdateParams {
   float* cum_static;      // [NX, L, dm] += c1 * CFG-combined static part, or null
   float* alpha_traj;      // [n_steps, NX, L, nb] CFG-combined alphas per executed step (index t_start - t), or null
   int t_start;
+  const int* overflow;    // fp32-grade steps: device flag raised by the operand split; non-zero poisons x with NaN
 };
 // per-sequence threshold s = clamp(quantile(|x0_hat[:, -L:]|, ratio), lo, hi) -> thr[S] (torch.quantile 'linear')
 int threshold_launch(const float* dec, const float* stat, float* thr, int S, int T, int L, int Lp, int dm, int nb, int ldd,
                      float ratio, float lo, float hi, cudaStream_t st);
-int update_launch(const UpdateParams& p, cudaStream_t st);
+// the parameter block is read from DEVICE memory (d_p), written by update_params_set in stream order
+int update_params_set(UpdateParams* d_dst, const UpdateParams& p, cudaStream_t st);
+int update_launch(const UpdateParams* d_p, int NX, int L, int dm, cudaStream_t st);
 int steps_set(int* steps, int S, int value, cudaStream_t st);
 int steps_advance(int* steps, int S, cudaStream_t st);
 
 // out[S, T-1... ] : x̂0 per sequence (module-level parity): dyn + static mix for ALL Lp+L rows -> [S, T-1, dm]
 int mix_static_launch(const float* dec, const float* stat, float* out, int S, int T, int dm, int nb, int ldd, cudaStream_t st);
 
+// keep_separate outputs (model.py:972-973): dyn [S,T-1,dm], sta [S,T-1,nb,dm] (tiled), alphas [S,T-1,nb]
+int split_parts_launch(const float* dec, const float* stat, float* dyn, float* sta, float* alphas, int S, int T, int dm,
+                       int nb, int ldd, cudaStream_t st);
+
 // tcgen05 self-attention (attn_tc.cu): same contract as self_attn_launch
-int self_attn_tc_launch(const bf16* qkv, bf16* ctx, int S, int T, int H, cudaStream_t st);
+int self_attn_tc_launch(const bf16* qkv, bf16* ctx, int S, int T, int H, int fp16, cudaStream_t st);
 
 // ---- fp32-grade variants (denoiser_f32.cu) ----
 int embed_f32_launch(const EmbedParams& p, float* out, cudaStream_t st);

@@ -87,7 +87,7 @@ static int launch_cfg2(const GemmDesc& d, cudaStream_t st) {
     const int wb = (d.batch > 1 && d.wz_mod != 0) ? (d.wz_mod > 0 ? d.wz_mod : d.batch) : 1;
     if ((rc = make_tmap_23(&p.b_map, d.W, in_dt, esz, d.K, d.N, d.ldw, wb, d.sW, Cfg::BK, Cfg::B_ROWS))) return rc;
   }
-  if (MODE != 0) {
+  if (Cfg::NSPLIT == 2) {
     MSMD_REQUIRE(d.A_lo && d.W_lo, "gemm: the three-pass modes need the lo operands");
     MSMD_REQUIRE(d.batch <= 1, "gemm: batched three-pass GEMMs are not implemented");
     if ((rc = make_tmap_23(&p.a_lo_map, d.A_lo, in_dt, esz, d.K, d.M, d.lda, 1, 0, Cfg::BK, Cfg::BM))) return rc;
@@ -95,11 +95,12 @@ static int launch_cfg2(const GemmDesc& d, cudaStream_t st) {
   }
   using OutT = typename Cfg::OutT;
   using AuxT = typename Cfg::AuxT;
-  const auto out_dt = sizeof(OutT) == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  const auto dt16 = MODE == 3 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const auto out_dt = sizeof(OutT) == 2 ? dt16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
   if ((rc = make_tmap_23(&p.out_map, d.out, out_dt, sizeof(OutT), d.N, d.M, d.ldo, d.batch, d.sO, Cfg::OUT_COLS, 32)))
     return rc;
   if (Cfg::HAS_AUX) {
-    const auto aux_dt = sizeof(AuxT) == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    const auto aux_dt = sizeof(AuxT) == 2 ? dt16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
     if ((rc = make_tmap_23(&p.aux_map, d.aux, aux_dt, sizeof(AuxT), d.N, d.M, d.ld_aux, d.batch, d.sAux,
                            Cfg::AUX_COLS, 32)))
       return rc;
@@ -131,7 +132,7 @@ static int launch_cfg2(const GemmDesc& d, cudaStream_t st) {
     MSMD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  ProfileScope prof(MODE == 0 ? "gemm_bf16" : (MODE == 1 ? "gemm_tf32x3" : "gemm_fp16x3"), st);
+  ProfileScope prof(MODE == 0 ? "gemm_bf16" : (MODE == 1 ? "gemm_tf32x3" : (MODE == 2 ? "gemm_fp16x3" : "gemm_fp16")), st);
   char shape_name[64];
   snprintf(shape_name, sizeof(shape_name), "gemm_%dx%dx%d%s", d.M, d.N, d.K, Cfg::CTA2 ? "_pair" : "");
   ProfileScope prof2(profiling_on() ? strdup(shape_name) : "", st);
@@ -188,45 +189,55 @@ static int launch_cfg(const GemmDesc& d, cudaStream_t st) {
   return d.act ? launch_cfg2<Cfg, MODE, true>(d, st) : launch_cfg2<Cfg, MODE, false>(d, st);
 }
 
+// single-pass 16-bit GEMMs: MODE 0 (bf16 storage) and MODE 3 (fp16 storage) share every tile configuration
+template <int MODE, class H>
+static int dispatch16(const GemmDesc& d, cudaStream_t st) {
+  const bool aux = d.aux != nullptr;
+  // narrow outputs (N <= 128) use the 128-wide tile so small problems still spread over SMs
+  const bool narrow = d.N <= 128;
+  static const int cta2_mode = [] { const char* e = getenv("MSMD_GEMM_CTA2"); return e ? atoi(e) : 1; }();  // 0 = never use CTA pairs
+  const bool cta2_env = cta2_mode != 0;
+  // measured on B200 (tools/pair_probe.py, M = 21312): the single-CTA 128x256 tile needs 96 B/clk of operands per SM
+  // at MMA peak and the L2->SM path delivers ~60, so its main loop runs at ~1.3 PFLOP/s; the pair (64 B/clk) is
+  // MMA-bound.  Pair vs single: 1536x512 31.8/33.5 us, 2048x512+GELU 50.0/53.2, 512x2048 41.4/46.1, 512x512 tie.
+  const bool pair = d.cta2 == 1 || (d.cta2 < 0 && cta2_env && !aux && !d.out_f32 && d.batch <= 1 && d.N >= 256 &&
+                                    d.M >= 2048);
+  const bool epi8 = d.gelu_heavy != 0;
+  if (pair) {
+    if (epi8) return launch_cfg<GemmCfg<MODE, 256, 8, false, H, H, true>, MODE>(d, st);
+    return launch_cfg<GemmCfg<MODE, 256, 4, false, H, H, true>, MODE>(d, st);
+  }
+  // a handful of rows (the person-token projections, M = sequences): 64-wide tiles spread the N dimension over
+  // 4x more SMs, and the whole K extent of a tile fits the 6-stage ring, so one TMA latency covers it
+  if (!aux && !d.out_f32 && d.batch <= 1 && d.M <= 512 && d.N >= 256)
+    return launch_cfg<GemmCfg<MODE, 64, 4, false, H, H>, MODE>(d, st);
+  if (!aux) {
+    if (d.out_f32) {
+      return narrow ? launch_cfg<GemmCfg<MODE, 128, 4, false, float, float>, MODE>(d, st)
+                    : launch_cfg<GemmCfg<MODE, 256, 4, false, float, float>, MODE>(d, st);
+    }
+    if (epi8 && !narrow) return launch_cfg<GemmCfg<MODE, 256, 8, false, H, H>, MODE>(d, st);
+    return narrow ? launch_cfg<GemmCfg<MODE, 128, 4, false, H, H>, MODE>(d, st)
+                  : launch_cfg<GemmCfg<MODE, 256, 4, false, H, H>, MODE>(d, st);
+  }
+  if constexpr (MODE == 0) {
+    if (d.out_f32 && !d.aux_f32) return launch_cfg<GemmCfg<0, 256, 4, true, float, H>, 0>(d, st);
+    if (d.out_f32 && d.aux_f32) return launch_cfg<GemmCfg<0, 256, 4, true, float, float>, 0>(d, st);
+    if (!d.out_f32 && !d.aux_f32) return launch_cfg<GemmCfg<0, 256, 4, true, H, H>, 0>(d, st);
+    set_error("gemm: bf16 output with fp32 aux is not instantiated");
+    return MSMD_ERR_UNSUPPORTED;
+  } else {
+    set_error("gemm: the one-pass fp16 mode has no residual (aux) epilogue");
+    return MSMD_ERR_UNSUPPORTED;
+  }
+}
+
 int gemm_tc_launch(const GemmDesc& d, cudaStream_t st) {
   MSMD_REQUIRE(d.M > 0 && d.N > 0 && d.K > 0, "gemm: empty problem %dx%dx%d", d.M, d.N, d.K);
   MSMD_REQUIRE(d.A && d.W && d.out, "gemm: null operand");
-  using bf = __nv_bfloat16;
   const bool aux = d.aux != nullptr;
-  if (d.mode == 0) {
-    // narrow outputs (N <= 128) use the 128-wide tile so small problems still spread over SMs
-    const bool narrow = d.N <= 128;
-    static const int cta2_mode = [] { const char* e = getenv("MSMD_GEMM_CTA2"); return e ? atoi(e) : 1; }();  // 0 = never use CTA pairs
-    const bool cta2_env = cta2_mode != 0;
-    // measured on B200 (tools/pair_probe.py, M = 21312): the single-CTA 128x256 tile needs 96 B/clk of operands per SM
-    // at MMA peak and the L2->SM path delivers ~60, so its main loop runs at ~1.3 PFLOP/s; the pair (64 B/clk) is
-    // MMA-bound.  Pair vs single: 1536x512 31.8/33.5 us, 2048x512+GELU 50.0/53.2, 512x2048 41.4/46.1, 512x512 tie.
-    const bool pair = d.cta2 == 1 || (d.cta2 < 0 && cta2_env && !aux && !d.out_f32 && d.batch <= 1 && d.N >= 256 &&
-                                      d.M >= 2048);
-    const bool epi8 = d.gelu_heavy != 0;
-    if (pair) {
-      if (epi8) return launch_cfg<GemmCfg<0, 256, 8, false, bf, bf, true>, 0>(d, st);
-      return launch_cfg<GemmCfg<0, 256, 4, false, bf, bf, true>, 0>(d, st);
-    }
-    // a handful of rows (the person-token projections, M = sequences): 64-wide tiles spread the N dimension over
-    // 4x more SMs, and the whole K extent of a tile fits the 6-stage ring, so one TMA latency covers it
-    if (!aux && !d.out_f32 && d.batch <= 1 && d.M <= 512 && d.N >= 256)
-      return launch_cfg<GemmCfg<0, 64, 4, false, bf, bf>, 0>(d, st);
-    if (!aux) {
-      if (d.out_f32) {
-        return narrow ? launch_cfg<GemmCfg<0, 128, 4, false, float, float>, 0>(d, st)
-                      : launch_cfg<GemmCfg<0, 256, 4, false, float, float>, 0>(d, st);
-      }
-      if (epi8 && !narrow) return launch_cfg<GemmCfg<0, 256, 8, false, bf, bf>, 0>(d, st);
-      return narrow ? launch_cfg<GemmCfg<0, 128, 4, false, bf, bf>, 0>(d, st)
-                    : launch_cfg<GemmCfg<0, 256, 4, false, bf, bf>, 0>(d, st);
-    }
-    if (d.out_f32 && !d.aux_f32) return launch_cfg<GemmCfg<0, 256, 4, true, float, bf>, 0>(d, st);
-    if (d.out_f32 && d.aux_f32) return launch_cfg<GemmCfg<0, 256, 4, true, float, float>, 0>(d, st);
-    if (!d.out_f32 && !d.aux_f32) return launch_cfg<GemmCfg<0, 256, 4, true, bf, bf>, 0>(d, st);
-    set_error("gemm: bf16 output with fp32 aux is not instantiated");
-    return MSMD_ERR_UNSUPPORTED;
-  }
+  if (d.mode == 0) return dispatch16<0, __nv_bfloat16>(d, st);
+  if (d.mode == 3) return dispatch16<3, __half>(d, st);
   MSMD_REQUIRE(d.mode == 1 || d.mode == 2, "gemm: unknown mode %d", d.mode);
   MSMD_REQUIRE(d.out_f32 && (!aux || d.aux_f32), "gemm: the three-pass modes are fp32 out");
   if (d.mode == 2) {

@@ -13,6 +13,8 @@
 //         msmd_split_f16); three kind::f16 MMAs per k-step, the cross terms rescaled in the epilogue.  Half the MMA
 //         instructions and operand bytes of MODE 1 (a K=8 tf32 MMA moves as many bytes as a K=16 fp16 one), but
 //         |x| must stay below the fp16 range (65504).
+// MODE 3: fp16 operands, one pass (kind::f16, fp16 in / fp16 out): the tensor-core cost of MODE 0 with 11 mantissa
+//         bits instead of 8 - the sampler's intermediate-precision steps (x0_hat error 8e-4 instead of 6.5e-3).
 #pragma once
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -54,7 +56,7 @@ struct GemmCfg {
   static constexpr int B_ROWS = CTA2 ? BN / 2 : BN;     // W rows this CTA stages per k-block
   static constexpr int A_BYTES = BM * 128, B_BYTES = B_ROWS * 128;
   static constexpr int UMMA_M = CTA2 ? 256 : 128;
-  static constexpr int NSPLIT = MODE == 0 ? 1 : 2;
+  static constexpr int NSPLIT = (MODE == 0 || MODE == 3) ? 1 : 2;
   static constexpr int STAGE_BYTES = NSPLIT * (A_BYTES + B_BYTES);
   static constexpr int OUT_COLS = 128 / (int)sizeof(OutT);
   static constexpr int AUX_COLS = 128 / (int)sizeof(AuxT);
@@ -111,7 +113,26 @@ __device__ __forceinline__ float gelu_tanh3(float x) {
 template <int MODE>
 __device__ __forceinline__ float gelu_erf(float x) {
   if constexpr (MODE == 0) return gelu_tanh3(x);
+  else if constexpr (MODE == 3) return 0.5f * x * (1.0f + erf_fast(x * 0.70710678118654752f));   // 1.5e-7: below fp16 rounding
   else return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+}
+template <class T> struct is_half_t { static constexpr bool value = false; };
+template <> struct is_half_t<__half> { static constexpr bool value = true; };
+// two floats -> one packed 16-bit pair in the storage format of T (bf16 or fp16)
+template <class T>
+__device__ __forceinline__ uint32_t pack16x2(float a, float b) {
+  if constexpr (is_half_t<T>::value) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  } else {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+}
+template <class T>
+__device__ __forceinline__ float2 unpack16x2(uint32_t w) {
+  if constexpr (is_half_t<T>::value) return __half22float2(*reinterpret_cast<const __half2*>(&w));
+  else return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
 }
 
 // Per-role timeline of the first 16 tiles (clock64 stamps), compiled in only with -DMSMD_GEMM_TRACE (tools/pair_probe.py)
@@ -154,7 +175,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_tc_kernel(const __grid_c
     prefetch_tmap(&p.a_map);
     prefetch_tmap(&p.b_map);
     prefetch_tmap(&p.out_map);
-    if (MODE != 0) { prefetch_tmap(&p.a_lo_map); prefetch_tmap(&p.b_lo_map); }
+    if (Cfg::NSPLIT == 2) { prefetch_tmap(&p.a_lo_map); prefetch_tmap(&p.b_lo_map); }
     if (Cfg::HAS_AUX) prefetch_tmap(&p.aux_map);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], Cfg::EPI_WARPS * (Cfg::CTA2 ? 2 : 1)); }
@@ -200,7 +221,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_tc_kernel(const __grid_c
             if (cta_rank == 0) mbar_expect_tx(&full_bar[s], 2 * Cfg::STAGE_BYTES);  // both CTAs' boxes land here
             tma_load_2d_2sm(sa, &p.a_map, &full_bar[s], kb * BK, m0);
             tma_load_2d_2sm(sb, &p.b_map, &full_bar[s], kb * BK, n0 + cta_rank * Cfg::B_ROWS);
-            if (MODE != 0) {
+            if (Cfg::NSPLIT == 2) {
               tma_load_2d_2sm(sa + Cfg::A_BYTES, &p.a_lo_map, &full_bar[s], kb * BK, m0);
               tma_load_2d_2sm(sb + Cfg::B_BYTES, &p.b_lo_map, &full_bar[s], kb * BK, n0 + cta_rank * Cfg::B_ROWS);
             }
@@ -213,7 +234,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_tc_kernel(const __grid_c
             mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
             tma_load_2d(sa, &p.a_map, &full_bar[s], kb * BK, m0);
             tma_load_2d(sb, &p.b_map, &full_bar[s], kb * BK, n0);
-            if (MODE != 0) {
+            if (Cfg::NSPLIT == 2) {
               tma_load_2d(sa + Cfg::A_BYTES, &p.a_lo_map, &full_bar[s], kb * BK, m0);
               tma_load_2d(sb + Cfg::B_BYTES, &p.b_lo_map, &full_bar[s], kb * BK, n0);
             }
@@ -251,7 +272,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_tc_kernel(const __grid_c
 #pragma unroll
           for (int k = 0; k < BK / Cfg::UK; ++k) {
             const uint32_t acc = (kb | k) != 0;
-            if constexpr (MODE == 0) {
+            if constexpr (Cfg::NSPLIT == 1) {
               if constexpr (Cfg::CTA2) umma_2sm(d_tmem, desc_advance(da, k * 32), desc_advance(db, k * 32), idesc, acc);
               else umma<0>(d_tmem, desc_advance(da, k * 32), desc_advance(db, k * 32), idesc, acc);
             } else {
@@ -356,7 +377,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_tc_kernel(const __grid_c
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + a * Cfg::ACC_COLS + csplit * CPW;
       const float* sbw = sb + csplit * CPW;
 
-      auto process = [&](uint32_t (&raw)[32], uint32_t (&raw2)[MODE != 0 ? 32 : 1], int c) {
+      auto process = [&](uint32_t (&raw)[32], uint32_t (&raw2)[Cfg::NSPLIT == 2 ? 32 : 1], int c) {
         const uint8_t* aux_buf = nullptr;
         int aux_off = 0;
         if constexpr (Cfg::HAS_AUX) {
@@ -403,8 +424,9 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_tc_kernel(const __grid_c
               const uint32_t w[4] = {r4.x, r4.y, r4.z, r4.w};
 #pragma unroll
               for (int u = 0; u < 4; ++u) {
-                v[8 * j + 2 * u + 0] += __uint_as_float(w[u] << 16);
-                v[8 * j + 2 * u + 1] += __uint_as_float(w[u] & 0xffff0000u);
+                const float2 f2 = unpack16x2<AuxT>(w[u]);
+                v[8 * j + 2 * u + 0] += f2.x;
+                v[8 * j + 2 * u + 1] += f2.y;
               }
             }
           }
@@ -428,10 +450,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_tc_kernel(const __grid_c
           for (int j = 0; j < 4; ++j) {
             uint32_t w[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              __nv_bfloat162 h = __floats2bfloat162_rn(v[8 * j + 2 * u], v[8 * j + 2 * u + 1]);
-              w[u] = *reinterpret_cast<uint32_t*>(&h);
-            }
+            for (int u = 0; u < 4; ++u) w[u] = pack16x2<OutT>(v[8 * j + 2 * u], v[8 * j + 2 * u + 1]);
             *reinterpret_cast<uint4*>(orow + (((o_off + j) ^ swz) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
           }
         }
@@ -457,7 +476,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_tc_kernel(const __grid_c
           else mbar_arrive(&tempty_bar[a]);
         }
       };
-      if constexpr (MODE != 0) {
+      if constexpr (Cfg::NSPLIT == 2) {
         // software-pipelined TMEM reads: chunk c+1 is in flight while chunk c is processed
         uint32_t rA[32], rB[32], rA2[32], rB2[32];
         tmem_ld32(t_addr, rA);
@@ -526,7 +545,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_tc_kernel(const __grid_c
 // ---------------------------------------------------------------------------------------------
 // Host-side description of one GEMM call.  Element strides; row-major [rows, K] operands.
 struct GemmDesc {
-  int mode = 0;                 // 0 bf16, 1 tf32x3, 2 fp16x3 (A/W hi and lo are __half, x = hi + 2^-11 lo)
+  int mode = 0;                 // 0 bf16, 1 tf32x3, 2 fp16x3 (A/W hi and lo are __half, x = hi + 2^-11 lo), 3 fp16 one pass
   const void* A = nullptr;      // [M,K] bf16 (mode 0) / fp32 hi (mode 1)
   const void* A_lo = nullptr;   // mode 1
   const void* W = nullptr;      // [N,K]

@@ -17,7 +17,8 @@ using namespace msmd;
 struct msmd_style {
   int device = 0, d_in = 67, d = 512, d_style = 256, cin_pad = 72, max_clips = 0, max_len = 0;
   bool loaded = false;
-  std::vector<void*> owned;
+  std::vector<void*> owned;   // workspaces first (allocated by create), then the packed weights
+  size_t n_workspace = (size_t)-1;   // owned[n_workspace..] are weights: released and re-packed by every load_weights
   bf16 *W1 = nullptr, *W2 = nullptr, *W3 = nullptr, *W4 = nullptr, *Wqkv = nullptr, *Wo = nullptr, *Wf1 = nullptr, *Wf2 = nullptr;
   float *b1 = nullptr, *b2 = nullptr, *b3 = nullptr, *b4 = nullptr, *bqkv = nullptr, *bo = nullptr, *bf1 = nullptr, *bf2 = nullptr;
   float *g_in1 = nullptr, *be_in1 = nullptr, *g_in2 = nullptr, *be_in2 = nullptr, *g_n1 = nullptr, *be_n1 = nullptr,
@@ -200,6 +201,12 @@ extern "C" int msmd_style_load_weights(msmd_style* m, const char* const* names, 
                                        const int64_t* numel, int n) {
   MSMD_REQUIRE(m && names && data && numel, "msmd_style_load_weights: null argument");
   MSMD_CHECK_CUDA(cudaSetDevice(m->device));
+  // a reload replaces the previous packed copies instead of accumulating them until destroy
+  MSMD_CHECK_CUDA(cudaDeviceSynchronize());
+  if (m->n_workspace == (size_t)-1) m->n_workspace = m->owned.size();
+  for (size_t i = m->n_workspace; i < m->owned.size(); ++i) cudaFree(m->owned[i]);
+  m->owned.resize(m->n_workspace);
+  m->loaded = false;
   std::map<std::string, int> idx;
   for (int i = 0; i < n; ++i) idx[names[i]] = i;
   std::string missing;

@@ -79,11 +79,16 @@ def _engine_cfg(net, n_diff_steps, target, max_seqs, precision='bf16'):
 class _EngineOwner:
     """Mixin: lazily creates / grows the CUDA engine and keeps its packed weights in sync with the module.
 
-    ``precision`` picks the engine arithmetic: 'bf16' (default; what the reference runs under autocast),
-    'fp32' (fp32 activations + 3-pass tf32 tensor-core GEMMs, ~1e-6 of the fp32 reference) or 'hybrid' (both
-    resident; ``precise_last_steps`` = the sampler's last k steps run in fp32-grade arithmetic)."""
-    precision = 'bf16'
-    precise_last_steps = 0     # int, or 'auto': every step whose bf16 error could exceed 1e-3 (MSMD.auto_precise_steps)
+    ``precision`` picks the engine arithmetic.  The reference runs plain fp32 (no autocast), so the default is the
+    mode that keeps EVERY sampling step within 1e-3 relative L2 of it:
+      'hybrid' (default)  bf16 tensor-core steps while the posterior coefficient c1(t) damps their 6.5e-3 x0_hat
+                          error below 1e-3, one-pass fp16 steps (same cost, error 8e-4) for the last ``fp16_last_steps``,
+                          fp32-grade steps (3-pass fp16-split GEMMs, error 2e-6) for the last ``precise_last_steps``;
+      'fp32'              every step fp32-grade (<= 1e-5);
+      'bf16' / 'fp16'     explicit opt-in: one 16-bit arithmetic for every step (the last steps miss 1e-3 in bf16)."""
+    precision = 'hybrid'
+    precise_last_steps = 'auto'   # int, or 'auto' = MSMD.auto_steps(FP16_ERR_BOUND): steps the fp16 path could miss 1e-3 on
+    fp16_last_steps = 'auto'      # int, or 'auto' = MSMD.auto_steps(BF16_ERR_BOUND)
 
     def _engine_state(self):
         raise NotImplementedError
@@ -161,7 +166,12 @@ class DenoisingNetwork_MSMD(nn.Module, _EngineOwner):
         return next(self.parameters()).device
 
     def _engine_state(self):
-        sched = DiffusionSchedule(self._n_diff_steps, 'cosine')   # standalone module use: tables only feed the sampler
+        # standalone module use: the tables only feed the sampler.  Built once: a fresh schedule per call changed the
+        # weights key (new data_ptrs) and forced a full weight re-pack on every forward.
+        sched = self.__dict__.get('_sched')
+        if sched is None:
+            sched = DiffusionSchedule(self._n_diff_steps, 'cosine')
+            self.__dict__['_sched'] = sched
         def sd():
             out = {'denoising_net.' + k: v for k, v in self.state_dict().items()}
             out.update({'diffusion_sched.' + k: v for k, v in sched.state_dict().items()})
@@ -171,15 +181,19 @@ class DenoisingNetwork_MSMD(nn.Module, _EngineOwner):
     @torch.no_grad()
     def forward(self, motion_feat, audio_feat, person_feat, static_style_feat, prev_motion_feat, prev_audio_feat,
                 step, indicator=None, keep_separate=False, precise=None):
-        if keep_separate:
-            raise _lib.MsmdError('msmd_b200: keep_separate (sample_separate path, model.py:442) is not built yet')
+        """model.py:914-996.  ``keep_separate`` returns (dynamic_features [N,Lp+L,dm], static_features [N,Lp+L,nb,dm],
+        alphas [N,Lp+L,nb]) like the reference (:972-973).  ``precise`` (extra): None = the most accurate arithmetic
+        the engine holds (fp32-grade unless precision is 'bf16'/'fp16'), True/False, or 'bf16' / 'fp16' / 'fp32'."""
         if self.use_indicator and indicator is None:
             raise ValueError('indicator is required when use_indicator is set')
         N = motion_feat.shape[0]
         eng = self._get_engine(N, motion_feat.device)
         eng.window_begin(audio_feat, person_feat.reshape(N, -1), static_style_feat.reshape(N, -1), prev_motion_feat,
                          prev_audio_feat, indicator, NX=N, E=1)
-        return eng.denoise(motion_feat, torch.as_tensor(step).reshape(-1).expand(N), precise)
+        steps = torch.as_tensor(step).reshape(-1).expand(N)
+        if keep_separate:
+            return eng.denoise_parts(motion_feat, steps, precise)
+        return eng.denoise(motion_feat, steps, precise)
 
 
 class MSMD(nn.Module, _EngineOwner):
@@ -243,10 +257,15 @@ class MSMD(nn.Module, _EngineOwner):
             return out
         return (lambda cap: _engine_cfg(net, self.diffusion_sched.num_steps, self.target, cap, self.precision)), sd
 
-    def auto_precise_steps(self, tol=1e-3, bf16_err=1.5e-2):
-        """Number of final sampling steps whose bf16 error could exceed ``tol``: x_{t-1} = c0 x_t + c1(t) x0_hat + sigma z
-        carries the network's bf16 error (``bf16_err`` = the tested bound on x0_hat) scaled by c1(t),
-        which decreases with t; 26 of 500 steps for the cosine schedule."""
+    # x0_hat relative-L2 error bounds of the 16-bit paths vs the fp32 reference, = measured x a safety margin
+    # (tests/test_denoiser_gpu.py asserts the measured values stay below them): bf16 6.5e-3 x 1.5, fp16 8e-4 x 2.5.
+    BF16_ERR_BOUND = 1.0e-2
+    FP16_ERR_BOUND = 2.0e-3
+
+    def auto_steps(self, err, tol=1e-3):
+        """Number of final sampling steps on which a network-output error of ``err`` could exceed ``tol`` in x_{t-1}:
+        x_{t-1} = c0 x_t + c1(t) x0_hat + sigma z carries the error scaled by c1(t), which decreases with t
+        (c1(1) = 1, c1(2) = 0.52, c1(16) = 0.10 for the 500-step cosine schedule)."""
         sch = self.diffusion_sched
         a, ab = sch.alphas.double().cpu(), sch.alpha_bars.double().cpu()
         t = torch.arange(1, sch.num_steps + 1)
@@ -254,14 +273,24 @@ class MSMD(nn.Module, _EngineOwner):
             c1 = (1 - a[t]) / torch.sqrt(1 - ab[t]) / torch.sqrt(a[t])
         else:
             c1 = (1 - a[t]) * torch.sqrt(ab[t - 1]) / (1 - ab[t])
-        over = torch.nonzero(c1 * bf16_err > tol)
+        over = torch.nonzero(c1 * err > tol)
         return int(over.max()) + 1 if len(over) else 0
 
+    def auto_precise_steps(self, tol=1e-3):
+        return self.auto_steps(self.FP16_ERR_BOUND, tol)
+
     def _precise_steps(self, override=None):
+        """(fp32-grade last steps, fp16 last steps) of the hybrid schedule; (0, 0) for the single-arithmetic engines."""
         if self.precision != 'hybrid':
             return 0
         k = self.precise_last_steps if override is None else override
-        return self.auto_precise_steps() if k == 'auto' else int(k)
+        return self.auto_steps(self.FP16_ERR_BOUND) if k == 'auto' else int(k)
+
+    def _fp16_steps(self, override=None):
+        if self.precision != 'hybrid':
+            return 0
+        k = self.fp16_last_steps if override is None else override
+        return self.auto_steps(self.BF16_ERR_BOUND) if k == 'auto' else int(k)
 
     @torch.no_grad()
     def extract_audio_feature(self, audio, frame_num=None):
@@ -273,12 +302,13 @@ class MSMD(nn.Module, _EngineOwner):
     def sample(self, audio_or_feat, shape_feat, style_feat=None, prev_motion_feat=None, prev_audio_feat=None,
                motion_at_T=None, indicator=None, cfg_mode=None, cfg_cond=None, cfg_scale=1.15, flexibility=0,
                dynamic_threshold=None, ret_traj=False, noise=None, n_steps=None, t_start=None, _separate=False,
-               precise_last_steps=None):
+               precise_last_steps=None, fp16_last_steps=None):
         """model.py:282-440.  Extra keyword arguments (not in the reference): ``noise`` = externally supplied
         z tensor [T+1, N, L, 67] indexed by step t (default: in-kernel Philox seeded from torch's generator);
         ``t_start`` / ``n_steps`` = start at step t_start (motion_at_T is then x_{t_start}) and run n steps
-        (teacher-forced parity tests); ``precise_last_steps`` = with ``self.precision == 'hybrid'``, run the steps
-        t <= precise_last_steps in fp32-grade arithmetic (default ``self.precise_last_steps``)."""
+        (teacher-forced parity tests); ``precise_last_steps`` / ``fp16_last_steps`` = with ``self.precision == 'hybrid'``,
+        run the steps t <= precise_last_steps in fp32-grade and precise_last_steps < t <= fp16_last_steps in one-pass
+        fp16 arithmetic (defaults: the attributes of the same names, 'auto')."""
         N = audio_or_feat.shape[0]
         dev = self.device
         cfg_mode = self.cfg_mode if cfg_mode is None else cfg_mode
@@ -346,7 +376,8 @@ class MSMD(nn.Module, _EngineOwner):
         res = eng.sample_window(motion_at_T, noise, seed, cfg_mode == 'independent', s0, s1, flexibility,
                                 t_start=T, n_steps=n_steps, want_traj=ret_traj, dynamic_threshold=dynamic_threshold,
                                 separate=_separate,
-                                precise_last_steps=self._precise_steps(precise_last_steps))
+                                precise_last_steps=self._precise_steps(precise_last_steps),
+                                fp16_last_steps=self._fp16_steps(fp16_last_steps))
         x0, traj = res[0], res[1]
         if _separate and not ret_traj:
             return x0, motion_at_T, audio_feat, res[2]

@@ -19,12 +19,24 @@ class _AudioEncoderMixin:
     _cfg_cls = None
 
     @classmethod
-    def from_pretrained(cls, name, *a, **k):
-        """Released weights when the HF cache has them, random init of the base architecture otherwise
-        (no network in the build / bench environment)."""
+    def from_pretrained(cls, name, *a, allow_random_init=None, **k):
+        """HF ``from_pretrained`` with the caller's arguments (``cache_dir``, ``local_files_only`` ... pass through, as in
+        the reference: model.py:94-101).  A checkpoint that cannot be found is an ERROR - a randomly initialised encoder
+        produces garbage audio features - unless the caller opts in with ``allow_random_init=True`` or the environment
+        variable MSMD_ALLOW_RANDOM_AUDIO_ENCODER=1 (tests / bench, which have no network and no HF cache); the fallback
+        then warns loudly.  Only the not-found errors are caught: a corrupt cache or an incompatible checkpoint raises."""
+        import os
+        import warnings
+        if allow_random_init is None:
+            allow_random_init = os.environ.get('MSMD_ALLOW_RANDOM_AUDIO_ENCODER', '0') not in ('', '0')
         try:
-            return super().from_pretrained(name, *a, local_files_only=True, **k)
-        except Exception:
+            return super().from_pretrained(name, *a, **k)
+        except (OSError, EnvironmentError) as e:      # HF raises OSError for "not cached / cannot reach the hub"
+            if not allow_random_init:
+                raise
+            warnings.warn(f'msmd_b200: pretrained audio encoder {name!r} is unavailable ({type(e).__name__}); using a RANDOMLY '
+                          'INITIALISED base architecture because allow_random_init is set - audio features are '
+                          'meaningless unless a full checkpoint is loaded afterwards', RuntimeWarning, stacklevel=2)
             return cls(cls._cfg_cls())
 
     def forward(self, input_values, output_fps=25, attention_mask=None, output_attentions=None,
