@@ -201,6 +201,9 @@ typedef struct {
                            * handle (or msmd_check) - this call does not synchronise. */
   int fp16_last_steps;    /* hybrid schedule (precision 2): steps with precise_last_steps < t <= fp16_last_steps run the
                            * one-pass fp16 path, earlier steps bf16; < 0 = every step.  Must be 0 when precision == 0. */
+  int64_t noise_clip_offset; /* in-kernel Philox noise (z == NULL) is keyed by (seed, t, GLOBAL element index): clip n of
+                           * this call draws the noise of global clip noise_clip_offset + n, so a clip's codes do not
+                           * depend on how the clips are partitioned over calls / GPUs. */
 } msmd_sample_extras;
 
 int msmd_sample_window_ex(msmd_model* m, const float* x_T, const float* z, uint64_t seed, int cfg_independent,

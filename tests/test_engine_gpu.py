@@ -175,9 +175,10 @@ def test_benchmark_size_full_window_vs_oracle(built_lib):
     """One full free-running window (all T steps, CUDA-graph replays + the schedule's fp16 / fp32-grade tail) at 192
     sequences: clips 0 / 31 / 63 against the oracle sampling those clips alone.  Free-running trajectories diverge from
     the fp32 one at the rate the 16-bit steps inject error, so the hybrid bound is loose (the per-step contract is the
-    teacher-forced test); the fp32-grade engine tracks the oracle over the whole window.  T = 60 keeps the CPU oracle
-    to about a minute; the 500-step schedule's segments are exercised by scaling them to T."""
-    T = 60
+    teacher-forced test) - but the last, fp32-grade steps pull the state back: x_0 = x0_hat(x_1) exactly, and the
+    network is insensitive to the small error x_1 carries, so the FINAL codes agree to 1e-3 (measured 1e-5).  The
+    fp32-grade engine tracks the oracle over the whole window.  The CPU oracle needs ~2 minutes for the 500 steps."""
+    T = 500
     i = _bench_inputs(T)
     sub = _sub(i, CHECK)
     dev = {k: v.cuda() for k, v in i.items()}
@@ -186,7 +187,7 @@ def test_benchmark_size_full_window_vs_oracle(built_lib):
     kw = dict(cfg_mode='incremental', cfg_scale=[1.4, 1.4])
     want, _, _ = D.sample(cpu_state_dict(mh), args, sub['audio_feat'], sub['shape'], sub['style'], x_T=sub['x_T'],
                           z=sub['z'], indicator=sub['indicator'], **kw)
-    for name, m, tol in (('hybrid', mh, 2e-2), ('fp32', m32, 1e-4)):
+    for name, m, tol in (('hybrid', mh, 1e-3), ('fp32', m32, 1e-5)):
         got, _, _ = m.sample(dev['audio_feat'], dev['shape'], dev['style'], motion_at_T=dev['x_T'],
                              indicator=dev['indicator'], noise=dev['z'], **kw)
         errs = [rel_l2(got[c], want[j]) for j, c in enumerate(CHECK)]
@@ -195,4 +196,4 @@ def test_benchmark_size_full_window_vs_oracle(built_lib):
         # the same clips sampled alone on the same engine give the same codes (batch-size independence of every kernel)
         alone, _, _ = m.sample(dev['audio_feat'][[31]], dev['shape'][[31]], dev['style'][[31]], motion_at_T=dev['x_T'][[31]],
                                indicator=dev['indicator'][[31]], noise=dev['z'][:, [31]].contiguous(), **kw)
-        assert rel_l2(alone[0], got[31]) < (1e-6 if name == 'fp32' else 2e-2)
+        assert rel_l2(alone[0], got[31]) < (1e-6 if name == 'fp32' else 1e-3)

@@ -16,7 +16,7 @@ class MsmdConfig(C.Structure):
 class SampleExtras(C.Structure):
     _fields_ = [('use_dynamic_threshold', C.c_int), ('dt_ratio', C.c_float), ('dt_min', C.c_float), ('dt_max', C.c_float),
                 ('target_dynamic', C.c_void_p), ('cumulative_static', C.c_void_p), ('alpha_traj', C.c_void_p),
-                ('precise_last_steps', C.c_int), ('fp16_last_steps', C.c_int)]
+                ('precise_last_steps', C.c_int), ('fp16_last_steps', C.c_int), ('noise_clip_offset', C.c_int64)]
 
 
 PRECISIONS = {'bf16': 0, 'fp32': 1, 'hybrid': 2, 'fp16': 3}
@@ -112,7 +112,7 @@ class DenoiserEngine:
 
     def sample_window(self, x_T, z=None, seed=0, cfg_independent=False, scale0=0.0, scale1=0.0, flexibility=0.0,
                       t_start=None, n_steps=None, want_traj=False, dynamic_threshold=None, separate=False,
-                      precise_last_steps=0, fp16_last_steps=0):
+                      precise_last_steps=0, fp16_last_steps=0, noise_clip_offset=0):
         c = self.cfg
         x_T = x_T.detach().to(self.device, torch.float32).contiguous()
         t_start = c.n_diff_steps if t_start is None else t_start
@@ -126,6 +126,7 @@ class DenoiserEngine:
         ex = SampleExtras()
         ex.precise_last_steps = int(precise_last_steps)
         ex.fp16_last_steps = int(fp16_last_steps)
+        ex.noise_clip_offset = int(noise_clip_offset)
         sep = None
         if dynamic_threshold:
             ex.use_dynamic_threshold = 1

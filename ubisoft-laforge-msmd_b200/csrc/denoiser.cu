@@ -680,6 +680,7 @@ extern "C" int msmd_sample_window_ex(msmd_model* m, const float* x_T, const floa
     MSMD_REQUIRE(!use_dt || (dt_ratio >= 0.f && dt_ratio <= 1.f), "quantile() q values must be in the range [0, 1]");
     if (use_dt) up.thr = m->thr;
     up.tgt_dyn = ex->target_dynamic; up.cum_static = ex->cumulative_static; up.alpha_traj = ex->alpha_traj;
+    up.noise_offset = (long long)ex->noise_clip_offset * c.n_motions * c.motion_dim;
     if (up.cum_static) MSMD_CHECK_CUDA(cudaMemsetAsync(up.cum_static, 0, n_el * 4, st));
   }
   if ((rc = update_params_set(m->d_up, up, st))) return rc;

@@ -667,7 +667,7 @@ __global__ void __launch_bounds__(256) update_kernel(const UpdateParams* __restr
       prev = r; pd = dyn; psv = sta;
     }
     float zt = 0.f;
-    if (t > 1) zt = p.z ? p.z[(int64_t)t * n_el + i] : philox_normal(p.seed, (uint32_t)t, (uint32_t)i);
+    if (t > 1) zt = p.z ? p.z[(int64_t)t * n_el + i] : philox_normal(p.seed, (uint32_t)t, (uint32_t)(i + p.noise_offset));
     const float xo = p.x[i];
     float xn = p.target_noise ? (c0 * (xo - c1 * tgt) + sigma * zt) : (c0 * xo + c1 * tgt + sigma * zt);
     // fp32-grade steps: an activation left the fp16 range of the operand split -> poison the state instead of

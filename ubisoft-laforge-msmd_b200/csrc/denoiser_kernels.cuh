@@ -83,6 +83,7 @@ struct UpdateParams {
   float* cum_static;      // [NX, L, dm] += c1 * CFG-combined static part, or null
   float* alpha_traj;      // [n_steps, NX, L, nb] CFG-combined alphas per executed step (index t_start - t), or null
   int t_start;
+  long long noise_offset; // added to the element index that keys the in-kernel Philox noise (= global clip id * L * dm)
   const int* overflow;    // fp32-grade steps: device flag raised by the operand split; non-zero poisons x with NaN
 };
 // per-sequence threshold s = clamp(quantile(|x0_hat[:, -L:]|, ratio), lo, hi) -> thr[S] (torch.quantile 'linear')

@@ -16,10 +16,13 @@ import torch.nn.functional as F
 
 @torch.no_grad()
 def infer_coeffs_batched(model, args, audio_feat, shape_coef, style_feats=None, clip_len=None, cfg_mode=None,
-                         cfg_cond=None, cfg_scale=1.15, dynamic_threshold=None, x_T=None, noise=None):
+                         cfg_cond=None, cfg_scale=1.15, dynamic_threshold=None, x_T=None, noise=None, noise_seed=None,
+                         clip_offset=0):
     """audio_feat [N, n_sub*n_motions, d] (already extracted); shape_coef [N,1,100] or [N,100];
     style_feats [N,d_style] (or a list per window); clip_len = frames to keep (<= n_sub*n_motions).
-    x_T [N,n_motions,67] / noise ([T+1,N,L,67] or a list per window) are optional fixed inputs.
+    x_T [N,n_motions,67] / noise ([T+1,N,L,67] or a list per window) are optional fixed inputs; without ``noise`` the
+    step noise is the in-kernel Philox stream keyed by (noise_seed + window, global clip id = clip_offset + n), so the
+    codes of a clip do not depend on which batch / GPU it was sampled in.
     Returns [N, clip_len, 67]."""
     N, total = audio_feat.shape[:2]
     L = args.n_motions
@@ -39,7 +42,8 @@ def infer_coeffs_batched(model, args, audio_feat, shape_coef, style_feats=None, 
         z = noise[i] if isinstance(noise, list) else noise
         motion_feat, noise_T, used_audio = model.sample(
             audio_in, shape_coef, style_feat, prev_motion_feat, prev_audio_feat, noise_T, indicator=indicator,
-            cfg_mode=cfg_mode, cfg_cond=cfg_cond, cfg_scale=cfg_scale, dynamic_threshold=dynamic_threshold, noise=z)
+            cfg_mode=cfg_mode, cfg_cond=cfg_cond, cfg_scale=cfg_scale, dynamic_threshold=dynamic_threshold, noise=z,
+            noise_seed=None if noise_seed is None else int(noise_seed) + i, clip_offset=clip_offset)
         prev_motion_feat = motion_feat[:, -args.n_prev_motions:].clone()
         prev_audio_feat = used_audio[:, -args.n_prev_motions:]
         if i == n_sub - 1 and n_padding_frames > 0:

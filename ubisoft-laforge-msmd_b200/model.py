@@ -93,6 +93,13 @@ class _EngineOwner:
     def _engine_state(self):
         raise NotImplementedError
 
+    def check(self):
+        """Synchronise and raise if an earlier fp32-grade call left the fp16 range of its operand split (the sampling
+        call itself never synchronises; it poisons its output with NaN and reports at the next call)."""
+        eng = getattr(self, '_eng', None)
+        if eng is not None:
+            eng.check()
+
     def _get_engine(self, n_seqs, device):
         cfg_fn, sd_fn = self._engine_state()
         eng = getattr(self, '_eng', None)
@@ -302,13 +309,16 @@ class MSMD(nn.Module, _EngineOwner):
     def sample(self, audio_or_feat, shape_feat, style_feat=None, prev_motion_feat=None, prev_audio_feat=None,
                motion_at_T=None, indicator=None, cfg_mode=None, cfg_cond=None, cfg_scale=1.15, flexibility=0,
                dynamic_threshold=None, ret_traj=False, noise=None, n_steps=None, t_start=None, _separate=False,
-               precise_last_steps=None, fp16_last_steps=None):
+               precise_last_steps=None, fp16_last_steps=None, noise_seed=None, clip_offset=0):
         """model.py:282-440.  Extra keyword arguments (not in the reference): ``noise`` = externally supplied
         z tensor [T+1, N, L, 67] indexed by step t (default: in-kernel Philox seeded from torch's generator);
         ``t_start`` / ``n_steps`` = start at step t_start (motion_at_T is then x_{t_start}) and run n steps
         (teacher-forced parity tests); ``precise_last_steps`` / ``fp16_last_steps`` = with ``self.precision == 'hybrid'``,
         run the steps t <= precise_last_steps in fp32-grade and precise_last_steps < t <= fp16_last_steps in one-pass
-        fp16 arithmetic (defaults: the attributes of the same names, 'auto')."""
+        fp16 arithmetic (defaults: the attributes of the same names, 'auto'); ``noise_seed`` / ``clip_offset`` = key of the
+        in-kernel Philox step noise (used when ``noise`` is None): clip n draws the stream of global clip clip_offset + n
+        under ``noise_seed`` (default: a seed drawn from torch's generator), so clip-sharded runs reproduce the
+        single-GPU codes."""
         N = audio_or_feat.shape[0]
         dev = self.device
         cfg_mode = self.cfg_mode if cfg_mode is None else cfg_mode
@@ -369,7 +379,12 @@ class MSMD(nn.Module, _EngineOwner):
         eng.window_begin(torch.cat(audio_in, 0), torch.cat(person_in, 0).reshape(N * E, -1),
                          rep(style_feat).reshape(N * E, -1), rep(prev_motion_feat), rep(prev_audio_feat),
                          rep(indicator) if indicator is not None else None, NX=N, E=E)
-        seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if noise is None else 0
+        if noise is not None:
+            seed = 0
+        elif noise_seed is not None:
+            seed = int(noise_seed)
+        else:
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
         s0 = float(cfg_scale[0]) if E > 1 else 0.0
         s1 = float(cfg_scale[1]) if E > 2 else 0.0
         T = t_start or self.diffusion_sched.num_steps
@@ -377,7 +392,7 @@ class MSMD(nn.Module, _EngineOwner):
                                 t_start=T, n_steps=n_steps, want_traj=ret_traj, dynamic_threshold=dynamic_threshold,
                                 separate=_separate,
                                 precise_last_steps=self._precise_steps(precise_last_steps),
-                                fp16_last_steps=self._fp16_steps(fp16_last_steps))
+                                fp16_last_steps=self._fp16_steps(fp16_last_steps), noise_clip_offset=clip_offset)
         x0, traj = res[0], res[1]
         if _separate and not ret_traj:
             return x0, motion_at_T, audio_feat, res[2]
