@@ -21,6 +21,7 @@ OBJ = os.path.join(ROOT, 'build')
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
          '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr', '-I', os.path.join(ROOT, 'include')]
+FLAGS += os.environ.get('MSMD_EXTRA_NVCC_FLAGS', '').split()     # e.g. -DMSMD_ROW0_TRACE for the timeline probes
 
 
 def sources():

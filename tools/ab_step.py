@@ -5,13 +5,15 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from bench import SamplerWorkload
 from msmd_b200 import _lib
-wl = SamplerWorkload(clips=64, seconds=4.0)
+CL = int(os.environ.get("MSMD_AB_CLIPS", 64))
+wl = SamplerWorkload(clips=CL, seconds=4.0)
+wl.precision = os.environ.get("MSMD_PRECISION", "bf16")
 wl.setup(torch.device('cuda', 0), 0)
 d = dict(wl.dev)
 g = torch.Generator(device='cuda').manual_seed(0)
-af = torch.randn(64, 100, 512, device='cuda', generator=g)
-st = torch.randn(64, 256, device='cuda', generator=g)
-ind = torch.ones(64, 100, device='cuda')
+af = torch.randn(CL, 100, 512, device='cuda', generator=g)
+st = torch.randn(CL, 256, device='cuda', generator=g)
+ind = torch.ones(CL, 100, device='cuda')
 m = wl.model
 m.sample(af, d['shape'], st, motion_at_T=d['x_T'], indicator=ind, cfg_scale=1.4, noise=d['z'], n_steps=4)
 eng = m._eng

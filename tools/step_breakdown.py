@@ -7,6 +7,7 @@ from msmd_b200 import _lib
 clips = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
 wl = SamplerWorkload(clips=clips, seconds=4.0)
+wl.precision = os.environ.get("MSMD_PRECISION", "bf16")
 wl.setup(torch.device('cuda', 0), 0)
 d = dict(wl.dev)
 g = torch.Generator(device='cuda').manual_seed(0)

@@ -24,6 +24,8 @@ using namespace msmd;
 
 namespace {
 
+constexpr int kRow0FusedMaxS = 96;
+
 struct LayerW {
   bf16 *Wqkv = nullptr, *Wo = nullptr, *Wq0 = nullptr, *Wkv = nullptr, *Wco = nullptr, *W1 = nullptr, *W2 = nullptr;
   float *bqkv = nullptr, *bo = nullptr, *bq0 = nullptr, *bkv = nullptr, *bco = nullptr, *b1 = nullptr, *b2 = nullptr;
@@ -246,11 +248,20 @@ int run_forward(msmd_model* m, const float* xrows, cudaStream_t st, int fmt) {
     lp.y = m->y; lp.g1 = w.g1; lp.b1 = w.be1; lp.add = ca; lp.g2 = w.g2; lp.b2 = w.be2; lp.out = m->x;
     lp.x0 = m->x0c; lp.skip_tok0 = 0; lp.M = M; lp.T = T; lp.d = d; lp.fp16 = fmt;
     if ((rc = ln_launch(lp, st))) return rc;
-    // person token (row 0): real cross attention over the memory (_mha_block) + norm2
-    if ((rc = gemm(fmt, m->x0c, d, Wq0, d, w.bq0, nullptr, 0, m->q0, d, 0, S, d, d, 0, st))) return rc;
-    if ((rc = cross_attn_row0_launch(m->q0, kv, m->ctx0, S, T - 1, c.n_heads, fmt, st))) return rc;
-    if ((rc = gemm(fmt, m->ctx0, d, Wco, d, w.bco, nullptr, 0, m->y0, d, 0, S, d, d, 0, st))) return rc;
-    if ((rc = ln_row0_launch(m->y0, m->x0c, w.g2, w.be2, m->x, nullptr, S, T, d, fmt, st))) return rc;
+    // person token (row 0): real cross attention over the memory (_mha_block) + norm2.  Up to kRow0FusedMaxS sequences:
+    // one cluster kernel (3 launches fewer per layer - the launch-bound regimes); above, the HBM-bound K/V read of the
+    // attention dominates and the four-launch chain, which spreads it over every SM, is faster (measured).
+    static const int row0_max_s = [] { const char* e = getenv("MSMD_ROW0_FUSED_MAX_S"); return e ? atoi(e) : kRow0FusedMaxS; }();
+    if (S <= row0_max_s) {
+      if ((rc = row0_fused_launch(m->x0c, static_cast<const bf16*>(Wq0), w.bq0, kv, static_cast<const bf16*>(Wco), w.bco, w.g2,
+                                  w.be2, m->x, S, T, T - 1, c.n_heads, d, fmt, st)))
+        return rc;
+    } else {
+      if ((rc = gemm(fmt, m->x0c, d, Wq0, d, w.bq0, nullptr, 0, m->q0, d, 0, S, d, d, 0, st))) return rc;
+      if ((rc = cross_attn_row0_launch(m->q0, kv, m->ctx0, S, T - 1, c.n_heads, fmt, st))) return rc;
+      if ((rc = gemm(fmt, m->ctx0, d, Wco, d, w.bco, nullptr, 0, m->y0, d, 0, S, d, d, 0, st))) return rc;
+      if ((rc = ln_row0_launch(m->y0, m->x0c, w.g2, w.be2, m->x, nullptr, S, T, d, fmt, st))) return rc;
+    }
     // feed-forward block (_ff_block) + norm3
     if ((rc = gemm(fmt, m->x, d, W1, d, w.b1, nullptr, 0, m->h, c.d_ff, 0, M, c.d_ff, d, 1, st))) return rc;
     if ((rc = gemm(fmt, m->h, c.d_ff, W2, c.d_ff, w.b2, nullptr, 0, m->y, d, 0, M, d, c.d_ff, 0, st))) return rc;

@@ -98,6 +98,11 @@ int steps_advance(int* steps, int S, cudaStream_t st);
 // out[S, T-1... ] : x̂0 per sequence (module-level parity): dyn + static mix for ALL Lp+L rows -> [S, T-1, dm]
 int mix_static_launch(const float* dec, const float* stat, float* out, int S, int T, int dm, int nb, int ldd, cudaStream_t st);
 
+// the whole person-token cross-attention block (q-proj, attention over the memory, out-proj, residual, norm2) as one
+// cluster kernel (row0_fused.cu): x0c [S,512] -> x[s*T + 0]
+int row0_fused_launch(const bf16* x0c, const bf16* Wq, const float* bq, const bf16* kv, const bf16* Wo, const float* bo,
+                      const float* g, const float* be, bf16* x, int S, int T, int Tk, int H, int d, int fp16, cudaStream_t st);
+
 // keep_separate outputs (model.py:972-973): dyn [S,T-1,dm], sta [S,T-1,nb,dm] (tiled), alphas [S,T-1,nb]
 int split_parts_launch(const float* dec, const float* stat, float* dyn, float* sta, float* alphas, int S, int T, int dm,
                        int nb, int ldd, cudaStream_t st);
