@@ -6,6 +6,7 @@
 // one GEMM over K = NB + 36 produces v_posed - template tile by tile and the skinning is its
 // epilogue, so HBM sees only betas/pose in and vertices out.
 #include "flame.cuh"
+#include <cmath>
 #include "rot_math.cuh"
 #include "profile.cuh"
 #include <vector>
@@ -346,9 +347,20 @@ extern "C" int msmd_flame_create(const float* v_template, const float* shapedirs
     MSMD_CHECK_CUDA(cudaMemcpy(*d, h.data(), h.size() * sizeof(__half), cudaMemcpyHostToDevice));
     return MSMD_OK;
   };
+  // per-vertex epilogue constants of the tensor-core path, one 32-byte record per vertex (two broadcast LDS.128):
+  // w0..w4 | template x y z.  Rows past V are zero (their columns are never stored).
+  std::vector<float> vconst((size_t)(fh->N3pad / 3 + 64) * 8, 0.f);
+  bool normalised = NJ == 5;
+  for (int v = 0; v < V && NJ == 5; ++v) {
+    double sum = 0;
+    for (int j = 0; j < 5; ++j) { vconst[(size_t)v * 8 + j] = h_w[(size_t)v * 5 + j]; sum += h_w[(size_t)v * 5 + j]; }
+    for (int c = 0; c < 3; ++c) vconst[(size_t)v * 8 + 5 + c] = h_t[(size_t)v * 3 + c];
+    if (std::fabs(sum - 1.0) > 1e-5) normalised = false;
+  }
+  fh->weights_normalised = normalised ? 1 : 0;
   if ((rc = up(&fh->basis, basis)) || (rc = up16(&fh->basis_hi, hi)) || (rc = up16(&fh->basis_lo, lo)) ||
       (rc = up(&fh->v_template, h_t)) || (rc = up(&fh->weights, h_w)) || (rc = up(&fh->Jt, Jt)) ||
-      (rc = up(&fh->Jb, Jb))) {
+      (rc = up(&fh->Jb, Jb)) || (rc = up(&fh->vconst, vconst))) {
     msmd_flame_destroy(fh);
     return rc;
   }
@@ -366,7 +378,7 @@ extern "C" void msmd_flame_destroy(msmd_flame* fh) {
   if (!fh) return;
   flame_tc_destroy(fh);
   cudaFree(fh->basis); cudaFree(fh->basis_hi); cudaFree(fh->basis_lo); cudaFree(fh->v_template);
-  cudaFree(fh->weights); cudaFree(fh->Jt); cudaFree(fh->Jb); cudaFree(fh->d_parents);
+  cudaFree(fh->weights); cudaFree(fh->vconst); cudaFree(fh->Jt); cudaFree(fh->Jb); cudaFree(fh->d_parents);
   cudaFree(fh->A); cudaFree(fh->A_hi); cudaFree(fh->A_lo); cudaFree(fh->xf);
   delete fh;
 }

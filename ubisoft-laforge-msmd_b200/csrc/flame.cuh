@@ -20,6 +20,8 @@ struct msmd_flame {
   __half* basis_lo = nullptr;
   float* v_template = nullptr;  // [N3]
   float* weights = nullptr;     // [V, NJ]
+  float* vconst = nullptr;      // [V, 8] per-vertex epilogue constants of the tensor-core path: w0..w4 | template xyz
+  int weights_normalised = 0;   // every row of the skinning weights sums to 1 (+-1e-5): the blend may use joint differences
   float* Jt = nullptr;          // [NJ*3]      J_regressor @ v_template
   float* Jb = nullptr;          // [NJ*3, NB]  J_regressor @ shapedirs (joint regression folded)
   int* d_parents = nullptr;     // [8]

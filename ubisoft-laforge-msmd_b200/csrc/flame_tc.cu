@@ -26,7 +26,12 @@ namespace msmd {
 
 namespace {
 
-constexpr int FT_BM = 128, FT_VERT = 42, FT_BN = 126, FT_UN = 128, FT_BK = 64, FT_STAGES = 3;
+#ifdef MSMD_FLAME_EXP   // timing experiment only (wrong results): all quarters share one staging buffer -> room for a 4th stage
+constexpr int FT_STAGES = 4, FT_NQ = 1;
+#else
+constexpr int FT_STAGES = 3, FT_NQ = 4;
+#endif
+constexpr int FT_BM = 128, FT_VERT = 42, FT_BN = 126, FT_UN = 128, FT_BK = 64;
 constexpr int FT_TILE_BYTES = 128 * 128;                 // one operand tile: 128 rows x 128 B
 constexpr int FT_BHALF_BYTES = 64 * 128;                 // this CTA's half of a basis tile: 64 rows x 128 B
 constexpr int FT_STAGE_BYTES = 2 * FT_TILE_BYTES + 2 * FT_BHALF_BYTES;   // A_hi, A_lo, B_hi half, B_lo half
@@ -34,18 +39,25 @@ constexpr int FT_CHUNK_V = 8;                             // vertices per epilog
 constexpr int FT_OUT_STRIDE = 127;                       // staging row stride (floats): odd -> conflict-free
 constexpr int FT_EPI_WARPS = 8;                          // two warps per TMEM lane quarter, alternating chunks
 constexpr int FT_EPI_Q_BYTES = 32 * FT_OUT_STRIDE * 4;    // one TMEM lane quarter (32 frames) x the tile's 126 columns
-constexpr int FT_MISC_BYTES = 2048;                      // barriers, tmem slot, per-tile weights + template
-constexpr int FT_SMEM_BYTES = 1024 + FT_STAGES * FT_STAGE_BYTES + 4 * FT_EPI_Q_BYTES + FT_MISC_BYTES + 2 * (FT_VERT * 5 + FT_BN + 2) * 4;
+constexpr int FT_MISC_BYTES = 2048;                      // barriers, tmem slot
+constexpr int FT_VC_FLOATS = (FT_VERT + 6) * 8;          // per-tile vertex constants (w0..w4 | template), padded to 48 vertices
+constexpr int FT_SMEM_BYTES = 1024 + FT_STAGES * FT_STAGE_BYTES + FT_NQ * FT_EPI_Q_BYTES + FT_MISC_BYTES + 2 * FT_VC_FLOATS * 4;
 constexpr int FT_THREADS = 64 + 32 * FT_EPI_WARPS;
 
 struct FlameTcParams {
   CUtensorMap a_hi, a_lo, b_hi, b_lo;
-  const float* tmpl;     // [3V]
-  const float* weights;  // [V,5]
+  const float* vconst;   // [V(+pad), 8]  w0..w4 | template xyz
   const float* xf;       // [B,60]
   float* out;            // [B,3V]
   int B, V, N3, num_kb, tiles_m, tiles_n;
+  unsigned long long* trace;   // -DMSMD_FLAME_TRACE builds: clock64 stamps of CTA 0, [role 0..2][tile 0..15][4]
 };
+
+__device__ __forceinline__ void ft_stamp(unsigned long long* tr, int role, int it, int ev) {
+#ifdef MSMD_FLAME_TRACE
+  if (tr != nullptr && blockIdx.x == 0 && it < 16) tr[(role * 16 + it) * 4 + ev] = clock64();
+#endif
+}
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
   asm volatile(
@@ -64,20 +76,23 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
                : "memory");
 }
 
+// NORM: every row of the skinning weights sums to 1, so T = A_0 + sum_{j>=1} w_j (A_j - A_0): 48 FMAs per vertex
+// instead of 60 (the blend is the epilogue's - and the kernel's - critical path).
+template <bool NORM>
 __global__ void __launch_bounds__(FT_THREADS, 1) flame_tc_kernel(const __grid_constant__ FlameTcParams p) {
   using namespace tc;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stage_base = smem;
   float* epi_base = reinterpret_cast<float*>(smem + FT_STAGES * FT_STAGE_BYTES);
-  uint8_t* misc = reinterpret_cast<uint8_t*>(epi_base) + 4 * FT_EPI_Q_BYTES;
+  uint8_t* misc = reinterpret_cast<uint8_t*>(epi_base) + FT_NQ * FT_EPI_Q_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(misc);  // [STAGES]
   uint64_t* empty_bar = full_bar + FT_STAGES;              // [STAGES]
   uint64_t* tfull_bar = empty_bar + FT_STAGES;             // [2]
   uint64_t* tempty_bar = tfull_bar + 2;                    // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  float* tile_w = reinterpret_cast<float*>(misc + FT_MISC_BYTES);  // [2][FT_VERT*5 + FT_BN + 2]: weights | template
-  constexpr int TILE_W_FLOATS = FT_VERT * 5 + FT_BN + 2;
+  float* tile_w = reinterpret_cast<float*>(misc + FT_MISC_BYTES);  // [2][48 vertices][8]: w0..w4 | template xyz
+  constexpr int TILE_W_FLOATS = FT_VC_FLOATS;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = p.tiles_m * p.tiles_n;
@@ -98,13 +113,16 @@ __global__ void __launch_bounds__(FT_THREADS, 1) flame_tc_kernel(const __grid_co
 
   if (warp == 0) {
     // ---------------------------------------------------------------- TMA producer
-    int s = 0;
+    int s = 0, pit = 0;
     uint32_t ph = 0;
-    for (int t = pair; t < num_tiles; t += npairs) {
+    for (int t = pair; t < num_tiles; t += npairs, ++pit) {
       const int m0 = (t / p.tiles_n) * 2 * FT_BM + cta_rank * FT_BM, n0 = (t % p.tiles_n) * FT_BN + cta_rank * 64;
       for (int kb = 0; kb < p.num_kb; ++kb) {
         if (lane == 0) {
+          if (kb == 0) ft_stamp(p.trace, 0, pit, 0);
           mbar_wait(&empty_bar[s], ph ^ 1);
+          if (kb == 0) ft_stamp(p.trace, 0, pit, 1);
+          if (kb == p.num_kb - 1) ft_stamp(p.trace, 0, pit, 2);
           uint8_t* st = stage_base + s * FT_STAGE_BYTES;
           // both CTAs' boxes land on the leader's barrier.  Rank 1's basis half covers tile columns 64..127: the
           // last two rows belong to the next tile (or are zero-filled past the end) and only feed junk columns
@@ -128,14 +146,17 @@ __global__ void __launch_bounds__(FT_THREADS, 1) flame_tc_kernel(const __grid_co
       const uint32_t aph = (it >> 1) & 1;
       const uint32_t d_main = tmem_base + a * 256, d_cross = d_main + 128;
       if (lane == 0) {
+        ft_stamp(p.trace, 1, it, 0);
         mbar_wait(&tempty_bar[a], aph ^ 1);
         tc_fence_after();
+        ft_stamp(p.trace, 1, it, 1);
       }
       __syncwarp();
       for (int kb = 0; kb < p.num_kb; ++kb) {
         if (lane == 0) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
+          if (kb == 0) ft_stamp(p.trace, 1, it, 2);
           const uint32_t sa = smem_u32(stage_base + s * FT_STAGE_BYTES);
           const uint64_t ah = make_smem_desc_sw128(sa), al = make_smem_desc_sw128(sa + FT_TILE_BYTES);
           const uint64_t bh = make_smem_desc_sw128(sa + 2 * FT_TILE_BYTES);
@@ -143,8 +164,10 @@ __global__ void __launch_bounds__(FT_THREADS, 1) flame_tc_kernel(const __grid_co
 #pragma unroll
           for (int k = 0; k < FT_BK / 16; ++k) {
             const uint32_t acc = (kb | k) != 0;
+#ifndef MSMD_FLAME_EXP2   // timing experiment: main pass only
             umma_2sm(d_cross, desc_advance(al, k * 32), desc_advance(bh, k * 32), idesc, acc);  // lo * hi
             umma_2sm(d_cross, desc_advance(ah, k * 32), desc_advance(bl, k * 32), idesc, 1u);   // hi * lo
+#endif
             umma_2sm(d_main, desc_advance(ah, k * 32), desc_advance(bh, k * 32), idesc, acc);   // hi * hi
           }
           umma_commit_2sm(&empty_bar[s]);
@@ -152,14 +175,14 @@ __global__ void __launch_bounds__(FT_THREADS, 1) flame_tc_kernel(const __grid_co
         __syncwarp();
         if (++s == FT_STAGES) { s = 0; ph ^= 1; }
       }
-      if (lane == 0) umma_commit_2sm(&tfull_bar[a]);
+      if (lane == 0) { ft_stamp(p.trace, 1, it, 3); umma_commit_2sm(&tfull_bar[a]); }
       __syncwarp();
     }
   } else {
     // ---------------------------------------------------------------- epilogue: skinning
     const int q = warp & 3;                     // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;           // which of the quarter's two warps: chunks half, half+2, ...
-    float* stage = epi_base + q * (FT_EPI_Q_BYTES / 4);   // shared by the quarter's two warps
+    float* stage = epi_base + (q % FT_NQ) * (FT_EPI_Q_BYTES / 4);   // shared by the quarter's two warps
     const int etid = threadIdx.x - 64;
     constexpr int EPI_THREADS = 32 * FT_EPI_WARPS;
     constexpr int NCHUNK = (FT_VERT + FT_CHUNK_V - 1) / FT_CHUNK_V;
@@ -169,11 +192,11 @@ __global__ void __launch_bounds__(FT_THREADS, 1) flame_tc_kernel(const __grid_co
       const int a = it & 1;
       const uint32_t aph = (it >> 1) & 1;
       const int v0 = n0 / 3;
-      // per-tile skinning weights + template slice -> smem (double-buffered by tile parity)
+      // per-tile vertex constants -> smem (double-buffered by tile parity); 16-byte copies
       float* tw = tile_w + a * TILE_W_FLOATS;
-      for (int i = etid; i < FT_VERT * 5; i += EPI_THREADS) tw[i] = (v0 + i / 5 < p.V) ? __ldg(p.weights + (int64_t)v0 * 5 + i) : 0.f;
-      for (int i = etid; i < FT_BN; i += EPI_THREADS) tw[FT_VERT * 5 + i] = (n0 + i < p.N3) ? __ldg(p.tmpl + n0 + i) : 0.f;
-      // this thread's frame: 5 joints x (3x3 | t)
+      for (int i = etid; i < FT_VC_FLOATS / 4; i += EPI_THREADS)
+        reinterpret_cast<float4*>(tw)[i] = __ldg(reinterpret_cast<const float4*>(p.vconst + (int64_t)v0 * 8) + i);
+      // this thread's frame: 5 joints x (3x3 | t); with normalised weights joints 1..4 are kept as differences to joint 0
       const int row = m0 + q * 32 + lane;
       float xf[60];
       {
@@ -183,66 +206,100 @@ __global__ void __launch_bounds__(FT_THREADS, 1) flame_tc_kernel(const __grid_co
           const float4 f = __ldg(src + i);
           xf[4 * i] = f.x; xf[4 * i + 1] = f.y; xf[4 * i + 2] = f.z; xf[4 * i + 3] = f.w;
         }
+        if constexpr (NORM) {
+#pragma unroll
+          for (int j = 1; j < 5; ++j)
+#pragma unroll
+            for (int e = 0; e < 12; ++e) xf[j * 12 + e] -= xf[e];
+        }
       }
       asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+      if (warp == 2 && lane == 0) ft_stamp(p.trace, 2, it, 0);
       mbar_wait(&tfull_bar[a], aph);
       tc_fence_after();
+      if (warp == 2 && lane == 0) ft_stamp(p.trace, 2, it, 1);
       const uint32_t t_main = tmem_base + ((uint32_t)(q * 32) << 16) + a * 256, t_cross = t_main + 128;
-      const float* tmpl = tw + FT_VERT * 5;
-#pragma unroll 1
-      for (int ck = half; ck < NCHUNK; ck += 2) {   // 8-vertex chunks (24 columns); the last one holds 2 vertices
+      // 8-vertex chunks (24 accumulator columns); the last one (ck = 5) holds 2 vertices.  This warp takes chunks
+      // half, half + 2, half + 4; the TMEM reads of its next chunk are in flight while the current one is skinned.
+      auto load_chunk = [&](int ck, uint32_t (&m)[24], uint32_t (&c)[24]) {
         const int c0 = ck * 3 * FT_CHUNK_V;
-        const int nv = min(FT_CHUNK_V, FT_VERT - ck * FT_CHUNK_V);
-        uint32_t m[24], c[24];
-        if (nv == FT_CHUNK_V) {
+        if (ck < NCHUNK - 1) {
           tmem_ld16(t_main + c0, m); tmem_ld8(t_main + c0 + 16, m + 16);
           tmem_ld16(t_cross + c0, c); tmem_ld8(t_cross + c0 + 16, c + 16);
-        } else {   // last chunk: 2 vertices = columns 120..125; an x16 load would run past the 128-column accumulator
+        } else {   // columns 120..125; an x16 load would run past the 128-column accumulator
           tmem_ld8(t_main + c0, m);
           tmem_ld8(t_cross + c0, c);
         }
-        tmem_ld_wait();
+      };
+      auto skin_chunk = [&](int ck, const uint32_t (&m)[24], const uint32_t (&c)[24]) {
+        const int nv = min(FT_CHUNK_V, FT_VERT - ck * FT_CHUNK_V);
 #pragma unroll
         for (int v = 0; v < FT_CHUNK_V; ++v) {
           if (v < nv) {
-            const int cc = c0 + 3 * v;
+            const int vv = ck * FT_CHUNK_V + v, cc = 3 * vv;
+            const float4 wa = *reinterpret_cast<const float4*>(tw + vv * 8);       // w0 w1 w2 w3   (broadcast)
+            const float4 wb = *reinterpret_cast<const float4*>(tw + vv * 8 + 4);   // w4 tx ty tz
             constexpr float kLo = 1.0f / 2048.0f;   // the residual terms were scaled by 2^11 (flame.cuh)
-            const float px = __uint_as_float(m[3 * v]) + fmaf(__uint_as_float(c[3 * v]), kLo, tmpl[cc]);
-            const float py = __uint_as_float(m[3 * v + 1]) + fmaf(__uint_as_float(c[3 * v + 1]), kLo, tmpl[cc + 1]);
-            const float pz = __uint_as_float(m[3 * v + 2]) + fmaf(__uint_as_float(c[3 * v + 2]), kLo, tmpl[cc + 2]);
-            const float* w = tw + (cc / 3) * 5;
+            const float px = __uint_as_float(m[3 * v]) + fmaf(__uint_as_float(c[3 * v]), kLo, wb.y);
+            const float py = __uint_as_float(m[3 * v + 1]) + fmaf(__uint_as_float(c[3 * v + 1]), kLo, wb.z);
+            const float pz = __uint_as_float(m[3 * v + 2]) + fmaf(__uint_as_float(c[3 * v + 2]), kLo, wb.w);
             float T[12];
 #pragma unroll
             for (int e = 0; e < 12; ++e) {
-              float s = w[0] * xf[e];
-#pragma unroll
-              for (int j = 1; j < 5; ++j) s = fmaf(w[j], xf[j * 12 + e], s);
-              T[e] = s;
+              float s = NORM ? xf[e] : wa.x * xf[e];
+              s = fmaf(wa.y, xf[12 + e], s);
+              s = fmaf(wa.z, xf[24 + e], s);
+              s = fmaf(wa.w, xf[36 + e], s);
+              T[e] = fmaf(wb.x, xf[48 + e], s);
             }
-            stage[lane * FT_OUT_STRIDE + cc + 0] = T[0] * px + T[1] * py + T[2] * pz + T[9];
-            stage[lane * FT_OUT_STRIDE + cc + 1] = T[3] * px + T[4] * py + T[5] * pz + T[10];
-            stage[lane * FT_OUT_STRIDE + cc + 2] = T[6] * px + T[7] * py + T[8] * pz + T[11];
+            stage[lane * FT_OUT_STRIDE + cc + 0] = fmaf(T[0], px, fmaf(T[1], py, fmaf(T[2], pz, T[9])));
+            stage[lane * FT_OUT_STRIDE + cc + 1] = fmaf(T[3], px, fmaf(T[4], py, fmaf(T[5], pz, T[10])));
+            stage[lane * FT_OUT_STRIDE + cc + 2] = fmaf(T[6], px, fmaf(T[7], py, fmaf(T[8], pz, T[11])));
           }
         }
+      };
+      {
+        uint32_t mA[24], cA[24], mB[24], cB[24];
+        load_chunk(half, mA, cA);
+        tmem_ld_wait();
+        load_chunk(half + 2, mB, cB);
+        skin_chunk(half, mA, cA);
+        tmem_ld_wait();
+        load_chunk(half + 4, mA, cA);
+        skin_chunk(half + 2, mB, cB);
+        tmem_ld_wait();
+        skin_chunk(half + 4, mA, cA);
       }
+      if (warp == 2 && lane == 0) ft_stamp(p.trace, 2, it, 2);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {   // accumulators are consumed: the MMAs of the next tile may overwrite them during the stores
         if (cta_rank != 0) mbar_arrive_cluster(&tempty_bar[a], 0);   // the leader's MMA warp waits for both CTAs
         else mbar_arrive(&tempty_bar[a]);
       }
-      // both warps of the quarter have staged their vertices: store whole 504-byte tile rows, coalesced
+      // both warps of the quarter have staged their vertices: store whole 504-byte tile rows, coalesced; four rows'
+      // shared-memory reads are issued together so the stores stream instead of paying one LDS latency per row
       asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
       const int ncol = min(FT_BN, p.N3 - n0);
-      for (int r = half; r < 32; r += 2) {
-        const int grow = m0 + q * 32 + r;
-        if (grow >= p.B) break;
-        float* dst = p.out + (int64_t)grow * p.N3 + n0;
-        const float* src = stage + r * FT_OUT_STRIDE;
+#pragma unroll 1
+      for (int r0 = half; r0 < 32; r0 += 8) {
+        float val[4][4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (lane + 32 * k < ncol) __stcs(dst + lane + 32 * k, src[lane + 32 * k]);
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) val[u][k] = (lane + 32 * k < FT_BN) ? stage[(r0 + 2 * u) * FT_OUT_STRIDE + lane + 32 * k] : 0.f;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int grow = m0 + q * 32 + r0 + 2 * u;
+          if (grow < p.B) {
+            float* dst = p.out + (int64_t)grow * p.N3 + n0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (lane + 32 * k < ncol) __stcs(dst + lane + 32 * k, val[u][k]);
+          }
+        }
       }
+      if (warp == 2 && lane == 0) ft_stamp(p.trace, 2, it, 3);
     }
   }
 
@@ -267,13 +324,14 @@ int flame_decode_tc(msmd_flame* fh, int64_t B, float* verts_out, cudaStream_t st
   if ((rc = make_tmap_2d(&p.a_lo, fh->A_lo, f32, fh->Kpad, rows, ldk, FT_BK, FT_BM, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   if ((rc = make_tmap_2d(&p.b_hi, fh->basis_hi, f32, fh->Kpad, fh->N3pad, ldk, FT_BK, 64, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   if ((rc = make_tmap_2d(&p.b_lo, fh->basis_lo, f32, fh->Kpad, fh->N3pad, ldk, FT_BK, 64, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
-  p.tmpl = fh->v_template; p.weights = fh->weights; p.xf = fh->xf; p.out = verts_out;
+  p.vconst = fh->vconst; p.xf = fh->xf; p.out = verts_out;
   p.B = (int)B; p.V = fh->V; p.N3 = fh->N3; p.num_kb = fh->Kpad / FT_BK;
   p.tiles_m = cdiv(B, 2 * FT_BM);
   p.tiles_n = cdiv(fh->N3, FT_BN);
   static bool attr = false;
   if (!attr) {
-    MSMD_CHECK_CUDA(cudaFuncSetAttribute(flame_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM_BYTES));
+    MSMD_CHECK_CUDA(cudaFuncSetAttribute(flame_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM_BYTES));
+    MSMD_CHECK_CUDA(cudaFuncSetAttribute(flame_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM_BYTES));
     attr = true;
   }
   const int tiles = p.tiles_m * p.tiles_n;
@@ -289,8 +347,36 @@ int flame_decode_tc(msmd_flame* fh, int64_t B, float* verts_out, cudaStream_t st
   attr_c[0].val.clusterDim.x = 2; attr_c[0].val.clusterDim.y = 1; attr_c[0].val.clusterDim.z = 1;
   cfg.attrs = attr_c;
   cfg.numAttrs = 1;
-  MSMD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, flame_tc_kernel, p));
+#ifdef MSMD_FLAME_TRACE
+  static unsigned long long* tbuf = nullptr;
+  if (!tbuf) MSMD_CHECK_CUDA(cudaMalloc(&tbuf, 3 * 16 * 4 * 8));
+  MSMD_CHECK_CUDA(cudaMemsetAsync(tbuf, 0, 3 * 16 * 4 * 8, st));
+  p.trace = tbuf;
+#endif
+  if (fh->weights_normalised) MSMD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, flame_tc_kernel<true>, p));
+  else MSMD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, flame_tc_kernel<false>, p));
   MSMD_CHECK_LAUNCH();
+#ifdef MSMD_FLAME_TRACE
+  {
+    static int calls = 0;
+    if (++calls == 10) {
+      unsigned long long h[3 * 16 * 4];
+      MSMD_CHECK_CUDA(cudaStreamSynchronize(st));
+      MSMD_CHECK_CUDA(cudaMemcpy(h, tbuf, sizeof(h), cudaMemcpyDeviceToHost));
+      const unsigned long long t0 = h[0];
+      const char* names[3] = {"tma  [tile start, slot free, last kb issued]", "mma  [start, acc free, first full, last issued]",
+                              "epi  [start, acc full, computed, stored]"};
+      for (int r = 0; r < 3; ++r) {
+        fprintf(stderr, "[flame trace] %s\n", names[r]);
+        for (int j = 0; j < 10; ++j) {
+          const unsigned long long* e = &h[(r * 16 + j) * 4];
+          fprintf(stderr, "   tile %2d: %7lld %7lld %7lld %7lld\n", j, (long long)(e[0] - t0), (long long)(e[1] - t0),
+                  (long long)(e[2] ? e[2] - t0 : 0), (long long)(e[3] ? e[3] - t0 : 0));
+        }
+      }
+    }
+  }
+#endif
   return MSMD_OK;
 }
 
