@@ -69,9 +69,19 @@ def test_rotations_large_ragged_and_empty(rc):
         assert np.abs(got - R.axis_angle_to_matrix(aa.numpy())).max() < 4e-6
         e = torch.randn(n, 3, generator=g)
         got = rc.euler_angles_to_axis_angle(e.cuda(), 'YXZ').cpu().numpy()
-        want = R.matrix_to_axis_angle(R.euler_angles_to_matrix(e.numpy(), 'YXZ'))
-        close = np.abs(got - want).max(-1) < 5e-5
-        assert close.mean() > 0.999  # the lossy sqrt/copysign formula flips sign exactly at pi
+        m_ref = R.euler_angles_to_matrix(e.numpy(), 'YXZ')
+        want = R.matrix_to_axis_angle(m_ref)
+        err = np.abs(got - want).max(-1)
+        # The reference's matrix_to_quaternion (rotation_conversions.py:100-120) takes 0.5*sqrt(1 +- m00 +- m11 +- m22): where
+        # such an argument is ~1e-7 (a quaternion component that should be 0, or the angle at pi) its OUTPUT is the rounding
+        # noise of the matrix entries, up to sqrt(4e-7)/2 = 3e-4 - any implementation whose matrix is not bit-identical
+        # differs there.  Everywhere else the fused kernel agrees to 2e-5.
+        d = np.stack([m_ref[:, 0, 0], m_ref[:, 1, 1], m_ref[:, 2, 2]], -1)
+        args = np.stack([1 + d.sum(-1), 1 + d[:, 0] - d[:, 1] - d[:, 2], 1 - d[:, 0] + d[:, 1] - d[:, 2],
+                         1 - d[:, 0] - d[:, 1] + d[:, 2]], -1)
+        ill = args.min(-1) < 2e-5
+        assert err[~ill].max(initial=0.0) < 2e-5, (n, err[~ill].max())
+        assert err[ill].max(initial=0.0) < 5e-3 and ill.sum() <= max(5, 0.01 * n), (n, err.max(), ill.mean())
     assert rc.axis_angle_to_matrix(torch.zeros(0, 3).cuda()).shape == (0, 3, 3)
     x = torch.randn(4, 5, 3, generator=g)
     assert rc.axis_angle_to_matrix(x.cuda()).shape == (4, 5, 3, 3)

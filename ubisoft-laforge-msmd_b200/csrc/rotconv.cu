@@ -37,17 +37,19 @@ __device__ __forceinline__ void st_mat(float* p, const Mat3& m) {
   for (int i = 0; i < 9; ++i) p[i] = m.m[i];
 }
 
-template <int KIND>
-__device__ __forceinline__ void rot_one(const float* i, float* o, int conv) {
+// CONV: Euler convention code (a*9 + b*3 + c) as a compile-time constant for the three Euler kinds (every axis test and
+// matrix index folds away), 0 for the others
+template <int KIND, int CONV>
+__device__ __forceinline__ void rot_one(const float* i, float* o) {
   if constexpr (KIND == MSMD_ROT_QUAT_TO_MATRIX) {
     st_mat(o, quat_to_matrix(Quat{i[0], i[1], i[2], i[3]}));
   } else if constexpr (KIND == MSMD_ROT_MATRIX_TO_QUAT) {
     Quat q = matrix_to_quat(ld_mat(i));
     o[0] = q.w; o[1] = q.x; o[2] = q.y; o[3] = q.z;
   } else if constexpr (KIND == MSMD_ROT_EULER_TO_MATRIX) {
-    st_mat(o, euler_to_matrix(i[0], i[1], i[2], conv));
+    st_mat(o, euler_to_matrix_c<CONV>(i[0], i[1], i[2]));
   } else if constexpr (KIND == MSMD_ROT_MATRIX_TO_EULER) {
-    Vec3 e = matrix_to_euler(ld_mat(i), conv);
+    Vec3 e = matrix_to_euler_c<CONV>(ld_mat(i));
     o[0] = e.x; o[1] = e.y; o[2] = e.z;
   } else if constexpr (KIND == MSMD_ROT_AA_TO_QUAT) {
     Quat q = aa_to_quat(Vec3{i[0], i[1], i[2]});
@@ -76,7 +78,7 @@ __device__ __forceinline__ void rot_one(const float* i, float* o, int conv) {
   } else if constexpr (KIND == MSMD_ROT_QUAT_INVERT) {
     o[0] = i[0]; o[1] = -i[1]; o[2] = -i[2]; o[3] = -i[3];
   } else if constexpr (KIND == MSMD_ROT_EULER_TO_AA) {
-    Vec3 a = quat_to_aa(matrix_to_quat(euler_to_matrix(i[0], i[1], i[2], conv)));
+    Vec3 a = quat_to_aa(matrix_to_quat(euler_to_matrix_c<CONV>(i[0], i[1], i[2])));
     o[0] = a.x; o[1] = a.y; o[2] = a.z;
   } else if constexpr (KIND == MSMD_ROT_RODRIGUES) {
     st_mat(o, rodrigues(i[0], i[1], i[2]));
@@ -103,9 +105,9 @@ __device__ __forceinline__ void block_store(float* g, const float* s, int count,
   }
 }
 
-template <int KIND>
+template <int KIND, int CONV>
 __global__ void __launch_bounds__(kRotBlock) rot_kernel(const float* __restrict__ in, float* __restrict__ out,
-                                                        int64_t n, int conv, bool aligned) {
+                                                        int64_t n, bool aligned) {
   constexpr int IN = RotTraits<KIND>::IN, OUT = RotTraits<KIND>::OUT;
   __shared__ __align__(16) float s_in[kRotBlock * IN];
   __shared__ __align__(16) float s_out[kRotBlock * OUT];
@@ -118,7 +120,7 @@ __global__ void __launch_bounds__(kRotBlock) rot_kernel(const float* __restrict_
       float li[IN], lo[OUT];
 #pragma unroll
       for (int k = 0; k < IN; ++k) li[k] = s_in[threadIdx.x * IN + k];
-      rot_one<KIND>(li, lo, conv);
+      rot_one<KIND, CONV>(li, lo);
 #pragma unroll
       for (int k = 0; k < OUT; ++k) s_out[threadIdx.x * OUT + k] = lo[k];
     }
@@ -154,13 +156,29 @@ __global__ void __launch_bounds__(kRotBlock) quat_binary_kernel(const float* __r
   }
 }
 
-template <int KIND>
-static int launch_rot(const float* in, float* out, int64_t n, int conv, cudaStream_t st) {
+template <int KIND, int CONV>
+static int launch_rot_c(const float* in, float* out, int64_t n, cudaStream_t st) {
   const int blocks = (int)std::min<int64_t>((n + kRotBlock - 1) / kRotBlock, (int64_t)kNumSMs * 16);
   const bool aligned = ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
-  rot_kernel<KIND><<<blocks, kRotBlock, 0, st>>>(in, out, n, conv, aligned);
+  rot_kernel<KIND, CONV><<<blocks, kRotBlock, 0, st>>>(in, out, n, aligned);
   MSMD_CHECK_LAUNCH();
   return MSMD_OK;
+}
+template <int KIND>
+static int launch_rot(const float* in, float* out, int64_t n, int conv, cudaStream_t st) {
+  constexpr bool euler = KIND == MSMD_ROT_EULER_TO_MATRIX || KIND == MSMD_ROT_MATRIX_TO_EULER || KIND == MSMD_ROT_EULER_TO_AA;
+  if constexpr (!euler) {
+    return launch_rot_c<KIND, 0>(in, out, n, st);
+  } else {
+    switch (conv) {     // the 12 valid conventions (middle axis differs from both neighbours)
+#define CV(C) case C: return launch_rot_c<KIND, C>(in, out, n, st);
+      CV(3) CV(5) CV(6) CV(7) CV(10) CV(11) CV(15) CV(16) CV(19) CV(20) CV(21) CV(23)
+#undef CV
+      default:
+        set_error("Invalid convention code %d.", conv);
+        return MSMD_ERR_INVALID;
+    }
+  }
 }
 
 }  // namespace msmd
