@@ -7,6 +7,7 @@
 // (row t = the k*512 contiguous elements starting at frame stride*t) - no im2col buffer.  The grouped
 // positional conv (k=128, 16 groups) is 16 GEMMs per clip over a group-major zero-padded copy.
 #include "audio_kernels.cuh"
+#include <cstdlib>
 #include "gemm_tc.cuh"
 #include <cmath>
 #include <cstring>
@@ -284,7 +285,7 @@ extern "C" int msmd_audio_encode(msmd_audio* m, const float* wav, int N, int n_s
     EncLayer& w = m->L[l];
     const bool last = l == m->n_layers - 1;
     if ((rc = gemm2d(m->x, 768, w.Wqkv, 768, w.bqkv, nullptr, 0, m->qkv, 2304, 0, M, 2304, 768, 0, st))) return rc;
-    if ((rc = flash_attn(m->qkv, m->ctx, N, F, m->n_heads, st))) return rc;
+    if ((rc = flash_attn_tc(m->qkv, m->ctx, N, F, m->n_heads, st))) return rc;
     if ((rc = gemm2d(m->ctx, 768, w.Wo, 768, w.bo, m->x, 768, m->y, 768, 1, M, 768, 768, 0, st))) return rc;
     if ((rc = ln768(m->y, w.g1, w.be1, m->x, nullptr, M, st))) return rc;
     if ((rc = gemm2d(m->x, 768, w.W1, 768, w.b1, nullptr, 0, m->hff, 3072, 0, M, 3072, 768, 1, st))) return rc;

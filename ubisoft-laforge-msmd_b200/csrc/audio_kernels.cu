@@ -292,136 +292,6 @@ int interp768_bf16(const float* hs, int N, int F, int L, bf16* out, cudaStream_t
   return MSMD_OK;
 }
 
-// ------------------------------------------------------------------------------------------- flash attention
-// 64 queries per CTA (4 warps x 16 rows), 64-key tiles through shared memory, online softmax in fp32,
-// S = Q K^T and O = P V on mma.sync m16n8k16 bf16.  q is pre-scaled (1/sqrt(64) folded into Wq at load).
-constexpr int kFaStride = 72;
-
-__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-
-__global__ void __launch_bounds__(128) flash_attn_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ ctx, int T,
-                                                         int H) {
-  __shared__ __align__(16) bf16 sQ[64 * kFaStride];
-  __shared__ __align__(16) bf16 sK[64 * kFaStride];
-  __shared__ __align__(16) bf16 sV[64 * kFaStride];
-  const int qt = blockIdx.x, h = blockIdx.y, n = blockIdx.z;
-  const int d = H * 64;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  const bf16* base = qkv + (int64_t)n * T * 3 * d + h * 64;
-  for (int idx = tid; idx < 64 * 8; idx += 128) {
-    const int row = idx >> 3, ch = idx & 7;
-    const int r = qt * 64 + row;
-    uint4 q = make_uint4(0, 0, 0, 0);
-    if (r < T) q = *reinterpret_cast<const uint4*>(base + (int64_t)r * 3 * d + ch * 8);
-    *reinterpret_cast<uint4*>(&sQ[row * kFaStride + ch * 8]) = q;
-  }
-  __syncthreads();
-  const int r0 = warp * 16;
-  uint32_t aq[4][4];
-#pragma unroll
-  for (int ks = 0; ks < 4; ++ks) {
-    aq[ks][0] = *reinterpret_cast<const uint32_t*>(&sQ[(r0 + g) * kFaStride + ks * 16 + 2 * t]);
-    aq[ks][1] = *reinterpret_cast<const uint32_t*>(&sQ[(r0 + g + 8) * kFaStride + ks * 16 + 2 * t]);
-    aq[ks][2] = *reinterpret_cast<const uint32_t*>(&sQ[(r0 + g) * kFaStride + ks * 16 + 8 + 2 * t]);
-    aq[ks][3] = *reinterpret_cast<const uint32_t*>(&sQ[(r0 + g + 8) * kFaStride + ks * 16 + 8 + 2 * t]);
-  }
-  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
-  float o[8][4];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
-  const float L2E = 1.4426950408889634f;
-  const int n_kt = (T + 63) / 64;
-  for (int kt = 0; kt < n_kt; ++kt) {
-    __syncthreads();  // previous tile fully consumed
-    for (int idx = tid; idx < 64 * 8; idx += 128) {
-      const int row = idx >> 3, ch = idx & 7;
-      const int r = kt * 64 + row;
-      uint4 k = make_uint4(0, 0, 0, 0), v = k;
-      if (r < T) {
-        const bf16* p = base + (int64_t)r * 3 * d + ch * 8;
-        k = *reinterpret_cast<const uint4*>(p + d);
-        v = *reinterpret_cast<const uint4*>(p + 2 * d);
-      }
-      *reinterpret_cast<uint4*>(&sK[row * kFaStride + ch * 8]) = k;
-      *reinterpret_cast<uint4*>(&sV[row * kFaStride + ch * 8]) = v;
-    }
-    __syncthreads();
-    float sc[8][4];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f;
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
-        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&sK[(j * 8 + g) * kFaStride + ks * 16 + 2 * t]);
-        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&sK[(j * 8 + g) * kFaStride + ks * 16 + 8 + 2 * t]);
-        mma16816(sc[j], aq[ks], b0, b1);
-      }
-    }
-    float t0 = -INFINITY, t1 = -INFINITY;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = kt * 64 + j * 8 + 2 * t;
-      if (c >= T) { sc[j][0] = -INFINITY; sc[j][2] = -INFINITY; }
-      if (c + 1 >= T) { sc[j][1] = -INFINITY; sc[j][3] = -INFINITY; }
-      t0 = fmaxf(t0, fmaxf(sc[j][0], sc[j][1]));
-      t1 = fmaxf(t1, fmaxf(sc[j][2], sc[j][3]));
-    }
-    t0 = fmaxf(t0, __shfl_xor_sync(0xffffffffu, t0, 1)); t0 = fmaxf(t0, __shfl_xor_sync(0xffffffffu, t0, 2));
-    t1 = fmaxf(t1, __shfl_xor_sync(0xffffffffu, t1, 1)); t1 = fmaxf(t1, __shfl_xor_sync(0xffffffffu, t1, 2));
-    const float n0 = fmaxf(m0, t0), n1 = fmaxf(m1, t1);
-    const float a0 = exp2f((m0 - n0) * L2E), a1 = exp2f((m1 - n1) * L2E);
-    m0 = n0; m1 = n1;
-    l0 *= a0; l1 *= a1;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { o[i][0] *= a0; o[i][1] *= a0; o[i][2] *= a1; o[i][3] *= a1; }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      sc[j][0] = exp2f((sc[j][0] - m0) * L2E); sc[j][1] = exp2f((sc[j][1] - m0) * L2E);
-      sc[j][2] = exp2f((sc[j][2] - m1) * L2E); sc[j][3] = exp2f((sc[j][3] - m1) * L2E);
-      l0 += sc[j][0] + sc[j][1];
-      l1 += sc[j][2] + sc[j][3];
-    }
-#pragma unroll
-    for (int kb = 0; kb < 4; ++kb) {
-      uint32_t ap[4];
-      ap[0] = pack2(sc[2 * kb][0], sc[2 * kb][1]);
-      ap[1] = pack2(sc[2 * kb][2], sc[2 * kb][3]);
-      ap[2] = pack2(sc[2 * kb + 1][0], sc[2 * kb + 1][1]);
-      ap[3] = pack2(sc[2 * kb + 1][2], sc[2 * kb + 1][3]);
-#pragma unroll
-      for (int n2 = 0; n2 < 4; ++n2) {
-        const int mrow = kb * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
-        const int mcol = (2 * n2 + (lane >> 4)) * 8;
-        uint32_t b0, b1, b2, b3;
-        const uint32_t addr = (uint32_t)__cvta_generic_to_shared(&sV[mrow * kFaStride + mcol]);
-        asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
-                     : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3) : "r"(addr));
-        mma16816(o[2 * n2], ap, b0, b1);
-        mma16816(o[2 * n2 + 1], ap, b2, b3);
-      }
-    }
-  }
-  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-  const float i0 = 1.0f / l0, i1 = 1.0f / l1;
-  const int ra = qt * 64 + r0 + g, rb = ra + 8;
-#pragma unroll
-  for (int nn = 0; nn < 8; ++nn) {
-    const int col = h * 64 + nn * 8 + 2 * t;
-    if (ra < T) *reinterpret_cast<uint32_t*>(ctx + ((int64_t)n * T + ra) * d + col) = pack2(o[nn][0] * i0, o[nn][1] * i0);
-    if (rb < T) *reinterpret_cast<uint32_t*>(ctx + ((int64_t)n * T + rb) * d + col) = pack2(o[nn][2] * i1, o[nn][3] * i1);
-  }
-}
-int flash_attn(const bf16* qkv, bf16* ctx, int N, int T, int H, cudaStream_t st) {
-  ProfileScope prof("flash_attn", st);
-  flash_attn_kernel<<<dim3(cdiv(T, 64), H, N), 128, 0, st>>>(qkv, ctx, T, H);
-  MSMD_CHECK_LAUNCH();
-  return MSMD_OK;
-}
+// (the encoder's self-attention is flash_attn_tc.cu: tcgen05 S = Q K^T / O = P V with an online softmax)
 
 }  // namespace msmd

@@ -31,7 +31,7 @@ int pos_add_ln768(const float* h0, const float* pos, const float* g, const float
 int ln768(const float* y, const float* g, const float* b, bf16* out, float* out_f32, int M, cudaStream_t st);
 
 // flash-style attention, head dim 64: qkv [N*T, 3*d] bf16 (q|k|v, q pre-scaled) -> ctx [N*T, d]
-int flash_attn(const bf16* qkv, bf16* ctx, int N, int T, int H, cudaStream_t st);
+int flash_attn_tc(const bf16* qkv, bf16* ctx, int N, int T, int H, cudaStream_t st);    // tcgen05 (flash_attn_tc.cu)
 
 // hs fp32 [N, F, 768] -> linear interpolation to L frames -> bf16 [N*L, 768]
 int interp768_bf16(const float* hs, int N, int F, int L, bf16* out, cudaStream_t st);

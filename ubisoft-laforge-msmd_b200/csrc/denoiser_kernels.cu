@@ -333,163 +333,6 @@ int ln_row0_launch(const bf16* y0, const bf16* resid0, const float* g, const flo
   return MSMD_OK;
 }
 
-// ------------------------------------------------------------------------------------------- self attention
-// One CTA per (sequence, head): T <= 112 tokens, head dim 64.  S = Q K^T and O = P V on mma.sync
-// m16n8k16 bf16 (the whole problem is one 112x112x64 tile, 3% of the layer's FLOPs); softmax in fp32.
-__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-
-constexpr int kAttT = 112, kAttDh = 64, kQKStride = 72;
-constexpr int kAttBuf = 3 * kAttT * kQKStride;   // bf16 elements of one (Q,K,V) buffer
-
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem)
-               : "memory");
-}
-
-// One CTA per sequence, looping over its heads: the (Q,K,V) tile of head h+1 streams into the second
-// shared-memory buffer with cp.async while head h is computed, so loads and MMAs overlap and every SM keeps
-// ~2 x 42 KB of loads in flight.
-constexpr int kAttHeadsPerCta = 4;   // 2*S*H/4 CTAs: enough CTAs to balance 148 SMs, enough heads to overlap loads
-__global__ void __launch_bounds__(224, 2) self_attn_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ ctx, int T,
-                                                           int H) {
-  extern __shared__ __align__(16) bf16 att_smem[];
-  griddep_launch();
-  griddep_wait();
-  const int s = blockIdx.x;
-  const int d = H * kAttDh;
-  const int tid = threadIdx.x;
-  const bf16* base = qkv + (int64_t)s * T * 3 * d;
-  // rows >= T stay zero in both buffers (the loads below never touch them)
-  for (int i = tid; i < 2 * kAttBuf / 8; i += blockDim.x) reinterpret_cast<uint4*>(att_smem)[i] = make_uint4(0, 0, 0, 0);
-  __syncthreads();
-  auto issue = [&](int h) {
-    bf16* buf = att_smem + (h & 1) * kAttBuf;
-    for (int idx = tid; idx < T * 8; idx += blockDim.x) {
-      const int row = idx >> 3, ch = idx & 7;
-      const bf16* src = base + (int64_t)row * 3 * d + h * kAttDh + ch * 8;
-      bf16* dst = buf + row * kQKStride + ch * 8;
-      cp_async16(dst, src);                                    // q
-      cp_async16(dst + kAttT * kQKStride, src + d);            // k
-      cp_async16(dst + 2 * kAttT * kQKStride, src + 2 * d);    // v
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  };
-  const int h_begin = blockIdx.y * kAttHeadsPerCta, h_end = min(H, h_begin + kAttHeadsPerCta);
-  issue(h_begin);
-
-  const int warp = tid >> 5, lane = tid & 31;
-  const int g = lane >> 2, t = lane & 3;
-  const int r0 = warp * 16;
-  for (int h = h_begin; h < h_end; ++h) {
-    if (h + 1 < h_end) {
-      issue(h + 1);
-      asm volatile("cp.async.wait_group 1;" ::: "memory");
-    } else {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-    }
-    __syncthreads();
-    const bf16* sQ = att_smem + (h & 1) * kAttBuf;
-    const bf16* sK = sQ + kAttT * kQKStride;
-    const bf16* sV = sK + kAttT * kQKStride;
-
-    uint32_t aq[4][4];
-#pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {
-      aq[ks][0] = *reinterpret_cast<const uint32_t*>(&sQ[(r0 + g) * kQKStride + ks * 16 + 2 * t]);
-      aq[ks][1] = *reinterpret_cast<const uint32_t*>(&sQ[(r0 + g + 8) * kQKStride + ks * 16 + 2 * t]);
-      aq[ks][2] = *reinterpret_cast<const uint32_t*>(&sQ[(r0 + g) * kQKStride + ks * 16 + 8 + 2 * t]);
-      aq[ks][3] = *reinterpret_cast<const uint32_t*>(&sQ[(r0 + g + 8) * kQKStride + ks * 16 + 8 + 2 * t]);
-    }
-    float sc[14][4];
-#pragma unroll
-    for (int j = 0; j < 14; ++j) {
-      sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f;
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
-        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&sK[(j * 8 + g) * kQKStride + ks * 16 + 2 * t]);
-        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&sK[(j * 8 + g) * kQKStride + ks * 16 + 8 + 2 * t]);
-        mma_bf16_16816(sc[j], aq[ks], b0, b1);
-      }
-    }
-    // softmax over keys (columns): thread holds cols j*8+2t, +1 of rows g (regs 0,1) and g+8 (regs 2,3)
-    const float kScale = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
-    float m0 = -INFINITY, m1 = -INFINITY;
-#pragma unroll
-    for (int j = 0; j < 14; ++j) {
-      const int c = j * 8 + 2 * t;
-      if (c >= T) { sc[j][0] = -INFINITY; sc[j][2] = -INFINITY; }
-      if (c + 1 >= T) { sc[j][1] = -INFINITY; sc[j][3] = -INFINITY; }
-      m0 = fmaxf(m0, fmaxf(sc[j][0], sc[j][1]));
-      m1 = fmaxf(m1, fmaxf(sc[j][2], sc[j][3]));
-    }
-    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
-    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
-    float l0 = 0.f, l1 = 0.f;
-#pragma unroll
-    for (int j = 0; j < 14; ++j) {
-      sc[j][0] = exp2f((sc[j][0] - m0) * kScale); sc[j][1] = exp2f((sc[j][1] - m0) * kScale);
-      sc[j][2] = exp2f((sc[j][2] - m1) * kScale); sc[j][3] = exp2f((sc[j][3] - m1) * kScale);
-      l0 += sc[j][0] + sc[j][1];
-      l1 += sc[j][2] + sc[j][3];
-    }
-    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-
-    float o[8][4];
-#pragma unroll
-    for (int n = 0; n < 8; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
-#pragma unroll
-    for (int kb = 0; kb < 7; ++kb) {
-      uint32_t ap[4];
-      ap[0] = pack_bf16(sc[2 * kb][0], sc[2 * kb][1]);
-      ap[1] = pack_bf16(sc[2 * kb][2], sc[2 * kb][3]);
-      ap[2] = pack_bf16(sc[2 * kb + 1][0], sc[2 * kb + 1][1]);
-      ap[3] = pack_bf16(sc[2 * kb + 1][2], sc[2 * kb + 1][3]);
-      // V is [key][dh] row-major: ldmatrix.trans hands out the (k = key, n = dh) B fragments, two dh tiles per x4
-#pragma unroll
-      for (int n2 = 0; n2 < 4; ++n2) {
-        const int mrow = kb * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
-        const int mcol = (2 * n2 + (lane >> 4)) * 8;
-        uint32_t b0, b1, b2, b3;
-        const uint32_t addr = (uint32_t)__cvta_generic_to_shared(&sV[mrow * kQKStride + mcol]);
-        asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
-                     : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3) : "r"(addr));
-        mma_bf16_16816(o[2 * n2], ap, b0, b1);
-        mma_bf16_16816(o[2 * n2 + 1], ap, b2, b3);
-      }
-    }
-    const float i0 = 1.0f / l0, i1 = 1.0f / l1;
-    const int row_a = r0 + g, row_b = r0 + g + 8;
-#pragma unroll
-    for (int n = 0; n < 8; ++n) {
-      const int col = h * kAttDh + n * 8 + 2 * t;
-      if (row_a < T)
-        *reinterpret_cast<uint32_t*>(ctx + ((int64_t)s * T + row_a) * d + col) = pack_bf16(o[n][0] * i0, o[n][1] * i0);
-      if (row_b < T)
-        *reinterpret_cast<uint32_t*>(ctx + ((int64_t)s * T + row_b) * d + col) = pack_bf16(o[n][2] * i1, o[n][3] * i1);
-    }
-    __syncthreads();   // every warp is done with this buffer before head h+2 streams into it
-  }
-}
-int self_attn_launch(const bf16* qkv, bf16* ctx, int S, int T, int H, cudaStream_t st) {
-  MSMD_REQUIRE(T <= kAttT, "self_attn: sequence length %d exceeds the %d-token tile", T, kAttT);
-  constexpr int smem = 2 * kAttBuf * (int)sizeof(bf16);
-  static bool attr = false;
-  if (!attr) {
-    MSMD_CHECK_CUDA(cudaFuncSetAttribute(self_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr = true;
-  }
-  ProfileScope prof("self_attn", st);
-  MSMD_CHECK_CUDA(launch_pdl(self_attn_kernel, dim3(S, cdiv(H, kAttHeadsPerCta)), dim3(224), smem, st, qkv, ctx, T, H));
-  MSMD_CHECK_LAUNCH();
-  return MSMD_OK;
-}
-
 // ------------------------------------------------------------------------------------------- row-0 cross attention
 // Person token (query row 0) over the Tk memory tokens (nn.MultiheadAttention inside _mha_block): one warp per
 // (sequence, head), no shared memory and no barriers.  K: lane j of key group g reads its key's 128-byte head

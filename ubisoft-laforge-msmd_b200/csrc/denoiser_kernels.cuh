@@ -58,8 +58,6 @@ int ln_launch(const LnParams& p, cudaStream_t st);
 int ln_row0_launch(const bf16* y0, const bf16* resid0, const float* g, const float* b, bf16* out, bf16* out_c, int S,
                    int T, int d, int fp16, cudaStream_t st);
 
-// self-attention over T <= 112 tokens, head dim 64: qkv [S*T, 3*d] bf16 (q|k|v) -> ctx [S*T, d] bf16
-int self_attn_launch(const bf16* qkv, bf16* ctx, int S, int T, int H, cudaStream_t st);
 // row-0 cross attention: q0 [S,d]; kv [S*Tk, 2d] (k|v) -> ctx0 [S,d]
 int cross_attn_row0_launch(const bf16* q0, const bf16* kv, bf16* ctx0, int S, int Tk, int H, int fp16, cudaStream_t st);
 
@@ -107,7 +105,7 @@ int row0_fused_launch(const bf16* x0c, const bf16* Wq, const float* bq, const bf
 int split_parts_launch(const float* dec, const float* stat, float* dyn, float* sta, float* alphas, int S, int T, int dm,
                        int nb, int ldd, cudaStream_t st);
 
-// tcgen05 self-attention (attn_tc.cu): same contract as self_attn_launch
+// tcgen05 self-attention (attn_tc.cu) over T <= 112 tokens, head dim 64: qkv [S*T, 3*d] (q|k|v) -> ctx [S*T, d], 16-bit storage
 int self_attn_tc_launch(const bf16* qkv, bf16* ctx, int S, int T, int H, int fp16, cudaStream_t st);
 
 // ---- fp32-grade variants (denoiser_f32.cu) ----

@@ -300,7 +300,7 @@ extern "C" int msmd_style_encode(msmd_style* m, const float* motion, int N, int 
   // TransformerEncoderLayer (post-LN): self-attention block
   const int M = N * L;
   if ((rc = gemm(m->xc, d, m->Wqkv, d, m->bqkv, nullptr, 0, m->qkv, 3 * d, 0, M, 3 * d, d, 0, st))) return rc;
-  if ((rc = self_attn_launch(m->qkv, m->ctx, N, L, 8, st))) return rc;
+  if ((rc = self_attn_tc_launch(m->qkv, m->ctx, N, L, 8, 0, st))) return rc;      // tcgen05 (attn_tc.cu), bf16 storage
   if ((rc = gemm(m->ctx, d, m->Wo, d, m->bo, m->xc, d, m->y, d, 1, M, d, d, 0, st))) return rc;
   lp.in = m->y; lp.in_stride = L; lp.in_off = 0; lp.elu = 0; lp.g = m->g_n1; lp.b = m->be_n1; lp.add = nullptr;
   lp.out = m->xc; lp.out_stride = L; lp.out_off = 0; lp.zero_pad = 0;
