@@ -90,6 +90,7 @@ struct msmd_model {
   // (format, S, NX, E, thresholding).  Nothing caller-owned is baked into a graph, so it is reused by every later
   // window / call of the same shape; the capture stream is created once here.
   UpdateParams* d_up = nullptr;
+  unsigned int* d_done = nullptr;   // block-completion counter of the update kernel
   cudaStream_t cap_stream = nullptr;
   typedef std::tuple<int, int, int, int, int, float, float, float> GraphKey;
   std::map<GraphKey, cudaGraphExec_t> graphs;
@@ -359,7 +360,7 @@ extern "C" int msmd_create(const msmd_config* cfg, int device, msmd_model** out)
   A(&m->thr, S);
   A(&m->xbuf, S * c.n_motions * c.motion_dim); A(&m->mixed, S * (T - 1) * c.motion_dim); A(&m->steps, S);
   A(&m->w_audio, S * c.n_motions * d); A(&m->w_prev_audio, S * c.n_prev_motions * d); A(&m->w_ind, S * c.n_motions);
-  A(&m->d_up, 1);
+  A(&m->d_up, 1); A(&m->d_done, 1);
   if (has_bf16(c) || has_fp16(c)) {
     A(&m->x, M * d); A(&m->qkv, M * 3 * d); A(&m->ctx, M * d); A(&m->h, M * c.d_ff); A(&m->dec1, M * d / 2);
     A(&m->x0c, S * d); A(&m->q0, S * d); A(&m->ctx0, S * d); A(&m->y, M * d); A(&m->y0, S * d);
@@ -391,6 +392,7 @@ extern "C" int msmd_create(const msmd_config* cfg, int device, msmd_model** out)
   }
   if (rc) { msmd_destroy(m); return rc; }
   cudaMemset(m->dec2, 0, M * m->ldd * sizeof(float));
+  cudaMemset(m->d_done, 0, sizeof(unsigned int));
   if (m->overflow) cudaMemset(m->overflow, 0, sizeof(int));
   *out = m;
   return MSMD_OK;
@@ -683,6 +685,7 @@ extern "C" int msmd_sample_window_ex(msmd_model* m, const float* x_T, const floa
   up.nb = c.n_basis; up.ldd = m->ldd; up.cfg_independent = cfg_independent; up.target_noise = c.target_noise;
   up.thr = nullptr; up.tgt_dyn = nullptr; up.cum_static = nullptr; up.alpha_traj = nullptr; up.t_start = t_start;
   up.overflow = k32 > 0 ? m->overflow : nullptr;
+  up.done = m->d_done; up.steps_rw = m->steps; up.S = m->S;
   bool use_dt = false;
   float dt_ratio = 0.f, dt_min = 0.f, dt_max = 0.f;
   if (ex) {
@@ -703,8 +706,7 @@ extern "C" int msmd_sample_window_ex(msmd_model* m, const float* x_T, const floa
     if (use_dt && (r = threshold_launch(m->dec2, m->stat, m->thr, m->S, m->T, c.n_motions, c.n_prev_motions, c.motion_dim,
                                         c.n_basis, m->ldd, dt_ratio, dt_min, dt_max, s)))
       return r;
-    if ((r = update_launch(m->d_up, m->NX, c.n_motions, c.motion_dim, s))) return r;
-    return steps_advance(m->steps, m->S, s);
+    return update_launch(m->d_up, m->NX, c.n_motions, c.motion_dim, s);     // also advances the step index
   };
 
   // n consecutive steps of one 16-bit path: replays of ONE captured step (the step index lives in device memory, the

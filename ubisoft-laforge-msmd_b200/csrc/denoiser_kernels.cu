@@ -115,13 +115,11 @@ int build_memory_h16(const float* prev_audio, const float* audio, bf16* mem, int
 }
 
 // ------------------------------------------------------------------------------------------- embeddings
-// rows 0..Lp: person token (+ timestep embedding) and the projected previous-motion context
+// rows 0..Lp: person token (+ timestep embedding) and the projected previous-motion context (one block per row; the
+// blocks past the x-row blocks of the fused embed kernel below)
 template <bool F16>
-__global__ void embed_ctx_kernel(EmbedParams p) {
-  griddep_launch();
-  griddep_wait();
+__device__ __forceinline__ void embed_ctx_rows(const EmbedParams& p, int row) {
   const int T = 1 + p.Lp + p.L;
-  const int row = blockIdx.x;  // s * (Lp+1) + i
   const int s = row / (p.Lp + 1), i = row % (p.Lp + 1);
   const int t = p.steps[s];
   for (int c = threadIdx.x; c < p.d; c += blockDim.x) {
@@ -142,6 +140,10 @@ __global__ void __launch_bounds__(256, 2) embed_x_kernel(EmbedParams p) {
   extern __shared__ __align__(16) float xs[];  // [dm][kEmbedPitch] x values (frame-minor), then [E][kEmbedPitch] indicators
   const int T = 1 + p.Lp + p.L;
   const int blocks_per_x = (p.L + kEmbedRows - 1) / kEmbedRows;
+  if ((int)blockIdx.x >= p.NX * blocks_per_x) {      // context rows ride in the same launch (one launch fewer per step)
+    embed_ctx_rows<F16>(p, (int)blockIdx.x - p.NX * blocks_per_x);
+    return;
+  }
   const int n = blockIdx.x / blocks_per_x;
   const int l0 = (blockIdx.x % blocks_per_x) * kEmbedRows;
   const int nr = min(kEmbedRows, p.L - l0);
@@ -206,9 +208,7 @@ __global__ void __launch_bounds__(256, 2) embed_x_kernel(EmbedParams p) {
 }
 int embed_launch(const EmbedParams& p, cudaStream_t st) {
   ProfileScope prof("embed", st);
-  MSMD_CHECK_CUDA(launch_pdl(p.fp16 ? embed_ctx_kernel<true> : embed_ctx_kernel<false>, dim3(p.S * (p.Lp + 1)), dim3(128), 0, st, p));
-  MSMD_CHECK_LAUNCH();
-  const int blocks = p.NX * ((p.L + kEmbedRows - 1) / kEmbedRows);
+  const int blocks = p.NX * ((p.L + kEmbedRows - 1) / kEmbedRows) + p.S * (p.Lp + 1);
   MSMD_CHECK_CUDA(launch_pdl(p.fp16 ? embed_x_kernel<true> : embed_x_kernel<false>, dim3(blocks), dim3(256),
                              (p.dm + 3) * kEmbedPitch * sizeof(float), st, p));
   MSMD_CHECK_LAUNCH();
@@ -531,6 +531,21 @@ __global__ void __launch_bounds__(256) update_kernel(const UpdateParams* __restr
       p.alpha_traj[(((int64_t)(p.t_start - t) * p.NX + n) * p.L + l) * p.nb + c] = ta;
     }
   }
+  // step index t -> t - 1 for the next step, by the LAST block to finish (every block has read t by then): the separate
+  // one-thread-block "advance" launch of round 1 is gone
+  if (p.done != nullptr) {
+    __shared__ bool last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      last = atomicAdd(p.done, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last) {
+      for (int i = threadIdx.x; i < p.S; i += blockDim.x) p.steps_rw[i] = t - 1;
+      if (threadIdx.x == 0) *p.done = 0u;
+    }
+  }
 }
 
 // Dynamic thresholding (model.py:396-402): one CTA per sequence; |x0_hat| of the L motion rows in shared memory,
@@ -613,23 +628,11 @@ __global__ void steps_set_kernel(int* steps, int S, int v) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < S) steps[i] = v;
 }
-__global__ void steps_advance_kernel(int* steps, int S) {
-  griddep_launch();
-  griddep_wait();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < S) steps[i] -= 1;
-}
 int steps_set(int* steps, int S, int value, cudaStream_t st) {
   steps_set_kernel<<<cdiv(S, 256), 256, 0, st>>>(steps, S, value);
   MSMD_CHECK_LAUNCH();
   return MSMD_OK;
 }
-int steps_advance(int* steps, int S, cudaStream_t st) {
-  MSMD_CHECK_CUDA(launch_pdl(steps_advance_kernel, dim3(cdiv(S, 256)), dim3(256), 0, st, steps, S));
-  MSMD_CHECK_LAUNCH();
-  return MSMD_OK;
-}
-
 __global__ void mix_static_kernel(const float* __restrict__ dec, const float* __restrict__ stat, float* __restrict__ out,
                                   int S, int T, int dm, int nb, int ldd) {
   const int64_t n_el = (int64_t)S * (T - 1) * dm;

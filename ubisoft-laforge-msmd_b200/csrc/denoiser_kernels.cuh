@@ -81,6 +81,9 @@ struct UpdateParams {
   float* cum_static;      // [NX, L, dm] += c1 * CFG-combined static part, or null
   float* alpha_traj;      // [n_steps, NX, L, nb] CFG-combined alphas per executed step (index t_start - t), or null
   int t_start;
+  unsigned int* done;     // block-completion counter (zeroed): the last block writes steps_rw[0..S) = t - 1, or null
+  int* steps_rw;          // [S] same array as `steps`
+  int S;
   long long noise_offset; // added to the element index that keys the in-kernel Philox noise (= global clip id * L * dm)
   const int* overflow;    // fp32-grade steps: device flag raised by the operand split; non-zero poisons x with NaN
 };
@@ -91,7 +94,6 @@ int threshold_launch(const float* dec, const float* stat, float* thr, int S, int
 int update_params_set(UpdateParams* d_dst, const UpdateParams& p, cudaStream_t st);
 int update_launch(const UpdateParams* d_p, int NX, int L, int dm, cudaStream_t st);
 int steps_set(int* steps, int S, int value, cudaStream_t st);
-int steps_advance(int* steps, int S, cudaStream_t st);
 
 // out[S, T-1... ] : x̂0 per sequence (module-level parity): dyn + static mix for ALL Lp+L rows -> [S, T-1, dm]
 int mix_static_launch(const float* dec, const float* stat, float* out, int S, int T, int dm, int nb, int ldd, cudaStream_t st);

@@ -34,8 +34,9 @@ constexpr int kOffQs = kOffXs + kNB * kD * 2;
 constexpr int kOffCs = kOffQs + kNB * kDh * 4;
 constexpr int kOffPo = kOffCs + kNB * kDh * 4;
 constexpr int kOffSt = kOffPo + kNB * kD * 4;
-constexpr int kOffPt = kOffSt + 2 * kHeads * kNB * 4;
-constexpr int kSmem = kOffPt + kNB * 66 * 4;
+constexpr int kSmem = kOffSt + 2 * kHeads * kNB * 4;
+constexpr int kMaxGroup = 7;            // sequences per cluster: their 16 x 66-float attention partials share the 32 KB po buffer
+static_assert(kMaxGroup * 16 * 66 * 4 <= kNB * kD * 4, "attention partials must fit the partial-projection buffer");
 static_assert(kSmem <= 227 * 1024, "row0_fused shared memory");
 
 struct Row0Params {
@@ -127,7 +128,6 @@ __global__ void __cluster_dims__(kHeads, 1, 1) __launch_bounds__(kThreads, 1) ro
   float* cs = reinterpret_cast<float*>(sm + kOffCs);
   float* po = reinterpret_cast<float*>(sm + kOffPo);
   float* st = reinterpret_cast<float*>(sm + kOffSt);   // [2][kHeads][kNB]
-  float* parts = reinterpret_cast<float*>(sm + kOffPt); // [16 warps][m, l, o(64)] attention partials
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int h = (int)ctarank();
   const int cid = blockIdx.x / kHeads, ncl = gridDim.x / kHeads;
@@ -149,8 +149,8 @@ __global__ void __cluster_dims__(kHeads, 1, 1) __launch_bounds__(kThreads, 1) ro
   asm volatile("cp.async.commit_group;" ::: "memory");
   griddep_wait();
 
-  for (int s0 = s_begin; s0 < s_end; s0 += kNB) {
-    const int n = min(kNB, s_end - s0);
+  for (int s0 = s_begin; s0 < s_end; s0 += kMaxGroup) {
+    const int n = min(kMaxGroup, s_end - s0);
     // ---- phase 0b: x0c rows of the group (zero-padded to kNB) + L2 prefetch of this head's K / V lines
     for (int i = tid; i < kNB * (kD / 8); i += kThreads) {
       const int s = i >> 6, c = i & 63;
@@ -206,96 +206,71 @@ __global__ void __cluster_dims__(kHeads, 1, 1) __launch_bounds__(kThreads, 1) ro
     }
     __syncthreads();
 
-    // ---- phase 2: attention of head h.  W = 16 / pow2ceil(n) warps share a sequence (all 16 warps stay busy when the
-    // group is small - the batch-1 latency regime): warp (seq, part) owns the keys [part * KP, (part + 1) * KP) and
-    // produces a partial (max, sum, P V); the parts are merged below.  Lane owns keys lane, lane + 32, ... of its range.
+    // ---- phase 2: attention of head h.  The Tk <= 128 keys are ALWAYS cut into 16 parts of 8 keys, warp w = part w of
+    // every sequence of the group: each part yields a partial (max, sum, P V) and the parts are merged in a fixed
+    // order below - the arithmetic of a sequence does not depend on how many sequences share the cluster, so a clip's
+    // codes are bit-identical whatever batch it is sampled in.  (All 16 warps stay busy even for a single sequence:
+    // the batch-1 latency regime.)  Lane j < 8 scores key 8w + j; every lane owns two of the 64 head dims for P V.
+    // The partials live in the (not yet used) partial-projection buffer: n <= kMaxGroup sequences per group.
     r0_stamp(p.trace, 2);
-    int npow = 1;
-    while (npow < n) npow <<= 1;
-    const int W = kNB / npow, KP = 128 / W;
+    float* parts = po;                              // [n][16 parts][66]: m, l, o(64)
     {
-      const int seq = warp / W, part = warp % W;
-      const int base = part * KP;
-      const int nk = seq < n ? max(0, min(KP, p.Tk - base)) : 0;   // keys of this warp
-      const int s = s0 + min(seq, n - 1);
-      const bf16* kbase = p.kv + ((int64_t)s * p.Tk + base) * (2 * kD) + h * kDh;
-      float sc[4];
-      {
-        float q[kDh];
+      const int part = warp, base = part * 8;
+      const int nk = max(0, min(8, p.Tk - base));   // keys of this part
+      for (int seq = 0; seq < n; ++seq) {
+        const bf16* kbase = p.kv + ((int64_t)(s0 + seq) * p.Tk + base) * (2 * kD) + h * kDh;
+        float dot = -INFINITY;
+        uint4 kr[8];
+        if (lane < nk) {
+          const uint4* kp = reinterpret_cast<const uint4*>(kbase + (int64_t)lane * (2 * kD));
 #pragma unroll
-        for (int i = 0; i < kDh / 4; ++i) {
-          const float4 t = *reinterpret_cast<const float4*>(qs + min(seq, kNB - 1) * kDh + 4 * i);   // broadcast
-          q[4 * i] = t.x; q[4 * i + 1] = t.y; q[4 * i + 2] = t.z; q[4 * i + 3] = t.w;
+          for (int i = 0; i < 8; ++i) kr[i] = __ldg(kp + i);
         }
+        // V rows of the part's keys: one coalesced 128-byte warp load per key, issued before the scores are needed
+        const uint32_t* vbase = reinterpret_cast<const uint32_t*>(kbase + kD) + lane;
+        uint32_t vr[8];
 #pragma unroll
-        for (int grp = 0; grp < 4; ++grp) {
-          const int j = grp * 32 + lane;
-          float dot = -INFINITY;
-          if (j < nk) {
-            const uint4* kp = reinterpret_cast<const uint4*>(kbase + (int64_t)j * (2 * kD));
-            uint4 kr[8];
+        for (int u = 0; u < 8; ++u) vr[u] = u < nk ? __ldg(vbase + (int64_t)u * kD) : 0u;
+        if (lane < nk) {
+          float a = 0.f;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) kr[i] = __ldg(kp + i);
-            float a = 0.f;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              float kf[8];
-              up8<F16>(kr[i], kf);
-#pragma unroll
-              for (int k = 0; k < 8; ++k) a = fmaf(q[8 * i + k], kf[k], a);
-            }
-            dot = a * 0.125f;
+          for (int i = 0; i < 8; ++i) {
+            float kf[8];
+            up8<F16>(kr[i], kf);
+            const float4 qa = *reinterpret_cast<const float4*>(qs + seq * kDh + 8 * i);
+            const float4 qb = *reinterpret_cast<const float4*>(qs + seq * kDh + 8 * i + 4);
+            a = fmaf(qa.x, kf[0], a); a = fmaf(qa.y, kf[1], a); a = fmaf(qa.z, kf[2], a); a = fmaf(qa.w, kf[3], a);
+            a = fmaf(qb.x, kf[4], a); a = fmaf(qb.y, kf[5], a); a = fmaf(qb.z, kf[6], a); a = fmaf(qb.w, kf[7], a);
           }
-          sc[grp] = dot;
+          dot = a * 0.125f;
         }
+        const float m = wmax(dot);
+        const float pj = (dot == -INFINITY) ? 0.f : __expf(dot - m);
+        const float l = wsum(pj);
+        float oa = 0.f, ob = 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const float pu = __shfl_sync(0xffffffffu, pj, u);
+          const float2 f = up2<F16>(vr[u]);
+          oa = fmaf(pu, f.x, oa);
+          ob = fmaf(pu, f.y, ob);
+        }
+        float* pt = parts + (seq * 16 + part) * 66;
+        if (lane == 0) { pt[0] = m; pt[1] = l; }
+        *reinterpret_cast<float2*>(pt + 2 + 2 * lane) = make_float2(oa, ob);
       }
-      const float m = wmax(fmaxf(fmaxf(sc[0], sc[1]), fmaxf(sc[2], sc[3])));
-      float l = 0.f;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) { sc[i] = (sc[i] == -INFINITY) ? 0.f : __expf(sc[i] - m); l += sc[i]; }
-      l = wsum(l);
-      // V: lane owns head dims 2*lane, 2*lane+1; a key's 128-byte slice is one coalesced warp load
-      const uint32_t* vbase = reinterpret_cast<const uint32_t*>(kbase + kD) + lane;
-      float oa = 0.f, ob = 0.f;
-      constexpr int VB = 28, NVB = 5;           // 5 x 28 >= 128 keys; batches beyond the warp's keys issue no loads
-      uint32_t vb[2][VB];
-      auto load_v = [&](int b, uint32_t (&dst)[VB]) {
-#pragma unroll
-        for (int u = 0; u < VB; ++u) {
-          const int j = b * VB + u;
-          dst[u] = j < nk ? __ldg(vbase + (int64_t)j * kD) : 0u;     // one key row = 2*kD halfs = kD uint32
-        }
-      };
-      auto consume = [&](int b, const uint32_t (&src)[VB]) {
-#pragma unroll
-        for (int u = 0; u < VB; ++u) {
-          const int j = b * VB + u;
-          const float pj = __shfl_sync(0xffffffffu, sc[j >> 5], j & 31);
-          const float2 f = up2<F16>(src[u]);
-          oa = fmaf(pj, f.x, oa);
-          ob = fmaf(pj, f.y, ob);
-        }
-      };
-      load_v(0, vb[0]);
-#pragma unroll
-      for (int b = 0; b < NVB; ++b) {
-        if (b + 1 < NVB && (b + 1) * VB < nk) load_v(b + 1, vb[(b + 1) & 1]);
-        if (b * VB < nk) consume(b, vb[b & 1]);
-      }
-      // partial of this warp: [m, l, o(64)]
-      float* pt = parts + warp * 66;
-      if (lane == 0) { pt[0] = m; pt[1] = l; }
-      *reinterpret_cast<float2*>(pt + 2 + 2 * lane) = make_float2(oa, ob);
     }
     __syncthreads();
-    if (warp < kNB) {      // merge the W parts of sequence `warp` (flash-style rescale); padded sequences give zeros
+    if (warp < kNB) {      // merge the 16 parts of sequence `warp` (flash-style rescale); padded sequences give zeros
       float2 o = make_float2(0.f, 0.f);
       if (warp < n) {
         float M = -INFINITY;
-        for (int w = 0; w < W; ++w) M = fmaxf(M, parts[(warp * W + w) * 66]);
+#pragma unroll
+        for (int w = 0; w < 16; ++w) M = fmaxf(M, parts[(warp * 16 + w) * 66]);
         float l = 0.f;
-        for (int w = 0; w < W; ++w) {
-          const float* pt = parts + (warp * W + w) * 66;
+#pragma unroll
+        for (int w = 0; w < 16; ++w) {
+          const float* pt = parts + (warp * 16 + w) * 66;
           const float sc_w = pt[1] > 0.f ? __expf(pt[0] - M) : 0.f;
           const float2 t = *reinterpret_cast<const float2*>(pt + 2 + 2 * lane);
           l = fmaf(pt[1], sc_w, l);
@@ -385,7 +360,7 @@ __global__ void __cluster_dims__(kHeads, 1, 1) __launch_bounds__(kThreads, 1) ro
       }
     }
     r0_stamp(p.trace, 6);
-    if (s0 + kNB < s_end) cluster_barrier();   // the next group overwrites po / st: every remote read of this one is done
+    if (s0 + kMaxGroup < s_end) cluster_barrier();   // the next group overwrites po / st: every remote read of this one is done
   }
 }
 
