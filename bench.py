@@ -597,6 +597,16 @@ def main():
                         d2h_bytes_per_step=d2h),
                gpu_launches=wl.launches_per_step() * a.steps,
                roofline=wl.roofline(peaks, kernel_ms) if kernel_ms > 0 else None)
+    if a.workload == 'clips1024' and rank == 0:
+        # every clip's codes + vertices arrived in rank 0's pinned host buffers (written by the LAST timed step)
+        torch.cuda.synchronize()
+        ho, hv = wl.host_out, wl.host_verts
+        per_clip = hv.reshape(hv.shape[0], -1).abs().amax(1)
+        ok = bool(torch.isfinite(ho).all()) and bool((per_clip > 0).all()) and bool(torch.isfinite(per_clip).all())
+        codes0, verts0 = wl._run(wl.dev, 0, min(wl.chunk, wl.hi - wl.lo))       # rank 0's first chunk, recomputed
+        same = torch.equal(codes0.cpu(), ho[:codes0.shape[0]]) and torch.equal(verts0.cpu(), hv[:verts0.shape[0]])
+        out['gather_check'] = dict(all_clips_present_and_finite=ok, first_chunk_bit_identical_to_recompute=bool(same),
+                                   clips=int(ho.shape[0]), host_bytes=int(ho.numel() * 4 + hv.numel() * 4))
     if a.workload == 'latency1':
         out['latency'] = dict(ms_per_clip=ms / a.steps, ms_per_clip_e2e=ms_e2e / a.steps,
                               us_per_sampling_step=out['roofline']['sampling_step']['us'] if out['roofline'] else None,
