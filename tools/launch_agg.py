@@ -7,7 +7,7 @@ hdr = rows[hi]; kn = hdr.index('Kernel Name'); mv = hdr.index('Metric Value')
 recs = [(r[kn], float(r[mv].replace(',', ''))) for r in rows[hi + 1:] if len(r) > mv]
 names = [r[0] for r in recs]
 upd = [i for i, n in enumerate(names) if 'update_kernel' in n]
-a, b = upd[-2] + 2, upd[-1] + 2
+a, b = upd[-2] + 1, upd[-1] + 1        # a step ends with its update kernel (which also advances the step index)
 agg = collections.OrderedDict()
 for n, v in recs[a:b]:
     key = n.split('(')[0][:100]
