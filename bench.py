@@ -281,8 +281,7 @@ class SamplerWorkload:
         return n * self.frames / 25.0
 
     def launches_per_step(self):
-        n_seq = 3 * min(self.chunk, self.hi - self.lo)
-        per_layer = 8 if n_seq <= 96 else 11           # fused person-token block (1 launch) up to 96 sequences, else 4
+        per_layer = 8                                    # QKV, self-attn, out-proj, LN1/LN2, person-token block, FF1, FF2, LN3
         per_denoise = 1 + 8 * per_layer + 2 + 1          # embed + layers + motion_dec(2) + update (advances the step index)
         batches = 1 if not self.total_clips else -(-(self.hi - self.lo) // self.chunk)
         return batches * (self.n_sub * (500 * per_denoise + 8 * 2 + 12) + 3 + 118 + 22)   # + audio encoder + style encoder

@@ -24,7 +24,7 @@ using namespace msmd;
 
 namespace {
 
-constexpr int kRow0FusedMaxS = 96;
+constexpr int kRow0FusedMaxS = 1 << 30;   // every batch size (MSMD_ROW0_FUSED_MAX_S=n: the four-launch chain above n sequences)
 
 struct LayerW {
   bf16 *Wqkv = nullptr, *Wo = nullptr, *Wq0 = nullptr, *Wkv = nullptr, *Wco = nullptr, *W1 = nullptr, *W2 = nullptr;
@@ -249,9 +249,8 @@ int run_forward(msmd_model* m, const float* xrows, cudaStream_t st, int fmt) {
     lp.y = m->y; lp.g1 = w.g1; lp.b1 = w.be1; lp.add = ca; lp.g2 = w.g2; lp.b2 = w.be2; lp.out = m->x;
     lp.x0 = m->x0c; lp.skip_tok0 = 0; lp.M = M; lp.T = T; lp.d = d; lp.fp16 = fmt;
     if ((rc = ln_launch(lp, st))) return rc;
-    // person token (row 0): real cross attention over the memory (_mha_block) + norm2.  Up to kRow0FusedMaxS sequences:
-    // one cluster kernel (3 launches fewer per layer - the launch-bound regimes); above, the HBM-bound K/V read of the
-    // attention dominates and the four-launch chain, which spreads it over every SM, is faster (measured).
+    // person token (row 0): real cross attention over the memory (_mha_block) + norm2 as one cluster kernel
+    // (row0_fused.cu); the four-launch chain it replaced is kept behind MSMD_ROW0_FUSED_MAX_S for A/B runs.
     static const int row0_max_s = [] { const char* e = getenv("MSMD_ROW0_FUSED_MAX_S"); return e ? atoi(e) : kRow0FusedMaxS; }();
     if (S <= row0_max_s) {
       if ((rc = row0_fused_launch(m->x0c, static_cast<const bf16*>(Wq0), w.bq0, kv, static_cast<const bf16*>(Wco), w.bco, w.g2,

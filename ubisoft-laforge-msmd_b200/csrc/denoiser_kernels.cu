@@ -5,6 +5,7 @@
 // warp-shuffle reductions, fp32 statistics.
 #include "denoiser_kernels.cuh"
 #include "profile.cuh"
+#include <cstdlib>
 
 namespace msmd {
 
@@ -255,47 +256,115 @@ __device__ __forceinline__ void load_h4(const bf16* src, float* v) {
   else { v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; }
 }
 
-template <int D, bool F16>
+// LayerNorm chain of the post-LN layers: out = LN2(LN1(y + resid) + add) (LN3: out = LN(y + resid)).  Inside the replayed
+// step y and the residual stream come out of L2 (ncu --cache-control none: 90% L2 hits, 2.5 MB of DRAM traffic), so the
+// kernel is bound by instruction issue and load latency, not by HBM.  Hence: a warp owns kLnRows consecutive rows;
+// a lane owns two 16-byte chunks of a row (8 + 8 of the 512 features: a quarter of the load instructions of the 8-byte
+// version); gamma / beta sit in shared memory (read once per CTA instead of once per row); the raw 16-bit words of the NEXT
+// row are in flight while the current one is normalised; statistics are fp32, two-pass, in registers.
+template <bool F16>
+__device__ __forceinline__ void ln_unpack8(const uint4& u, float* v, bool add) {
+  const float2 a = unpack_h<F16>(u.x), b = unpack_h<F16>(u.y), c = unpack_h<F16>(u.z), d = unpack_h<F16>(u.w);
+  if (add) { v[0] += a.x; v[1] += a.y; v[2] += b.x; v[3] += b.y; v[4] += c.x; v[5] += c.y; v[6] += d.x; v[7] += d.y; }
+  else { v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y; }
+}
+template <bool F16>
+__device__ __forceinline__ uint4 ln_pack8(const float* v) {
+  return make_uint4(pack_h<F16>(v[0], v[1]), pack_h<F16>(v[2], v[3]), pack_h<F16>(v[4], v[5]), pack_h<F16>(v[6], v[7]));
+}
+// normalise the 16 values of this lane (row of 512 over the warp) with gamma / beta from shared memory
+__device__ __forceinline__ void ln16(float (&v)[16], const float* __restrict__ sg, const float* __restrict__ sb, int lane) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += v[i];
+  const float mean = warp_sum(s) * (1.0f / 512.0f);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { v[i] -= mean; q = fmaf(v[i], v[i], q); }
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / 512.0f) + 1e-5f);
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const float4 g0 = *reinterpret_cast<const float4*>(sg + h * 256 + lane * 8), g1 = *reinterpret_cast<const float4*>(sg + h * 256 + lane * 8 + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(sb + h * 256 + lane * 8), b1 = *reinterpret_cast<const float4*>(sb + h * 256 + lane * 8 + 4);
+    float* w = v + 8 * h;
+    w[0] = fmaf(w[0] * rstd, g0.x, b0.x); w[1] = fmaf(w[1] * rstd, g0.y, b0.y); w[2] = fmaf(w[2] * rstd, g0.z, b0.z); w[3] = fmaf(w[3] * rstd, g0.w, b0.w);
+    w[4] = fmaf(w[4] * rstd, g1.x, b1.x); w[5] = fmaf(w[5] * rstd, g1.y, b1.y); w[6] = fmaf(w[6] * rstd, g1.z, b1.z); w[7] = fmaf(w[7] * rstd, g1.w, b1.w);
+  }
+}
+
+template <int D, bool F16, int kLnRows>
 __global__ void __launch_bounds__(256) ln_kernel(LnParams p) {
+  static_assert(D == 512, "lane layout: two 8-element chunks per lane");
   griddep_launch();
+  __shared__ __align__(16) float sgb[4][D];          // g1, b1, g2, b2
+  for (int i = threadIdx.x; i < D; i += blockDim.x) {
+    sgb[0][i] = p.g1[i]; sgb[1][i] = p.b1[i];
+    sgb[2][i] = p.g2 ? p.g2[i] : 0.f; sgb[3][i] = p.b2 ? p.b2[i] : 0.f;
+  }
   griddep_wait();
-  constexpr int NV = D / 32;
+  __syncthreads();
   const int lane = threadIdx.x & 31;
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= p.M) return;
-  const int s = row / p.T, tok = row % p.T;
-  float v[NV];
-  const bf16* y = p.y + (int64_t)row * D;
+  const int row0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * kLnRows;
+  const int c0 = lane * 8, c1 = 256 + lane * 8;
+  struct Raw { uint4 y0, y1, r0, r1, a0, a1; };
+  auto load = [&](int row, Raw& w) {
+    if (row >= p.M) return;
+    const bf16* y = p.y + (int64_t)row * D;
+    w.y0 = *reinterpret_cast<const uint4*>(y + c0); w.y1 = *reinterpret_cast<const uint4*>(y + c1);
+    if (p.resid != nullptr) {
+      const bf16* r = p.resid + (int64_t)row * D;
+      w.r0 = *reinterpret_cast<const uint4*>(r + c0); w.r1 = *reinterpret_cast<const uint4*>(r + c1);
+    }
+    const int s = row / p.T, tok = row - s * p.T;
+    if (p.add != nullptr && tok > 0) {
+      const bf16* a = p.add + ((int64_t)s * (p.T - 1) + (tok - 1)) * D;
+      w.a0 = __ldg(reinterpret_cast<const uint4*>(a + c0)); w.a1 = __ldg(reinterpret_cast<const uint4*>(a + c1));
+    }
+  };
+  Raw cur, nxt;
+  load(row0, cur);
 #pragma unroll
-  for (int i = 0; i < NV / 4; ++i) load_h4<F16, false>(y + i * 128 + lane * 4, v + 4 * i);
-  if (p.resid != nullptr) {  // x + sublayer(x): the residual add of the post-LN layer (model.py:874-878)
-    const bf16* r = p.resid + (int64_t)row * D;
-#pragma unroll
-    for (int i = 0; i < NV / 4; ++i) load_h4<F16, true>(r + i * 128 + lane * 4, v + 4 * i);
+  for (int i = 0; i < kLnRows; ++i) {
+    const int row = row0 + i;
+    if (i + 1 < kLnRows) load(row + 1, nxt);
+    if (row < p.M) {
+      const int s = row / p.T, tok = row - s * p.T;
+      float v[16];
+      ln_unpack8<F16>(cur.y0, v, false); ln_unpack8<F16>(cur.y1, v + 8, false);
+      if (p.resid != nullptr) {  // x + sublayer(x): the residual add of the post-LN layer (model.py:874-878)
+        ln_unpack8<F16>(cur.r0, v, true); ln_unpack8<F16>(cur.r1, v + 8, true);
+      }
+      if (!(tok == 0 && p.skip_tok0)) {
+        ln16(v, sgb[0], sgb[1], lane);
+        if (tok == 0 && p.x0 != nullptr) {
+          bf16* o = p.x0 + (int64_t)s * D;
+          *reinterpret_cast<uint4*>(o + c0) = ln_pack8<F16>(v); *reinterpret_cast<uint4*>(o + c1) = ln_pack8<F16>(v + 8);
+        } else {
+          if (p.add != nullptr && tok > 0) {
+            // x1 is rounded to 16 bits where the reference's next sub-layer reads it; keep the same rounding point
+            ln_unpack8<F16>(cur.a0, v, true); ln_unpack8<F16>(cur.a1, v + 8, true);
+            ln16(v, sgb[2], sgb[3], lane);
+          }
+          bf16* o = p.out + (int64_t)row * D;
+          *reinterpret_cast<uint4*>(o + c0) = ln_pack8<F16>(v); *reinterpret_cast<uint4*>(o + c1) = ln_pack8<F16>(v + 8);
+        }
+      }
+    }
+    cur = nxt;
   }
-  if (tok == 0 && p.skip_tok0) return;
-  ln_row<D>(v, p.g1, p.b1, lane);
-  if (tok == 0 && p.x0 != nullptr) {
-#pragma unroll
-    for (int i = 0; i < NV / 4; ++i)
-      store_h4<F16>(p.x0 + (int64_t)s * D + i * 128 + lane * 4, v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-    return;
-  }
-  if (p.add != nullptr && tok > 0) {
-    // x1 is rounded to bf16 where the reference's next sub-layer reads it; keep the same rounding point
-    const bf16* a = p.add + ((int64_t)s * (p.T - 1) + (tok - 1)) * D;
-#pragma unroll
-    for (int i = 0; i < NV / 4; ++i) load_h4<F16, true>(a + i * 128 + lane * 4, v + 4 * i);
-    ln_row<D>(v, p.g2, p.b2, lane);
-  }
-  bf16* o = p.out + (int64_t)row * D;
-#pragma unroll
-  for (int i = 0; i < NV / 4; ++i) store_h4<F16>(o + i * 128 + lane * 4, v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
 }
 int ln_launch(const LnParams& p, cudaStream_t st) {
   MSMD_REQUIRE(p.d == 512, "ln: only d_model = 512 is instantiated (got %d)", p.d);
   ProfileScope prof(p.add ? "ln1_ln2" : "ln3", st);
-  MSMD_CHECK_CUDA(launch_pdl(p.fp16 ? ln_kernel<512, true> : ln_kernel<512, false>, dim3(cdiv(p.M, 8)), dim3(256), 0, st, p));
+  // rows per warp: 6 makes the configuration-3 grid (21 312 rows) exactly 444 CTAs = 3 resident CTAs on each of the 148 SMs
+  static const int rows = [] { const char* e = getenv("MSMD_LN_ROWS"); return e ? atoi(e) : 6; }();
+  if (p.M <= 148 * 3 * 8) {      // small batches (latency regime): one row per warp, as many CTAs as rows allow
+    MSMD_CHECK_CUDA(launch_pdl(p.fp16 ? ln_kernel<512, true, 1> : ln_kernel<512, false, 1>, dim3(cdiv(p.M, 8)), dim3(256), 0, st, p));
+  } else if (rows == 4 || p.M < 148 * 3 * 8 * 4) {
+    MSMD_CHECK_CUDA(launch_pdl(p.fp16 ? ln_kernel<512, true, 4> : ln_kernel<512, false, 4>, dim3(cdiv(p.M, 8 * 4)), dim3(256), 0, st, p));
+  } else {
+    MSMD_CHECK_CUDA(launch_pdl(p.fp16 ? ln_kernel<512, true, 6> : ln_kernel<512, false, 6>, dim3(cdiv(p.M, 8 * 6)), dim3(256), 0, st, p));
+  }
   MSMD_CHECK_LAUNCH();
   return MSMD_OK;
 }
@@ -485,10 +554,14 @@ __global__ void __launch_bounds__(256) update_kernel(const UpdateParams* __restr
     c1 = (1.0f - alpha) * sqrtf(abp) / (1.0f - ab);
   }
   const bool sep = p.tgt_dyn != nullptr || p.cum_static != nullptr;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_el; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % p.dm);
-    const int l = (int)((i / p.dm) % p.L);
-    const int n = (int)(i / ((int64_t)p.dm * p.L));
+  // warp = one (clip, frame) row of dm codes, lane = column c (+32, +64): no 64-bit index arithmetic per element (three
+  // int64 divisions per element made this kernel instruction-bound: 600 instructions per element, 23 us per step)
+  const int lane = threadIdx.x & 31;
+  const int rows = p.NX * p.L;
+  for (int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += gridDim.x * (blockDim.x >> 5)) {
+    const int n = row / p.L, l = row - n * p.L;
+   for (int c = lane; c < p.dm; c += 32) {
+    const int64_t i = (int64_t)row * p.dm + c;
     // CFG combine (model.py:404-417); results[0] is updated in place through a view, so 'independent'
     // subtracts the running target.  The same recursion runs on the dynamic / static parts
     // (model.py:603-626) when the separate outputs are requested.
@@ -530,6 +603,7 @@ __global__ void __launch_bounds__(256) update_kernel(const UpdateParams* __restr
       }
       p.alpha_traj[(((int64_t)(p.t_start - t) * p.NX + n) * p.L + l) * p.nb + c] = ta;
     }
+   }
   }
   // step index t -> t - 1 for the next step, by the LAST block to finish (every block has read t by then): the separate
   // one-thread-block "advance" launch of round 1 is gone
@@ -617,9 +691,9 @@ int update_params_set(UpdateParams* d_dst, const UpdateParams& p, cudaStream_t s
   return MSMD_OK;
 }
 int update_launch(const UpdateParams* d_p, int NX, int L, int dm, cudaStream_t st) {
-  const int64_t n = (int64_t)NX * L * dm;
+  (void)dm;
   ProfileScope prof("update", st);
-  MSMD_CHECK_CUDA(launch_pdl(update_kernel, dim3((int)std::min<int64_t>(cdiv(n, 256), kNumSMs * 8)), dim3(256), 0, st, d_p));
+  MSMD_CHECK_CUDA(launch_pdl(update_kernel, dim3(std::min(cdiv(NX * L, 8), kNumSMs * 8)), dim3(256), 0, st, d_p));   // warp per row
   MSMD_CHECK_LAUNCH();
   return MSMD_OK;
 }

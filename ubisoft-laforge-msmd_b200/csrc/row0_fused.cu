@@ -4,19 +4,24 @@
 //     x[s, 0, :] = LayerNorm2( x0c[s] + Wco . attn_h( Wq0 . x0c[s] + bq0 ; K_s, V_s ) + bco )
 //
 // It replaces four launches (q-projection GEMM, warp-per-head attention, out-projection GEMM, LayerNorm) that cost
-// 23 us per layer on the critical path for S rows of work (S = sequences, 192 at config 3; 3 in the batch-1 latency
+// ~31 us per layer on the critical path for S rows of work (S = sequences, 192 at config 3; 3 in the batch-1 latency
 // regime, where the three saved launches per layer are 20% of the step).
 //
 // One thread-block CLUSTER of 8 CTAs per group of <= 16 sequences, CTA rank = attention head h:
 //   phase 0  stage this head's weight slices in shared memory once per CTA: Wq0 rows [64h, 64h+64) (64 KB) and the
 //            K-slice Wco[:, 64h:64h+64) (64 KB); L2-prefetch the head's K / V cache lines of the group's sequences;
-//   phase 1  q_h = Wq0_h . x0c + b      [64 x 512] x [512 x n]   register tiles 4 outputs x 4 sequences, CUDA cores
-//   phase 2  one warp per sequence: scores over the Tk memory keys, softmax, ctx_h = P V   (HBM-bound: the K/V cache)
-//   phase 3  partial out-projection po = Wco[:, h-slice] . ctx_h   [512 x 64] x [64 x n]
-//   phase 4  distributed-shared-memory reduction of the 8 partial projections: CTA h sums ITS 64 output columns from
-//            all 8 CTAs, adds residual + bias, and the LayerNorm statistics are exchanged through DSMEM as well
-//            (two-pass: mean, then centred second moment); each CTA writes its 128-byte column block of the row.
-// Three cluster barriers per group.  16-bit storage format (bf16 / fp16) is a template parameter like everywhere else.
+//   phase 1  q_h = Wq0_h . x0c + b      [64 x 512] x [512 x n]   warp-level mma.sync m16n8k16 (the sequences are the
+//            N columns, ldmatrix'd weight rows the A operand): 16 warps = 4 output tiles x 4 K quarters, summed in a
+//            fixed order.  (The CUDA-core version of this phase was shared-memory-bandwidth bound: 5500 cycles per 7
+//            sequences; a tcgen05 tile would idle 120 of its 128 rows.)
+//   phase 2  attention of head h: warp w = keys [8w, 8w+8) of every sequence, four sequences' K / V rows in flight
+//            per warp (HBM / L2-bound: the K/V cache is the only large read of the kernel)
+//   phase 3  partial out-projection po = Wco[:, h-slice] . ctx_h   [512 x 64] x [64 x n], mma.sync again
+//   phase 4  distributed-shared-memory reduction of the 8 partial projections: CTA h finishes the rows of sequences h and
+//            h + 8 of the group (thread = column): sums the 8 partials over DSMEM, adds residual + bias, block LayerNorm.
+// Two cluster barriers per group.  16-bit storage format (bf16 / fp16) is a template parameter like everywhere else.
+// Every sequence is a column of the MMAs and a private slice of the attention partials: its arithmetic does not depend
+// on which other sequences share the cluster, so a clip's codes are bit-identical whatever batch it is sampled in.
 #include "denoiser_kernels.cuh"
 #include "profile.cuh"
 #include <cuda_fp16.h>
@@ -25,18 +30,27 @@ namespace msmd {
 namespace {
 
 constexpr int kThreads = 512, kNB = 16, kD = 512, kDh = 64, kHeads = 8;
-constexpr int kWqPitch = kD + 8;        // halfs per staged Wq0 row (1040 B: 16-byte aligned, bank-staggered)
-constexpr int kWoPitch = kDh + 8;       // halfs per staged Wco row slice (144 B)
+constexpr int kParts = 14, kPartKeys = 8;   // the memory keys are ALWAYS cut into 14 parts of 8 (Tk <= 112)
+constexpr int kWqPitch = kD + 8;        // halfs per staged Wq0 row (1040 B: 16-byte aligned, rows 4 banks apart: ldmatrix conflict-free)
+constexpr int kWoPitch = kDh + 8;       // halfs per staged Wco row slice (144 B, same stagger)
+constexpr int kXPitch = kD + 8;         // halfs per x0c row (B operand of the q projection)
+constexpr int kCPitch = kDh + 8;        // halfs per ctx row (B operand of the out-projection)
+constexpr int kPoPitch = kD + 4;        // floats per partial-projection row
+constexpr int kPartFloats = 66;         // max, sum, o[64]
 constexpr int kOffWq = 0;
 constexpr int kOffWo = kOffWq + kDh * kWqPitch * 2;
 constexpr int kOffXs = kOffWo + kD * kWoPitch * 2;
-constexpr int kOffQs = kOffXs + kNB * kD * 2;
+constexpr int kOffQs = kOffXs + kNB * kXPitch * 2;
 constexpr int kOffCs = kOffQs + kNB * kDh * 4;
-constexpr int kOffPo = kOffCs + kNB * kDh * 4;
-constexpr int kOffSt = kOffPo + kNB * kD * 4;
-constexpr int kSmem = kOffSt + 2 * kHeads * kNB * 4;
-constexpr int kMaxGroup = 7;            // sequences per cluster: their 16 x 66-float attention partials share the 32 KB po buffer
-static_assert(kMaxGroup * 16 * 66 * 4 <= kNB * kD * 4, "attention partials must fit the partial-projection buffer");
+constexpr int kOffPo = kOffCs + kNB * kCPitch * 2;
+// one buffer, three lives per group: K-quarter partials of the q projection [4][64][16], attention partials
+// [16][14][66], partial out-projection [16][516] (each is dead before the next is written)
+constexpr int kPoBytes = kNB * kParts * kPartFloats * 4;
+constexpr int kOffSt = kOffPo + kPoBytes;
+constexpr int kSmem = kOffSt + 2 * 32 * 4;      // LayerNorm block-reduction scratch: [2 rows][sum(16 warps) | sq(16 warps)]
+constexpr int kMaxGroup = kNB;          // sequences per cluster pass = two 8-column MMA tiles
+static_assert(kNB * kPoPitch * 4 <= kPoBytes && 4 * kDh * kNB * 4 <= kPoBytes, "po / q-partial views must fit the shared buffer");
+static_assert(kOffWo % 16 == 0 && kOffXs % 16 == 0 && kOffQs % 16 == 0 && kOffCs % 16 == 0 && kOffPo % 16 == 0 && kOffSt % 16 == 0, "alignment");
 static_assert(kSmem <= 227 * 1024, "row0_fused shared memory");
 
 struct Row0Params {
@@ -112,8 +126,26 @@ __device__ __forceinline__ float2 ld_remote_f2(uint32_t addr) {
   asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr) : "memory");
   return v;
 }
-__device__ __forceinline__ void st_remote_f(uint32_t addr, float v) {
-  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+__device__ __forceinline__ float ld_remote_f(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* smem_row) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"((uint32_t)__cvta_generic_to_shared(smem_row)));
+}
+// D (16x8, fp32) += A (16x16, row-major) . B (16x8, K-major per column), 16-bit operands in the storage format
+template <bool F16>
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  if constexpr (F16)
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  else
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
 template <bool F16>
@@ -125,10 +157,11 @@ __global__ void __cluster_dims__(kHeads, 1, 1) __launch_bounds__(kThreads, 1) ro
   bf16* wo = reinterpret_cast<bf16*>(sm + kOffWo);
   bf16* xs = reinterpret_cast<bf16*>(sm + kOffXs);
   float* qs = reinterpret_cast<float*>(sm + kOffQs);
-  float* cs = reinterpret_cast<float*>(sm + kOffCs);
+  bf16* cs = reinterpret_cast<bf16*>(sm + kOffCs);   // ctx_h of the group, 16-bit (the format the unfused chain stores it in)
   float* po = reinterpret_cast<float*>(sm + kOffPo);
-  float* st = reinterpret_cast<float*>(sm + kOffSt);   // [2][kHeads][kNB]
+  float* st = reinterpret_cast<float*>(sm + kOffSt);   // [2][32]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int gid = lane >> 2, tig = lane & 3;           // mma.sync fragment coordinates
   const int h = (int)ctarank();
   const int cid = blockIdx.x / kHeads, ncl = gridDim.x / kHeads;
   const int s_begin = (int)(((int64_t)p.S * cid) / ncl), s_end = (int)(((int64_t)p.S * (cid + 1)) / ncl);
@@ -151,12 +184,13 @@ __global__ void __cluster_dims__(kHeads, 1, 1) __launch_bounds__(kThreads, 1) ro
 
   for (int s0 = s_begin; s0 < s_end; s0 += kMaxGroup) {
     const int n = min(kMaxGroup, s_end - s0);
+    const int ntiles = (n + 7) >> 3;           // 8-sequence MMA column tiles in use
     // ---- phase 0b: x0c rows of the group (zero-padded to kNB) + L2 prefetch of this head's K / V lines
     for (int i = tid; i < kNB * (kD / 8); i += kThreads) {
       const int s = i >> 6, c = i & 63;
       uint4 v = make_uint4(0, 0, 0, 0);
       if (s < n) v = *reinterpret_cast<const uint4*>(p.x0c + (int64_t)(s0 + s) * kD + c * 8);
-      *reinterpret_cast<uint4*>(xs + s * kD + c * 8) = v;
+      *reinterpret_cast<uint4*>(xs + s * kXPitch + c * 8) = v;
     }
     for (int i = tid; i < n * p.Tk * 2; i += kThreads) {
       const int s = i / (p.Tk * 2), r = i % (p.Tk * 2);
@@ -167,110 +201,137 @@ __global__ void __cluster_dims__(kHeads, 1, 1) __launch_bounds__(kThreads, 1) ro
     __syncthreads();
     r0_stamp(p.trace, 1);
 
-    // ---- phase 1: q_h[s][o] = bq[64h+o] + sum_k Wq0[64h+o][k] x0c[s][k]
+    // ---- phase 1: q_h[s][o] = bq[64h+o] + sum_k Wq0[64h+o][k] x0c[s][k].  Warp = (output tile mt of 16, K quarter kq);
+    // the four K-quarter partials of every (o, s) are summed below in a fixed order.
     {
-      const int kpart = tid & 7, tile = tid >> 3, og = tile & 15, sg = tile >> 4;
-      if (sg * 4 < n) {       // (warp-uniform: a warp holds 4 tiles of one sequence group) padded groups do no work
-      float acc[4][4];
+      const int mt = warp & 3, kq = warp >> 2;
+      float acc[2][4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-#pragma unroll 2
-      for (int c = 0; c < 8; ++c) {
-        const int ch = kpart + 8 * c;          // 16-byte chunk of the K axis: the 8 lanes of a tile read 128 contiguous bytes
-        float xv[4][8];
+        for (int j = 0; j < 4; ++j) acc[nt][j] = 0.f;
+      const bf16* arow = wq + (16 * mt + (lane & 7) + ((lane >> 3) & 1) * 8) * kWqPitch + (lane >> 4) * 8 + 128 * kq;
+      const bf16* brow = xs + gid * kXPitch + 128 * kq + tig * 2;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) up8<F16>(*reinterpret_cast<const uint4*>(xs + (sg * 4 + j) * kD + ch * 8), xv[j]);
+      for (int ks = 0; ks < 8; ++ks) {
+        uint32_t a[4];
+        ldmatrix_x4(a, arow + 16 * ks);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          float wv[8];
-          up8<F16>(*reinterpret_cast<const uint4*>(wq + (og * 4 + i) * kWqPitch + ch * 8), wv);
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-#pragma unroll
-            for (int k = 0; k < 8; ++k) acc[i][j] = fmaf(wv[k], xv[j][k], acc[i][j]);
+        for (int nt = 0; nt < 2; ++nt) {
+          if (nt < ntiles) {
+            const uint32_t b0 = *reinterpret_cast<const uint32_t*>(brow + nt * 8 * kXPitch + 16 * ks);
+            const uint32_t b1 = *reinterpret_cast<const uint32_t*>(brow + nt * 8 * kXPitch + 16 * ks + 8);
+            mma16816<F16>(acc[nt], a, b0, b1);
+          }
         }
       }
+      float* qpart = po + kq * (kDh * kNB);         // [kq][o][seq]
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float v = acc[i][j];
-          v += __shfl_xor_sync(0xffffffffu, v, 1);
-          v += __shfl_xor_sync(0xffffffffu, v, 2);
-          v += __shfl_xor_sync(0xffffffffu, v, 4);
-          if (kpart == 0) qs[(sg * 4 + j) * kDh + og * 4 + i] = v + __ldg(p.bq + h * kDh + og * 4 + i);
+      for (int nt = 0; nt < 2; ++nt) {
+        if (nt < ntiles) {
+          *reinterpret_cast<float2*>(qpart + (16 * mt + gid) * kNB + 8 * nt + 2 * tig) = make_float2(acc[nt][0], acc[nt][1]);
+          *reinterpret_cast<float2*>(qpart + (16 * mt + gid + 8) * kNB + 8 * nt + 2 * tig) = make_float2(acc[nt][2], acc[nt][3]);
         }
+      }
+    }
+    __syncthreads();
+    for (int i = tid; i < kDh * kNB; i += kThreads) {
+      const int o = i >> 4, s = i & 15;
+      if (s < 8 * ntiles) {
+        float v = po[0 * (kDh * kNB) + i];
+        v += po[1 * (kDh * kNB) + i];
+        v += po[2 * (kDh * kNB) + i];
+        v += po[3 * (kDh * kNB) + i];
+        qs[s * kDh + o] = v + __ldg(p.bq + h * kDh + o);
       }
     }
     __syncthreads();
 
-    // ---- phase 2: attention of head h.  The Tk <= 128 keys are ALWAYS cut into 16 parts of 8 keys, warp w = part w of
+    // ---- phase 2: attention of head h.  The Tk <= 112 keys are ALWAYS cut into 14 parts of 8 keys, warp w = part w of
     // every sequence of the group: each part yields a partial (max, sum, P V) and the parts are merged in a fixed
-    // order below - the arithmetic of a sequence does not depend on how many sequences share the cluster, so a clip's
-    // codes are bit-identical whatever batch it is sampled in.  (All 16 warps stay busy even for a single sequence:
-    // the batch-1 latency regime.)  Lane j < 8 scores key 8w + j; every lane owns two of the 64 head dims for P V.
-    // The partials live in the (not yet used) partial-projection buffer: n <= kMaxGroup sequences per group.
+    // order below - the arithmetic of a sequence does not depend on how many sequences share the cluster.  Lane
+    // (j, qd) = (lane / 4, lane % 4) scores 16 of the 64 head dims of key 8w + j (two 16-byte loads; the 4-lane sums are
+    // two shuffles); every lane owns two of the 64 head dims for P V (one coalesced 128-byte warp load per key).
+    // Four sequences' rows are requested before the first is used: the phase is bound by the K / V bytes, not by
+    // one load latency per sequence.
     r0_stamp(p.trace, 2);
-    float* parts = po;                              // [n][16 parts][66]: m, l, o(64)
-    {
-      const int part = warp, base = part * 8;
-      const int nk = max(0, min(8, p.Tk - base));   // keys of this part
-      for (int seq = 0; seq < n; ++seq) {
-        const bf16* kbase = p.kv + ((int64_t)(s0 + seq) * p.Tk + base) * (2 * kD) + h * kDh;
-        float dot = -INFINITY;
-        uint4 kr[8];
-        if (lane < nk) {
-          const uint4* kp = reinterpret_cast<const uint4*>(kbase + (int64_t)lane * (2 * kD));
+    float* parts = po;                              // [seq][kParts][66]: m, l, o(64)
+    if (warp < kParts) {
+      const int part = warp, base = part * kPartKeys;
+      const int nk = max(0, min(kPartKeys, p.Tk - base));   // keys of this part
+      const int j = lane >> 2, qd = lane & 3;
+      const bool valid = j < nk;
+      for (int c0 = 0; c0 < n; c0 += 4) {
+        uint4 ka[4], kb[4];
+        uint32_t vr[4][8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) kr[i] = __ldg(kp + i);
-        }
-        // V rows of the part's keys: one coalesced 128-byte warp load per key, issued before the scores are needed
-        const uint32_t* vbase = reinterpret_cast<const uint32_t*>(kbase + kD) + lane;
-        uint32_t vr[8];
+        for (int u4 = 0; u4 < 4; ++u4) {
+          if (c0 + u4 < n) {
+            const bf16* kbase = p.kv + ((int64_t)(s0 + c0 + u4) * p.Tk + base) * (2 * kD) + h * kDh;
+            ka[u4] = kb[u4] = make_uint4(0, 0, 0, 0);
+            if (valid) {
+              const uint4* kp = reinterpret_cast<const uint4*>(kbase + (int64_t)j * (2 * kD) + qd * 16);
+              ka[u4] = __ldg(kp);
+              kb[u4] = __ldg(kp + 1);
+            }
+            const uint32_t* vbase = reinterpret_cast<const uint32_t*>(kbase + kD) + lane;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) vr[u] = u < nk ? __ldg(vbase + (int64_t)u * kD) : 0u;
-        if (lane < nk) {
-          float a = 0.f;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float kf[8];
-            up8<F16>(kr[i], kf);
-            const float4 qa = *reinterpret_cast<const float4*>(qs + seq * kDh + 8 * i);
-            const float4 qb = *reinterpret_cast<const float4*>(qs + seq * kDh + 8 * i + 4);
-            a = fmaf(qa.x, kf[0], a); a = fmaf(qa.y, kf[1], a); a = fmaf(qa.z, kf[2], a); a = fmaf(qa.w, kf[3], a);
-            a = fmaf(qb.x, kf[4], a); a = fmaf(qb.y, kf[5], a); a = fmaf(qb.z, kf[6], a); a = fmaf(qb.w, kf[7], a);
+            for (int u = 0; u < 8; ++u) vr[u4][u] = u < nk ? __ldg(vbase + (int64_t)u * kD) : 0u;
           }
-          dot = a * 0.125f;
         }
-        const float m = wmax(dot);
-        const float pj = (dot == -INFINITY) ? 0.f : __expf(dot - m);
-        const float l = wsum(pj);
-        float oa = 0.f, ob = 0.f;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const float pu = __shfl_sync(0xffffffffu, pj, u);
-          const float2 f = up2<F16>(vr[u]);
-          oa = fmaf(pu, f.x, oa);
-          ob = fmaf(pu, f.y, ob);
+        for (int u4 = 0; u4 < 4; ++u4) {
+          const int seq = c0 + u4;
+          if (seq < n) {
+            float kf[16];
+            up8<F16>(ka[u4], kf);
+            up8<F16>(kb[u4], kf + 8);
+            const float* qp = qs + seq * kDh + qd * 16;
+            float a = 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 q4 = *reinterpret_cast<const float4*>(qp + 4 * i);
+              a = fmaf(q4.x, kf[4 * i], a); a = fmaf(q4.y, kf[4 * i + 1], a);
+              a = fmaf(q4.z, kf[4 * i + 2], a); a = fmaf(q4.w, kf[4 * i + 3], a);
+            }
+            a += __shfl_xor_sync(0xffffffffu, a, 1);
+            a += __shfl_xor_sync(0xffffffffu, a, 2);
+            const float dot = valid ? a * 0.125f : -INFINITY;
+            float m = dot;
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 16));
+            const float pj = valid ? __expf(dot - m) : 0.f;
+            float l = pj;
+            l += __shfl_xor_sync(0xffffffffu, l, 4);
+            l += __shfl_xor_sync(0xffffffffu, l, 8);
+            l += __shfl_xor_sync(0xffffffffu, l, 16);
+            float oa = 0.f, ob = 0.f;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const float pu = __shfl_sync(0xffffffffu, pj, 4 * u);
+              const float2 f = up2<F16>(vr[u4][u]);
+              oa = fmaf(pu, f.x, oa);
+              ob = fmaf(pu, f.y, ob);
+            }
+            float* pt = parts + (seq * kParts + part) * kPartFloats;
+            if (lane == 0) { pt[0] = m; pt[1] = l; }
+            *reinterpret_cast<float2*>(pt + 2 + 2 * lane) = make_float2(oa, ob);
+          }
         }
-        float* pt = parts + (seq * 16 + part) * 66;
-        if (lane == 0) { pt[0] = m; pt[1] = l; }
-        *reinterpret_cast<float2*>(pt + 2 + 2 * lane) = make_float2(oa, ob);
       }
     }
     __syncthreads();
-    if (warp < kNB) {      // merge the 16 parts of sequence `warp` (flash-style rescale); padded sequences give zeros
+    {      // merge the 14 parts of sequence `warp` (flash-style rescale); padded sequences give zeros
       float2 o = make_float2(0.f, 0.f);
       if (warp < n) {
         float M = -INFINITY;
 #pragma unroll
-        for (int w = 0; w < 16; ++w) M = fmaxf(M, parts[(warp * 16 + w) * 66]);
+        for (int w = 0; w < kParts; ++w) M = fmaxf(M, parts[(warp * kParts + w) * kPartFloats]);
         float l = 0.f;
 #pragma unroll
-        for (int w = 0; w < 16; ++w) {
-          const float* pt = parts + (warp * 16 + w) * 66;
+        for (int w = 0; w < kParts; ++w) {
+          const float* pt = parts + (warp * kParts + w) * kPartFloats;
           const float sc_w = pt[1] > 0.f ? __expf(pt[0] - M) : 0.f;
           const float2 t = *reinterpret_cast<const float2*>(pt + 2 + 2 * lane);
           l = fmaf(pt[1], sc_w, l);
@@ -280,87 +341,101 @@ __global__ void __cluster_dims__(kHeads, 1, 1) __launch_bounds__(kThreads, 1) ro
         const float inv = 1.0f / l;
         o.x *= inv; o.y *= inv;
       }
-      *reinterpret_cast<float2*>(cs + warp * kDh + 2 * lane) = o;
+      *reinterpret_cast<uint32_t*>(cs + warp * kCPitch + 2 * lane) = pk2<F16>(o.x, o.y);
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");     // Wco slice
     __syncthreads();
     r0_stamp(p.trace, 3);
 
-    // ---- phase 3: partial out-projection of this head's K-slice: po[s][c] = sum_{k<64} Wco[c][64h+k] ctx_h[s][k]
+    // ---- phase 3: partial out-projection of this head's K-slice: po[s][c] = sum_{k<64} Wco[c][64h+k] ctx_h[s][k];
+    // warp w owns the 16-row output tiles w and w + 16
     {
-      const int cg = tid & 127, sg = tid >> 7;      // rows cg, cg+128, cg+256, cg+384 (consecutive lanes -> consecutive rows)
-      if (sg * 4 < n) {
-      float acc[4][4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int mi = 0; mi < 2; ++mi) {
+        const int mt = warp + 16 * mi;
+        float acc[2][4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-#pragma unroll 2
-      for (int ch = 0; ch < 8; ++ch) {
-        float cv[4][8];
+        for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4 a = *reinterpret_cast<const float4*>(cs + (sg * 4 + j) * kDh + ch * 8);
-          const float4 b = *reinterpret_cast<const float4*>(cs + (sg * 4 + j) * kDh + ch * 8 + 4);
-          cv[j][0] = a.x; cv[j][1] = a.y; cv[j][2] = a.z; cv[j][3] = a.w;
-          cv[j][4] = b.x; cv[j][5] = b.y; cv[j][6] = b.z; cv[j][7] = b.w;
+          for (int jj = 0; jj < 4; ++jj) acc[nt][jj] = 0.f;
+        const bf16* arow = wo + (16 * mt + (lane & 7) + ((lane >> 3) & 1) * 8) * kWoPitch + (lane >> 4) * 8;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          uint32_t a[4];
+          ldmatrix_x4(a, arow + 16 * ks);
+#pragma unroll
+          for (int nt = 0; nt < 2; ++nt) {
+            if (nt < ntiles) {
+              const bf16* brow = cs + (8 * nt + gid) * kCPitch + 16 * ks + tig * 2;
+              mma16816<F16>(acc[nt], a, *reinterpret_cast<const uint32_t*>(brow), *reinterpret_cast<const uint32_t*>(brow + 8));
+            }
+          }
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          float wv[8];
-          up8<F16>(*reinterpret_cast<const uint4*>(wo + (cg + 128 * i) * kWoPitch + ch * 8), wv);
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-#pragma unroll
-            for (int k = 0; k < 8; ++k) acc[i][j] = fmaf(wv[k], cv[j][k], acc[i][j]);
+        for (int nt = 0; nt < 2; ++nt) {
+          if (nt < ntiles) {
+            float* o0 = po + (8 * nt + 2 * tig) * kPoPitch + 16 * mt + gid;
+            o0[0] = acc[nt][0]; o0[kPoPitch] = acc[nt][1];
+            o0[8] = acc[nt][2]; o0[kPoPitch + 8] = acc[nt][3];
+          }
         }
-      }
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) po[(sg * 4 + j) * kD + cg + 128 * i] = acc[i][j];
       }
     }
     r0_stamp(p.trace, 4);
     cluster_barrier();     // every CTA's partial projection is complete and visible cluster-wide
     r0_stamp(p.trace, 5);
 
-    // ---- phase 4: CTA h reduces ITS 64 output columns over the 8 partials (DSMEM), + residual + bias, LayerNorm
+    // ---- phase 4: CTA h finishes the rows of the group's sequences s = h, h + 8: thread = output column.  The 8 partial
+    // projections of the row come over DSMEM (fixed order), + residual + bias, then an ordinary block LayerNorm (two-pass,
+    // fp32) - no statistics exchange between CTAs.  The cluster barrier that lets the peers reuse / retire their po
+    // buffers is ARRIVED at as soon as the remote values are in registers and only WAITED for after the row is stored.
     {
-      const int s = warp;                       // warp = sequence of the group (kNB = 16 warps)
-      const int c = h * kDh + 2 * lane;         // this lane's two columns of the row
-      float v0 = 0.f, v1 = 0.f;
+      const int c = tid;                        // kThreads == kD
+      float v[2] = {0.f, 0.f};
 #pragma unroll
-      for (int r = 0; r < kHeads; ++r) {
-        const float2 t = ld_remote_f2(remote_addr(po + s * kD + c, r));
-        v0 += t.x; v1 += t.y;
+      for (int u = 0; u < 2; ++u) {
+        const int sq = h + kHeads * u;
+        if (sq < n) {
+#pragma unroll
+          for (int r = 0; r < kHeads; ++r) v[u] += ld_remote_f(remote_addr(po + sq * kPoPitch + c, r));
+        }
       }
-      const float2 xr = up2<F16>(*reinterpret_cast<const uint32_t*>(xs + s * kD + c));
-      v0 += xr.x + __ldg(p.bo + c);
-      v1 += xr.y + __ldg(p.bo + c + 1);
-      const float part = wsum(v0 + v1);
-      if (lane < kHeads) st_remote_f(remote_addr(st + (0 * kHeads + h) * kNB + s, lane), part);
-      cluster_barrier();
-      float mean = 0.f;
+      asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+      const float bo = __ldg(p.bo + c), gg = __ldg(p.g + c), bb = __ldg(p.be + c);
 #pragma unroll
-      for (int r = 0; r < kHeads; ++r) mean += st[(0 * kHeads + r) * kNB + s];
-      mean *= (1.0f / kD);
-      const float d0 = v0 - mean, d1 = v1 - mean;
-      const float part2 = wsum(d0 * d0 + d1 * d1);
-      if (lane < kHeads) st_remote_f(remote_addr(st + (1 * kHeads + h) * kNB + s, lane), part2);
-      cluster_barrier();
-      float var = 0.f;
+      for (int u = 0; u < 2; ++u) {
+        const int sq = h + kHeads * u;
+        if (sq < n) {                             // uniform over the CTA
+          const bf16 xh = xs[sq * kXPitch + c];
+          float xr;
+          if constexpr (F16) xr = __half2float(*reinterpret_cast<const __half*>(&xh));
+          else xr = __bfloat162float(xh);
+          const float val = v[u] + (xr + bo);
+          const float ps = wsum(val);
+          if (lane == 0) st[u * 32 + warp] = ps;
+          __syncthreads();
+          float mean = 0.f;
 #pragma unroll
-      for (int r = 0; r < kHeads; ++r) var += st[(1 * kHeads + r) * kNB + s];
-      const float rstd = rsqrtf(var * (1.0f / kD) + 1e-5f);
-      if (s < n) {
-        const float2 gg = __ldg(reinterpret_cast<const float2*>(p.g + c)), bb = __ldg(reinterpret_cast<const float2*>(p.be + c));
-        *reinterpret_cast<uint32_t*>(p.x + (int64_t)(s0 + s) * p.T * kD + c) =
-            pk2<F16>(d0 * rstd * gg.x + bb.x, d1 * rstd * gg.y + bb.y);
+          for (int w = 0; w < kThreads / 32; ++w) mean += st[u * 32 + w];
+          mean *= (1.0f / kD);
+          const float dlt = val - mean;
+          const float pq = wsum(dlt * dlt);
+          if (lane == 0) st[u * 32 + 16 + warp] = pq;
+          __syncthreads();
+          float var = 0.f;
+#pragma unroll
+          for (int w = 0; w < kThreads / 32; ++w) var += st[u * 32 + 16 + w];
+          const float rstd = rsqrtf(var * (1.0f / kD) + 1e-5f);
+          const float outv = dlt * rstd * gg + bb;
+          bf16* dst = p.x + (int64_t)(s0 + sq) * p.T * kD + c;
+          if constexpr (F16) { const __half hv = __float2half_rn(outv); *dst = *reinterpret_cast<const bf16*>(&hv); }
+          else *dst = __float2bfloat16_rn(outv);
+        }
       }
+      r0_stamp(p.trace, 6);
+      // every peer has finished reading this CTA's po: the next group may overwrite it / the CTA may retire
+      asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
     }
-    r0_stamp(p.trace, 6);
-    if (s0 + kMaxGroup < s_end) cluster_barrier();   // the next group overwrites po / st: every remote read of this one is done
   }
 }
 
@@ -368,8 +443,8 @@ __global__ void __cluster_dims__(kHeads, 1, 1) __launch_bounds__(kThreads, 1) ro
 
 int row0_fused_launch(const bf16* x0c, const bf16* Wq, const float* bq, const bf16* kv, const bf16* Wo, const float* bo,
                       const float* g, const float* be, bf16* x, int S, int T, int Tk, int H, int d, int fp16, cudaStream_t st) {
-  MSMD_REQUIRE(d == kD && H == kHeads && Tk >= 1 && Tk <= 128,
-               "row0_fused: built for d_model 512, 8 heads x 64 and <= 128 memory tokens (got %d, %d, %d)", d, H, Tk);
+  MSMD_REQUIRE(d == kD && H == kHeads && Tk >= 1 && Tk <= kParts * kPartKeys,
+               "row0_fused: built for d_model 512, 8 heads x 64 and <= 112 memory tokens (got %d, %d, %d)", d, H, Tk);
   Row0Params p{x0c, Wq, bq, kv, Wo, bo, g, be, x, S, T, Tk, nullptr};
 #ifdef MSMD_ROW0_TRACE
   static unsigned long long* tbuf = nullptr;
