@@ -61,6 +61,7 @@ struct msmd_model {
   bool packing = false;       // dalloc target: wowned while load_weights runs
   // fp32 parameters
   float *PE = nullptr, *temb = nullptr, *Wp = nullptr, *bp = nullptr, *Wf = nullptr, *WfT = nullptr, *bf_ = nullptr;
+  __half* Wf16 = nullptr;     // [2][d][80] fp16 hi | lo of feature_proj.weight[:, :dm] (tensor-core embedding)
   std::vector<float*> Ws0, bs0, Ws2, bs2;
   bf16 *Wd1 = nullptr, *Wd2 = nullptr;
   float *bd1 = nullptr, *bd2 = nullptr;
@@ -174,7 +175,7 @@ int run_forward_f32(msmd_model* m, const float* xrows, cudaStream_t st) {
   const int S = m->S, T = m->T, d = c.d_model, M = S * T;
   int rc;
   if (!m->window32 && (rc = window_begin_f32(m, st))) return rc;
-  EmbedParams ep;
+  EmbedParams ep{};
   ep.pp = m->pp; ep.temb = m->temb; ep.pmproj = m->pmproj; ep.PE = m->PE; ep.steps = m->steps;
   ep.x = xrows; ep.indicator = c.use_indicator ? m->indicator : nullptr; ep.WfT = m->WfT; ep.bf = m->bf_;
   ep.out = nullptr; ep.S = S; ep.NX = m->NX; ep.E = m->E; ep.Lp = c.n_prev_motions; ep.L = c.n_motions; ep.d = d;
@@ -231,7 +232,7 @@ int run_forward(msmd_model* m, const float* xrows, cudaStream_t st, int fmt) {
   ep.pp = m->pp; ep.temb = m->temb; ep.pmproj = m->pmproj; ep.PE = m->PE; ep.steps = m->steps;
   ep.x = xrows; ep.indicator = c.use_indicator ? m->indicator : nullptr; ep.WfT = m->WfT; ep.bf = m->bf_;
   ep.out = m->x; ep.S = S; ep.NX = m->NX; ep.E = m->E; ep.Lp = c.n_prev_motions; ep.L = c.n_motions; ep.d = d;
-  ep.dm = c.motion_dim; ep.fp16 = fmt;
+  ep.dm = c.motion_dim; ep.fp16 = fmt; ep.Wf16 = m->Wf16;
   if ((rc = embed_launch(ep, st))) return rc;
   for (int l = 0; l < c.n_layers; ++l) {
     LayerW& w = m->L[l];
@@ -492,6 +493,18 @@ extern "C" int msmd_load_weights(msmd_model* m, const char* const* names, const 
     for (size_t cc = 0; cc < d; ++cc)
       for (size_t k = 0; k < fin; ++k) t[k * d + cc] = h[cc * fin + k];
     if (!rc) rc = up_f32(m, &m->WfT, t);
+    if (!rc && dm <= 80) {   // fp16 two-term split of the motion columns, [n][k] with K zero-padded to 80 (embed_x_mma_kernel)
+      std::vector<__half> w16(2 * d * 80, __float2half_rn(0.f));
+      for (size_t cc = 0; cc < d; ++cc)
+        for (size_t k = 0; k < dm; ++k) {
+          const float v = h[cc * fin + k];
+          const __half hi = __float2half_rn(v);
+          w16[cc * 80 + k] = hi;
+          w16[d * 80 + cc * 80 + k] = __float2half_rn(v - __half2float(hi));
+        }
+      rc = dalloc(m, &m->Wf16, w16.size());
+      if (!rc) MSMD_CHECK_CUDA(cudaMemcpy(m->Wf16, w16.data(), w16.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    }
   }
   F32(P + "feature_proj.bias", d, &m->bf_);
   m->Ws0.assign(c.n_basis, nullptr); m->bs0 = m->Ws2 = m->bs2 = m->Ws0;

@@ -5,6 +5,7 @@
 // warp-shuffle reductions, fp32 statistics.
 #include "denoiser_kernels.cuh"
 #include "profile.cuh"
+#include <cuda_fp16.h>
 #include <cstdlib>
 
 namespace msmd {
@@ -207,8 +208,152 @@ __global__ void __launch_bounds__(256, 2) embed_x_kernel(EmbedParams p) {
     }
   }
 }
+
+// The same rows on the tensor cores.  feature_proj is a [rows, dm] x [dm, 512] product with fp32 inputs (x_t is the
+// sampler state) and a 16-bit output: three mma.sync passes over fp16 two-term splits (x = hi + lo, W = hi + lo:
+// hi*hi + lo*hi + hi*lo, 22 mantissa bits - the result rounds to the same 16-bit value as the fp32 FMA chain except
+// for rare last-bit ties) cost 240 MMAs per warp instead of 3800 FFMAs + 480 shared-memory loads per thread.
+//   CTA   = 32 consecutive x rows (clip boundaries may fall inside a tile) x 512 features, 8 warps x 64 features
+//   A     = the rows' hi / lo halves in shared memory (pitch 88: ldmatrix conflict-free), K zero-padded to 80
+//   B     = Wf16 [n][k] fragments straight from global memory (164 KB in all: L1 / L2 resident)
+//   out   = accumulators -> a warp-private fp32 staging tile -> + bias + PE (+ indicator * w_ind per guidance entry)
+//           -> 16-byte stores of 8 features, one row segment of 128 bytes per 8 lanes, to each of the E sequences
+constexpr int kEmRows = 32, kEmK = 80, kEmAPitch = 88, kEmSPitch = 72;
+constexpr int kEmSmem = 2 * kEmRows * kEmAPitch * 2 + 3 * kEmRows * 4 + 8 * kEmRows * kEmSPitch * 4;
+__device__ __forceinline__ void em_ldmatrix_x4(uint32_t (&r)[4], const void* smem_row) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"((uint32_t)__cvta_generic_to_shared(smem_row)));
+}
+__device__ __forceinline__ void em_mma(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+template <bool F16>
+__global__ void __launch_bounds__(256, 2) embed_x_mma_kernel(EmbedParams p) {
+  griddep_launch();
+  griddep_wait();
+  extern __shared__ __align__(16) uint8_t esm[];
+  const int T = 1 + p.Lp + p.L;
+  const int rows_total = p.NX * p.L;
+  const int n_tiles = (rows_total + kEmRows - 1) / kEmRows;
+  if ((int)blockIdx.x >= n_tiles) {                  // context rows ride in the same launch
+    embed_ctx_rows<F16>(p, (int)blockIdx.x - n_tiles);
+    return;
+  }
+  __half* a_hi = reinterpret_cast<__half*>(esm);
+  __half* a_lo = a_hi + kEmRows * kEmAPitch;
+  float* inds = reinterpret_cast<float*>(a_lo + kEmRows * kEmAPitch);      // [3][32]
+  float* stage = inds + 3 * kEmRows;                                         // [8 warps][32][72]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gid = lane >> 2, tig = lane & 3;
+  const int g0 = blockIdx.x * kEmRows;
+  for (int i = tid; i < kEmRows * kEmK; i += 256) {
+    const int r = i / kEmK, k = i - r * kEmK;
+    float v = 0.f;
+    if (k < p.dm && g0 + r < rows_total) v = p.x[(int64_t)(g0 + r) * p.dm + k];
+    const __half hi = __float2half_rn(v);
+    a_hi[r * kEmAPitch + k] = hi;
+    a_lo[r * kEmAPitch + k] = __float2half_rn(v - __half2float(hi));
+  }
+  for (int i = tid; i < 3 * kEmRows; i += 256) {
+    const int e = i / kEmRows, r = i - e * kEmRows, g = g0 + r;
+    float v = 0.f;
+    if (p.indicator != nullptr && e < p.E && g < rows_total) {
+      const int n = g / p.L, l = g - n * p.L;
+      v = p.indicator[(int64_t)(e * p.NX + n) * p.L + l];
+    }
+    inds[i] = v;
+  }
+  __syncthreads();
+
+  const int n0 = warp * 64;
+  float acc[2][8][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[mt][nt][j] = 0.f;
+  const __half* Wh = static_cast<const __half*>(p.Wf16);
+  const __half* Wl = Wh + (int64_t)p.d * kEmK;
+  const int a_off = ((lane & 7) + ((lane >> 3) & 1) * 8) * kEmAPitch + (lane >> 4) * 8;
+#pragma unroll
+  for (int ks = 0; ks < kEmK / 16; ++ks) {
+    uint32_t ah[2][4], al[2][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      em_ldmatrix_x4(ah[mt], a_hi + 16 * mt * kEmAPitch + a_off + 16 * ks);
+      em_ldmatrix_x4(al[mt], a_lo + 16 * mt * kEmAPitch + a_off + 16 * ks);
+    }
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const int64_t wo = (int64_t)(n0 + 8 * nt + gid) * kEmK + 16 * ks + 2 * tig;
+      const uint32_t bh0 = __ldg(reinterpret_cast<const uint32_t*>(Wh + wo)), bh1 = __ldg(reinterpret_cast<const uint32_t*>(Wh + wo + 8));
+      const uint32_t bl0 = __ldg(reinterpret_cast<const uint32_t*>(Wl + wo)), bl1 = __ldg(reinterpret_cast<const uint32_t*>(Wl + wo + 8));
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        em_mma(acc[mt][nt], al[mt], bh0, bh1);   // lo * hi
+        em_mma(acc[mt][nt], ah[mt], bl0, bl1);   // hi * lo
+        em_mma(acc[mt][nt], ah[mt], bh0, bh1);   // hi * hi
+      }
+    }
+  }
+  float* sw = stage + warp * (kEmRows * kEmSPitch);
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      *reinterpret_cast<float2*>(sw + (16 * mt + gid) * kEmSPitch + 8 * nt + 2 * tig) = make_float2(acc[mt][nt][0], acc[mt][nt][1]);
+      *reinterpret_cast<float2*>(sw + (16 * mt + gid + 8) * kEmSPitch + 8 * nt + 2 * tig) = make_float2(acc[mt][nt][2], acc[mt][nt][3]);
+    }
+  __syncwarp();
+  // lane = (row within a group of 4, 8-feature segment): 8 lanes write one 128-byte row segment per entry
+  const int c8 = (lane & 7) * 8, col = n0 + c8;
+  float bias[8], wi[8];
+  {
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bf + col)), b1 = __ldg(reinterpret_cast<const float4*>(p.bf + col + 4));
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.WfT + (int64_t)p.dm * p.d + col));
+    const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.WfT + (int64_t)p.dm * p.d + col + 4));
+    bias[0] = b0.x; bias[1] = b0.y; bias[2] = b0.z; bias[3] = b0.w; bias[4] = b1.x; bias[5] = b1.y; bias[6] = b1.z; bias[7] = b1.w;
+    wi[0] = w0.x; wi[1] = w0.y; wi[2] = w0.z; wi[3] = w0.w; wi[4] = w1.x; wi[5] = w1.y; wi[6] = w1.z; wi[7] = w1.w;
+  }
+#pragma unroll 2
+  for (int it = 0; it < kEmRows / 4; ++it) {
+    const int r = it * 4 + (lane >> 3), g = g0 + r;
+    if (g < rows_total) {
+      const int n = g / p.L, l = g - n * p.L;
+      const float4 s0 = *reinterpret_cast<const float4*>(sw + r * kEmSPitch + c8), s1 = *reinterpret_cast<const float4*>(sw + r * kEmSPitch + c8 + 4);
+      const float* pe = p.PE + (int64_t)(1 + p.Lp + l) * p.d + col;
+      const float4 p0 = __ldg(reinterpret_cast<const float4*>(pe)), p1 = __ldg(reinterpret_cast<const float4*>(pe + 4));
+      float v[8] = {s0.x + (bias[0] + p0.x), s0.y + (bias[1] + p0.y), s0.z + (bias[2] + p0.z), s0.w + (bias[3] + p0.w),
+                    s1.x + (bias[4] + p1.x), s1.y + (bias[5] + p1.y), s1.z + (bias[6] + p1.z), s1.w + (bias[7] + p1.w)};
+      for (int e = 0; e < p.E; ++e) {
+        const float ind = inds[e * kEmRows + r];
+        uint4 o;
+        o.x = pack_h<F16>(fmaf(ind, wi[0], v[0]), fmaf(ind, wi[1], v[1]));
+        o.y = pack_h<F16>(fmaf(ind, wi[2], v[2]), fmaf(ind, wi[3], v[3]));
+        o.z = pack_h<F16>(fmaf(ind, wi[4], v[4]), fmaf(ind, wi[5], v[5]));
+        o.w = pack_h<F16>(fmaf(ind, wi[6], v[6]), fmaf(ind, wi[7], v[7]));
+        *reinterpret_cast<uint4*>(p.out + ((int64_t)(e * p.NX + n) * T + 1 + p.Lp + l) * p.d + col) = o;
+      }
+    }
+  }
+}
 int embed_launch(const EmbedParams& p, cudaStream_t st) {
   ProfileScope prof("embed", st);
+  static const bool use_mma = [] { const char* e = getenv("MSMD_EMBED_MMA"); return e ? atoi(e) != 0 : true; }();
+  if (use_mma && p.Wf16 != nullptr && p.d == 512 && p.dm <= kEmK && p.E <= 3) {
+    static bool attr = false;
+    if (!attr) {
+      MSMD_CHECK_CUDA(cudaFuncSetAttribute(embed_x_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEmSmem));
+      MSMD_CHECK_CUDA(cudaFuncSetAttribute(embed_x_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEmSmem));
+      attr = true;
+    }
+    const int blocks = cdiv(p.NX * p.L, kEmRows) + p.S * (p.Lp + 1);
+    MSMD_CHECK_CUDA(launch_pdl(p.fp16 ? embed_x_mma_kernel<true> : embed_x_mma_kernel<false>, dim3(blocks), dim3(256), kEmSmem, st, p));
+    MSMD_CHECK_LAUNCH();
+    return MSMD_OK;
+  }
   const int blocks = p.NX * ((p.L + kEmbedRows - 1) / kEmbedRows) + p.S * (p.Lp + 1);
   MSMD_CHECK_CUDA(launch_pdl(p.fp16 ? embed_x_kernel<true> : embed_x_kernel<false>, dim3(blocks), dim3(256),
                              (p.dm + 3) * kEmbedPitch * sizeof(float), st, p));
@@ -353,12 +498,54 @@ __global__ void __launch_bounds__(256) ln_kernel(LnParams p) {
     cur = nxt;
   }
 }
+// Default kernel: one row per warp, 8-byte loads, parameters from global memory (46 registers: high occupancy)
+template <int D, bool F16>
+__global__ void __launch_bounds__(256) ln_kernel_v1(LnParams p) {
+  griddep_launch();
+  griddep_wait();
+  constexpr int NV = D / 32;
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= p.M) return;
+  const int s = row / p.T, tok = row % p.T;
+  float v[NV];
+  const bf16* y = p.y + (int64_t)row * D;
+#pragma unroll
+  for (int i = 0; i < NV / 4; ++i) load_h4<F16, false>(y + i * 128 + lane * 4, v + 4 * i);
+  if (p.resid != nullptr) {
+    const bf16* r = p.resid + (int64_t)row * D;
+#pragma unroll
+    for (int i = 0; i < NV / 4; ++i) load_h4<F16, true>(r + i * 128 + lane * 4, v + 4 * i);
+  }
+  if (tok == 0 && p.skip_tok0) return;
+  ln_row<D>(v, p.g1, p.b1, lane);
+  if (tok == 0 && p.x0 != nullptr) {
+#pragma unroll
+    for (int i = 0; i < NV / 4; ++i)
+      store_h4<F16>(p.x0 + (int64_t)s * D + i * 128 + lane * 4, v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    return;
+  }
+  if (p.add != nullptr && tok > 0) {
+    const bf16* a = p.add + ((int64_t)s * (p.T - 1) + (tok - 1)) * D;
+#pragma unroll
+    for (int i = 0; i < NV / 4; ++i) load_h4<F16, true>(a + i * 128 + lane * 4, v + 4 * i);
+    ln_row<D>(v, p.g2, p.b2, lane);
+  }
+  bf16* o = p.out + (int64_t)row * D;
+#pragma unroll
+  for (int i = 0; i < NV / 4; ++i) store_h4<F16>(o + i * 128 + lane * 4, v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+}
 int ln_launch(const LnParams& p, cudaStream_t st) {
   MSMD_REQUIRE(p.d == 512, "ln: only d_model = 512 is instantiated (got %d)", p.d);
   ProfileScope prof(p.add ? "ln1_ln2" : "ln3", st);
-  // rows per warp: 6 makes the configuration-3 grid (21 312 rows) exactly 444 CTAs = 3 resident CTAs on each of the 148 SMs
-  static const int rows = [] { const char* e = getenv("MSMD_LN_ROWS"); return e ? atoi(e) : 6; }();
-  if (p.M <= 148 * 3 * 8) {      // small batches (latency regime): one row per warp, as many CTAs as rows allow
+  // MSMD_LN_ROWS (A/B): 0 = one row per warp with 8-byte loads (default: measured fastest inside the replayed step, where
+  // y and the residual stream come out of L2 and occupancy - 46 registers, 2664 CTAs - hides the load latency);
+  // 1 / 4 / 6 = the 16-byte-load kernel with that many rows per warp (6: one wave of 444 CTAs at configuration 3;
+  // measured 1.2% SLOWER per step than 0 on the same box, 4 rows 3% slower)
+  static const int rows = [] { const char* e = getenv("MSMD_LN_ROWS"); return e ? atoi(e) : 0; }();
+  if (rows == 0) {
+    MSMD_CHECK_CUDA(launch_pdl(p.fp16 ? ln_kernel_v1<512, true> : ln_kernel_v1<512, false>, dim3(cdiv(p.M, 8)), dim3(256), 0, st, p));
+  } else if (rows == 1 || p.M <= 148 * 3 * 8) {
     MSMD_CHECK_CUDA(launch_pdl(p.fp16 ? ln_kernel<512, true, 1> : ln_kernel<512, false, 1>, dim3(cdiv(p.M, 8)), dim3(256), 0, st, p));
   } else if (rows == 4 || p.M < 148 * 3 * 8 * 4) {
     MSMD_CHECK_CUDA(launch_pdl(p.fp16 ? ln_kernel<512, true, 4> : ln_kernel<512, false, 4>, dim3(cdiv(p.M, 8 * 4)), dim3(256), 0, st, p));
@@ -539,7 +726,14 @@ __device__ __forceinline__ void split_target(const float* dec, const float* stat
 __global__ void __launch_bounds__(256) update_kernel(const UpdateParams* __restrict__ pp) {
   griddep_launch();
   griddep_wait();
-  const UpdateParams p = *pp;
+  // the parameter block is read through shared memory: as a local copy of *pp its ~30 fields were re-fetched from global
+  // memory (generic loads) all over the loop, one more dependent latency in front of every data load
+  __shared__ __align__(16) unsigned char p_raw[sizeof(UpdateParams)];
+  static_assert(sizeof(UpdateParams) % 4 == 0, "UpdateParams is copied in 32-bit words");
+  for (int i = threadIdx.x; i < (int)(sizeof(UpdateParams) / 4); i += blockDim.x)
+    reinterpret_cast<uint32_t*>(p_raw)[i] = reinterpret_cast<const uint32_t*>(pp)[i];
+  __syncthreads();
+  const UpdateParams& p = *reinterpret_cast<const UpdateParams*>(p_raw);
   const int64_t n_el = (int64_t)p.NX * p.L * p.dm;
   const int t = p.steps[0];
   // model.py:383-386, :421-428 - 0-dim fp32 tensor arithmetic, same operation order
@@ -560,18 +754,41 @@ __global__ void __launch_bounds__(256) update_kernel(const UpdateParams* __restr
   const int rows = p.NX * p.L;
   for (int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += gridDim.x * (blockDim.x >> 5)) {
     const int n = row / p.L, l = row - n * p.L;
+    // per-row invariants of the (<= 3) guidance entries: decoder row, static-basis block, threshold, mixing weights
+    const float* rowp[3];
+    const float* stp[3];
+    float thv[3], al[3][4];
+#pragma unroll
+    for (int e = 0; e < 3; ++e) {
+      const int sq = (e < p.E ? e : 0) * p.NX + n;
+      rowp[e] = p.dec + ((int64_t)sq * p.T + 1 + p.Lp + l) * p.ldd;
+      stp[e] = p.stat + (int64_t)sq * p.nb * p.dm;
+      thv[e] = p.thr ? p.thr[sq] : 0.f;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) al[e][b] = b < p.nb ? rowp[e][p.dm + b] : 0.f;
+    }
    for (int c = lane; c < p.dm; c += 32) {
     const int64_t i = (int64_t)row * p.dm + c;
+    const bool face = c < p.dm - 3;
     // CFG combine (model.py:404-417); results[0] is updated in place through a view, so 'independent'
     // subtracts the running target.  The same recursion runs on the dynamic / static parts
     // (model.py:603-626) when the separate outputs are requested.
     float tgt = 0.f, prev = 0.f, td = 0.f, pd = 0.f, ts = 0.f, psv = 0.f;
-    for (int e = 0; e < p.E; ++e) {
-      const int s = e * p.NX + n;
-      float dyn, sta;
-      split_target(p.dec, p.stat, p.T, p.Lp, p.dm, p.nb, p.ldd, s, l, c, dyn, sta);
+#pragma unroll
+    for (int e = 0; e < 3; ++e) {
+      if (e >= p.E) break;
+      // split_target() with the row's pointers / mixing weights held in registers (same operation order)
+      const float dyn = rowp[e][c];
+      float sta = 0.f;
+      if (p.nb <= 4) {
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+          if (b < p.nb) sta += (face ? al[e][b] : 1.0f) * stp[e][b * p.dm + c];
+      } else {
+        for (int b = 0; b < p.nb; ++b) sta += (face ? rowp[e][p.dm + b] : 1.0f) * stp[e][b * p.dm + c];
+      }
       float r = dyn + sta;
-      if (p.thr) { const float th = p.thr[s]; r = fminf(fmaxf(r, -th), th); }
+      if (p.thr) { const float th = thv[e]; r = fminf(fmaxf(r, -th), th); }
       if (e == 0) {
         tgt = r; td = dyn; ts = sta;
       } else {
@@ -693,7 +910,9 @@ int update_params_set(UpdateParams* d_dst, const UpdateParams& p, cudaStream_t s
 int update_launch(const UpdateParams* d_p, int NX, int L, int dm, cudaStream_t st) {
   (void)dm;
   ProfileScope prof("update", st);
-  MSMD_CHECK_CUDA(launch_pdl(update_kernel, dim3(std::min(cdiv(NX * L, 8), kNumSMs * 8)), dim3(256), 0, st, d_p));   // warp per row
+  // warp per row, ONE wave (2 CTAs of 123 registers per SM): every CTA starts with a chain of dependent scalar loads
+  // (parameter block -> step index -> schedule coefficients, ~2 us); the 4-wave grid of round 1 paid it four times
+  MSMD_CHECK_CUDA(launch_pdl(update_kernel, dim3(std::min(cdiv(NX * L, 8), kNumSMs * 2)), dim3(256), 0, st, d_p));
   MSMD_CHECK_LAUNCH();
   return MSMD_OK;
 }

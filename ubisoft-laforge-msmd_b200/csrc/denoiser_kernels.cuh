@@ -32,6 +32,8 @@ struct EmbedParams {
   const float* indicator; // [S, L] or null (-> no indicator column)
   const float* WfT;       // [dm+1, d] feature_proj weight transposed (k-major), fp32
   const float* bf;        // [d]
+  const void* Wf16;       // [2][d][80] fp16: hi | lo halves of feature_proj.weight[:, :dm] (K zero-padded to 80), or null
+                          // (-> the CUDA-core kernel); the tensor-core embedding (embed_x_mma_kernel) needs d = 512, dm <= 80
   bf16* out;              // [S, 1+Lp+L, d]
   int S, NX, E, Lp, L, d, dm;
   int fp16;               // storage format of `out`
