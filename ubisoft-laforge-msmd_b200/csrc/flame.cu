@@ -39,9 +39,10 @@ __global__ void __launch_bounds__(256) flame_pose_kernel(const float* __restrict
     const float v = be[k];
     Arow[k] = v;
     if (A_hi) {
-      const __half hi = __float2half_rn(v);
+      const float sv = v * kFlameScaleA;
+      const __half hi = __float2half_rn(sv);
       A_hi[b * Kpad + k] = hi;
-      A_lo[b * Kpad + k] = __float2half_rn((v - __half2float(hi)) * 2048.0f);
+      A_lo[b * Kpad + k] = __float2half_rn(sv - __half2float(hi));
     }
 #pragma unroll
     for (int i = 0; i < NJ * 3; ++i) acc[i] = fmaf(Jb[i * NB + k], v, acc[i]);
@@ -84,9 +85,10 @@ __global__ void __launch_bounds__(256) flame_pose_kernel(const float* __restrict
       const int k = NB + (j - 1) * 9 + i;
       Arow[k] = v;
       if (A_hi) {
-        const __half hi = __float2half_rn(v);
+        const float sv = v * kFlameScaleA;
+        const __half hi = __float2half_rn(sv);
         A_hi[b * Kpad + k] = hi;
-        A_lo[b * Kpad + k] = __float2half_rn((v - __half2float(hi)) * 2048.0f);
+        A_lo[b * Kpad + k] = __float2half_rn(sv - __half2float(hi));
       }
     }
 
@@ -320,8 +322,14 @@ extern "C" int msmd_flame_create(const float* v_template, const float* shapedirs
     for (int p = 0; p < P; ++p) row[NB + p] = h_p[(size_t)p * N3 + n];
   }
   for (size_t i = 0; i < basis.size(); ++i) {
-    hi[i] = __float2half_rn(basis[i]);
-    lo[i] = __float2half_rn((basis[i] - __half2float(hi[i])) * 2048.0f);
+    const float sv = basis[i] * kFlameScaleB;
+    if (!(fabsf(sv) < 60000.0f)) {   // |entry| >= 234: not a blendshape basis in metres (and it would overflow the fp16 split)
+      delete fh;
+      set_error("msmd_flame_create: blendshape basis entry %g is outside the range of the fp16 two-term split (|x| < 234)", basis[i]);
+      return MSMD_ERR_INVALID;
+    }
+    hi[i] = __float2half_rn(sv);
+    lo[i] = __float2half_rn(sv - __half2float(hi[i]));
   }
   // Joint regression folded through the blendshapes (double accumulation on the host).
   std::vector<float> Jt(NJ * 3), Jb((size_t)NJ * 3 * NB);

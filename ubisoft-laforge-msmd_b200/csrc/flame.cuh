@@ -14,8 +14,10 @@ struct msmd_flame {
   int parents[8] = {-1, 0, 1, 1, 1, 0, 0, 0};
   // static device buffers
   float* basis = nullptr;     // [N3pad, Kpad] K-major: row n=(v,c): shapedirs[v,c,:] | posedirs[:,n] | 0
-  // fp16 two-term split for the 3-pass tensor-core path (flame_tc.cu): x = hi + lo * 2^-11 with hi = fp16(x),
-  // lo = fp16((x - hi) * 2^11): 22 mantissa bits, the residual kept out of the fp16 subnormal range by the scale
+  // fp16 two-term split for the 3-pass tensor-core path (flame_tc.cu): s x = hi + lo with hi = fp16(s x),
+  // lo = fp16(s x - hi): 22 mantissa bits.  hi and lo share ONE scale (s = kFlameScaleB for the basis, kFlameScaleA for
+  // the coefficients) so that hi*hi, lo*hi and hi*lo can be summed in the same TMEM accumulator; the scales keep the
+  // residuals of the small basis entries (1e-3 m) inside the fp16 normal range.  The epilogue multiplies by 1 / (sA sB).
   __half* basis_hi = nullptr;
   __half* basis_lo = nullptr;
   float* v_template = nullptr;  // [N3]
@@ -35,6 +37,7 @@ struct msmd_flame {
 };
 
 namespace msmd {
+constexpr float kFlameScaleA = 16.0f, kFlameScaleB = 256.0f;
 int flame_decode_tc(msmd_flame* fh, int64_t B, float* verts_out, cudaStream_t st);  // flame_tc.cu
 void flame_tc_destroy(msmd_flame* fh);
 }  // namespace msmd

@@ -5,17 +5,21 @@
 //
 //   tile      = 256 frames x 126 columns on a CTA PAIR (cta_group::2; 42 whole vertices; the MMA is issued with
 //               N = 128, the last two columns are junk and never stored).  Each CTA stages its own 128 frames of
-//               A and HALF of the basis tile: 48 KB of operands per k-block per SM instead of 64 KB — the
-//               single-CTA tile needed ~84 B/clk of operands per SM against the ~60 the L2->SM path delivers.
-//   operands  = two-term fp16 splits x = hi + 2^-11 lo (22 mantissa bits; flame.cuh) of A [B,Kpad] (betas |
-//               vec(R-I) | 0) and of the basis [3V,Kpad], K-major, TMA -> 128B-swizzled smem, 3 stages x 48 KB of
+//               A and HALF of the basis tile.  TWO neighbouring column tiles are computed together ("super-tile"):
+//               every k-block of A feeds both, so the operand bytes per tile drop from 48 KB to 32 KB per k-block per
+//               SM.  The kernel is bound by the L2 -> SM delivery of its operands (ncu: 3.05 GB in 423 us = the
+//               7.2 TB/s every TMA-fed kernel of this library tops out at, tensor pipe 42% active), not by the MMAs.
+//   operands  = two-term fp16 splits s x = hi + lo (22 mantissa bits; flame.cuh) of A [B,Kpad] (betas |
+//               vec(R-I) | 0) and of the basis [3V,Kpad], K-major, TMA -> 128B-swizzled smem, 2 stages x 64 KB of
 //               64-deep k-blocks.  (The tf32 hi/lo version of this kernel was bound by shared-memory bandwidth:
 //               a K=8 tf32 MMA reads as many operand bytes as a K=16 fp16 one for half the FLOPs.)
 //   MMA       = kind::f16 (fp16 in, fp32 accumulate), M256 N128 K16 issued by the leader CTA, three passes per
-//               k-step: hi*hi -> accumulator 0 (exact products), lo*hi + hi*lo -> accumulator 1, scaled by 2^-11
-//               in the epilogue (kept apart: the tensor core truncates when it accumulates)
-//   TMEM      = per CTA 2 stages x (128 + 128) columns: the epilogue of tile i overlaps the MMAs of tile i+1
-//   epilogue  = thread <-> frame: v_posed = acc0 + acc1 + template, T = sum_j w[v][j] * A_j[b] (5 joints x 12
+//               k-step and column tile: lo*hi, hi*lo, hi*hi into ONE accumulator (hi and lo carry the same scale).
+//               Round 1 kept the cross terms in a second accumulator; sharing one costs ~3 more truncating
+//               accumulations per k-step (measured error in tests/test_flame_gpu.py, bound 1e-5) and halves the
+//               TMEM per tile, which is what lets two column tiles stay double-buffered.
+//   TMEM      = per CTA 2 stages x 2 column tiles x 128 columns: the epilogue of super-tile i overlaps the MMAs of i+1
+//   epilogue  = thread <-> frame: v_posed = acc / (sA sB) + template, T = sum_j w[v][j] * A_j[b] (5 joints x 12
 //               coefficients held in registers), x = T [v_posed; 1]; staged through smem for coalesced stores
 #include "flame.cuh"
 #include "tc_common.cuh"
@@ -26,22 +30,19 @@ namespace msmd {
 
 namespace {
 
-#ifdef MSMD_FLAME_EXP   // timing experiment only (wrong results): all quarters share one staging buffer -> room for a 4th stage
-constexpr int FT_STAGES = 4, FT_NQ = 1;
-#else
-constexpr int FT_STAGES = 3, FT_NQ = 4;
-#endif
+constexpr int FT_STAGES = 2, FT_NQ = 4, FT_G = 2;       // FT_G column tiles share every A k-block
 constexpr int FT_BM = 128, FT_VERT = 42, FT_BN = 126, FT_UN = 128, FT_BK = 64;
 constexpr int FT_TILE_BYTES = 128 * 128;                 // one operand tile: 128 rows x 128 B
 constexpr int FT_BHALF_BYTES = 64 * 128;                 // this CTA's half of a basis tile: 64 rows x 128 B
-constexpr int FT_STAGE_BYTES = 2 * FT_TILE_BYTES + 2 * FT_BHALF_BYTES;   // A_hi, A_lo, B_hi half, B_lo half
+constexpr int FT_STAGE_BYTES = 2 * FT_TILE_BYTES + FT_G * 2 * FT_BHALF_BYTES;   // A_hi, A_lo, then per column tile: B_hi half, B_lo half
 constexpr int FT_CHUNK_V = 8;                             // vertices per epilogue chunk (24 accumulator columns)
 constexpr int FT_OUT_STRIDE = 127;                       // staging row stride (floats): odd -> conflict-free
 constexpr int FT_EPI_WARPS = 8;                          // two warps per TMEM lane quarter, alternating chunks
 constexpr int FT_EPI_Q_BYTES = 32 * FT_OUT_STRIDE * 4;    // one TMEM lane quarter (32 frames) x the tile's 126 columns
 constexpr int FT_MISC_BYTES = 2048;                      // barriers, tmem slot
 constexpr int FT_VC_FLOATS = (FT_VERT + 6) * 8;          // per-tile vertex constants (w0..w4 | template), padded to 48 vertices
-constexpr int FT_SMEM_BYTES = 1024 + FT_STAGES * FT_STAGE_BYTES + FT_NQ * FT_EPI_Q_BYTES + FT_MISC_BYTES + 2 * FT_VC_FLOATS * 4;
+constexpr int FT_SMEM_BYTES = 1024 + FT_STAGES * FT_STAGE_BYTES + FT_NQ * FT_EPI_Q_BYTES + FT_MISC_BYTES + 2 * FT_G * FT_VC_FLOATS * 4;
+static_assert(FT_SMEM_BYTES <= 227 * 1024, "flame_tc shared memory");
 constexpr int FT_THREADS = 64 + 32 * FT_EPI_WARPS;
 
 struct FlameTcParams {
@@ -49,7 +50,7 @@ struct FlameTcParams {
   const float* vconst;   // [V(+pad), 8]  w0..w4 | template xyz
   const float* xf;       // [B,60]
   float* out;            // [B,3V]
-  int B, V, N3, num_kb, tiles_m, tiles_n;
+  int B, V, N3, num_kb, tiles_m, tiles_n, tiles_n2;   // tiles_n2 = ceil(tiles_n / FT_G) super-tile columns
   unsigned long long* trace;   // -DMSMD_FLAME_TRACE builds: clock64 stamps of CTA 0, [role 0..2][tile 0..15][4]
 };
 
@@ -91,11 +92,11 @@ __global__ void __launch_bounds__(FT_THREADS, 1) flame_tc_kernel(const __grid_co
   uint64_t* tfull_bar = empty_bar + FT_STAGES;             // [2]
   uint64_t* tempty_bar = tfull_bar + 2;                    // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  float* tile_w = reinterpret_cast<float*>(misc + FT_MISC_BYTES);  // [2][48 vertices][8]: w0..w4 | template xyz
+  float* tile_w = reinterpret_cast<float*>(misc + FT_MISC_BYTES);  // [2][FT_G][48 vertices][8]: w0..w4 | template xyz
   constexpr int TILE_W_FLOATS = FT_VC_FLOATS;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_tiles = p.tiles_m * p.tiles_n;
+  const int num_tiles = p.tiles_m * p.tiles_n2;     // super-tiles
   const int cta_rank = (int)cluster_ctarank();
   const int pair = (int)blockIdx.x / 2, npairs = (int)gridDim.x / 2;
 
@@ -116,7 +117,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) flame_tc_kernel(const __grid_co
     int s = 0, pit = 0;
     uint32_t ph = 0;
     for (int t = pair; t < num_tiles; t += npairs, ++pit) {
-      const int m0 = (t / p.tiles_n) * 2 * FT_BM + cta_rank * FT_BM, n0 = (t % p.tiles_n) * FT_BN + cta_rank * 64;
+      const int m0 = (t / p.tiles_n2) * 2 * FT_BM + cta_rank * FT_BM, n0 = (t % p.tiles_n2) * FT_G * FT_BN + cta_rank * 64;
       for (int kb = 0; kb < p.num_kb; ++kb) {
         if (lane == 0) {
           if (kb == 0) ft_stamp(p.trace, 0, pit, 0);
@@ -125,12 +126,17 @@ __global__ void __launch_bounds__(FT_THREADS, 1) flame_tc_kernel(const __grid_co
           if (kb == p.num_kb - 1) ft_stamp(p.trace, 0, pit, 2);
           uint8_t* st = stage_base + s * FT_STAGE_BYTES;
           // both CTAs' boxes land on the leader's barrier.  Rank 1's basis half covers tile columns 64..127: the
-          // last two rows belong to the next tile (or are zero-filled past the end) and only feed junk columns
+          // last two rows belong to the next tile (or are zero-filled past the end) and only feed junk columns.  A
+          // column tile past the last one (odd tile count) reads zero rows / is zero-filled: its results are never stored.
           if (cta_rank == 0) mbar_expect_tx(&full_bar[s], 2 * FT_STAGE_BYTES);
           tma_load_2d_2sm(st, &p.a_hi, &full_bar[s], kb * FT_BK, m0);
           tma_load_2d_2sm(st + FT_TILE_BYTES, &p.a_lo, &full_bar[s], kb * FT_BK, m0);
-          tma_load_2d_2sm(st + 2 * FT_TILE_BYTES, &p.b_hi, &full_bar[s], kb * FT_BK, n0);
-          tma_load_2d_2sm(st + 2 * FT_TILE_BYTES + FT_BHALF_BYTES, &p.b_lo, &full_bar[s], kb * FT_BK, n0);
+#pragma unroll
+          for (int g = 0; g < FT_G; ++g) {
+            uint8_t* sb = st + 2 * FT_TILE_BYTES + g * 2 * FT_BHALF_BYTES;
+            tma_load_2d_2sm(sb, &p.b_hi, &full_bar[s], kb * FT_BK, n0 + g * FT_BN);
+            tma_load_2d_2sm(sb + FT_BHALF_BYTES, &p.b_lo, &full_bar[s], kb * FT_BK, n0 + g * FT_BN);
+          }
         }
         __syncwarp();
         if (++s == FT_STAGES) { s = 0; ph ^= 1; }
@@ -144,7 +150,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) flame_tc_kernel(const __grid_co
     for (int t = cta_rank == 0 ? pair : num_tiles; t < num_tiles; t += npairs, ++it) {   // leader only
       const int a = it & 1;
       const uint32_t aph = (it >> 1) & 1;
-      const uint32_t d_main = tmem_base + a * 256, d_cross = d_main + 128;
+      const uint32_t d_acc = tmem_base + a * (FT_G * 128);
       if (lane == 0) {
         ft_stamp(p.trace, 1, it, 0);
         mbar_wait(&tempty_bar[a], aph ^ 1);
@@ -159,16 +165,18 @@ __global__ void __launch_bounds__(FT_THREADS, 1) flame_tc_kernel(const __grid_co
           if (kb == 0) ft_stamp(p.trace, 1, it, 2);
           const uint32_t sa = smem_u32(stage_base + s * FT_STAGE_BYTES);
           const uint64_t ah = make_smem_desc_sw128(sa), al = make_smem_desc_sw128(sa + FT_TILE_BYTES);
-          const uint64_t bh = make_smem_desc_sw128(sa + 2 * FT_TILE_BYTES);
-          const uint64_t bl = make_smem_desc_sw128(sa + 2 * FT_TILE_BYTES + FT_BHALF_BYTES);
 #pragma unroll
           for (int k = 0; k < FT_BK / 16; ++k) {
             const uint32_t acc = (kb | k) != 0;
-#ifndef MSMD_FLAME_EXP2   // timing experiment: main pass only
-            umma_2sm(d_cross, desc_advance(al, k * 32), desc_advance(bh, k * 32), idesc, acc);  // lo * hi
-            umma_2sm(d_cross, desc_advance(ah, k * 32), desc_advance(bl, k * 32), idesc, 1u);   // hi * lo
-#endif
-            umma_2sm(d_main, desc_advance(ah, k * 32), desc_advance(bh, k * 32), idesc, acc);   // hi * hi
+#pragma unroll
+            for (int g = 0; g < FT_G; ++g) {
+              const uint32_t sb = sa + 2 * FT_TILE_BYTES + g * 2 * FT_BHALF_BYTES;
+              const uint64_t bh = make_smem_desc_sw128(sb), bl = make_smem_desc_sw128(sb + FT_BHALF_BYTES);
+              const uint32_t d = d_acc + g * 128;
+              umma_2sm(d, desc_advance(al, k * 32), desc_advance(bh, k * 32), idesc, acc);   // lo * hi
+              umma_2sm(d, desc_advance(ah, k * 32), desc_advance(bl, k * 32), idesc, 1u);    // hi * lo
+              umma_2sm(d, desc_advance(ah, k * 32), desc_advance(bh, k * 32), idesc, 1u);    // hi * hi
+            }
           }
           umma_commit_2sm(&empty_bar[s]);
         }
@@ -188,14 +196,18 @@ __global__ void __launch_bounds__(FT_THREADS, 1) flame_tc_kernel(const __grid_co
     constexpr int NCHUNK = (FT_VERT + FT_CHUNK_V - 1) / FT_CHUNK_V;
     int it = 0;
     for (int t = pair; t < num_tiles; t += npairs, ++it) {
-      const int m0 = (t / p.tiles_n) * 2 * FT_BM + cta_rank * FT_BM, n0 = (t % p.tiles_n) * FT_BN;
+      const int m0 = (t / p.tiles_n2) * 2 * FT_BM + cta_rank * FT_BM;
+      const int nt0 = (t % p.tiles_n2) * FT_G;                    // first column tile of the super-tile
+      const int ng = min(FT_G, p.tiles_n - nt0);                  // column tiles that exist
       const int a = it & 1;
       const uint32_t aph = (it >> 1) & 1;
-      const int v0 = n0 / 3;
-      // per-tile vertex constants -> smem (double-buffered by tile parity); 16-byte copies
-      float* tw = tile_w + a * TILE_W_FLOATS;
-      for (int i = etid; i < FT_VC_FLOATS / 4; i += EPI_THREADS)
-        reinterpret_cast<float4*>(tw)[i] = __ldg(reinterpret_cast<const float4*>(p.vconst + (int64_t)v0 * 8) + i);
+      // per-tile vertex constants -> smem (double-buffered by super-tile parity); 16-byte copies
+      float* tw_all = tile_w + a * (FT_G * TILE_W_FLOATS);
+      for (int i = etid; i < ng * (FT_VC_FLOATS / 4); i += EPI_THREADS) {
+        const int g = i / (FT_VC_FLOATS / 4), r = i - g * (FT_VC_FLOATS / 4);
+        const int v0g = (nt0 + g) * FT_VERT;
+        reinterpret_cast<float4*>(tw_all + g * TILE_W_FLOATS)[r] = __ldg(reinterpret_cast<const float4*>(p.vconst + (int64_t)v0g * 8) + r);
+      }
       // this thread's frame: 5 joints x (3x3 | t); with normalised weights joints 1..4 are kept as differences to joint 0
       const int row = m0 + q * 32 + lane;
       float xf[60];
@@ -218,86 +230,97 @@ __global__ void __launch_bounds__(FT_THREADS, 1) flame_tc_kernel(const __grid_co
       mbar_wait(&tfull_bar[a], aph);
       tc_fence_after();
       if (warp == 2 && lane == 0) ft_stamp(p.trace, 2, it, 1);
-      const uint32_t t_main = tmem_base + ((uint32_t)(q * 32) << 16) + a * 256, t_cross = t_main + 128;
-      // 8-vertex chunks (24 accumulator columns); the last one (ck = 5) holds 2 vertices.  This warp takes chunks
-      // half, half + 2, half + 4; the TMEM reads of its next chunk are in flight while the current one is skinned.
-      auto load_chunk = [&](int ck, uint32_t (&m)[24], uint32_t (&c)[24]) {
-        const int c0 = ck * 3 * FT_CHUNK_V;
-        if (ck < NCHUNK - 1) {
-          tmem_ld16(t_main + c0, m); tmem_ld8(t_main + c0 + 16, m + 16);
-          tmem_ld16(t_cross + c0, c); tmem_ld8(t_cross + c0 + 16, c + 16);
-        } else {   // columns 120..125; an x16 load would run past the 128-column accumulator
-          tmem_ld8(t_main + c0, m);
-          tmem_ld8(t_cross + c0, c);
-        }
-      };
-      auto skin_chunk = [&](int ck, const uint32_t (&m)[24], const uint32_t (&c)[24]) {
-        const int nv = min(FT_CHUNK_V, FT_VERT - ck * FT_CHUNK_V);
-#pragma unroll
-        for (int v = 0; v < FT_CHUNK_V; ++v) {
-          if (v < nv) {
-            const int vv = ck * FT_CHUNK_V + v, cc = 3 * vv;
-            const float4 wa = *reinterpret_cast<const float4*>(tw + vv * 8);       // w0 w1 w2 w3   (broadcast)
-            const float4 wb = *reinterpret_cast<const float4*>(tw + vv * 8 + 4);   // w4 tx ty tz
-            constexpr float kLo = 1.0f / 2048.0f;   // the residual terms were scaled by 2^11 (flame.cuh)
-            const float px = __uint_as_float(m[3 * v]) + fmaf(__uint_as_float(c[3 * v]), kLo, wb.y);
-            const float py = __uint_as_float(m[3 * v + 1]) + fmaf(__uint_as_float(c[3 * v + 1]), kLo, wb.z);
-            const float pz = __uint_as_float(m[3 * v + 2]) + fmaf(__uint_as_float(c[3 * v + 2]), kLo, wb.w);
-            float T[12];
-#pragma unroll
-            for (int e = 0; e < 12; ++e) {
-              float s = NORM ? xf[e] : wa.x * xf[e];
-              s = fmaf(wa.y, xf[12 + e], s);
-              s = fmaf(wa.z, xf[24 + e], s);
-              s = fmaf(wa.w, xf[36 + e], s);
-              T[e] = fmaf(wb.x, xf[48 + e], s);
-            }
-            stage[lane * FT_OUT_STRIDE + cc + 0] = fmaf(T[0], px, fmaf(T[1], py, fmaf(T[2], pz, T[9])));
-            stage[lane * FT_OUT_STRIDE + cc + 1] = fmaf(T[3], px, fmaf(T[4], py, fmaf(T[5], pz, T[10])));
-            stage[lane * FT_OUT_STRIDE + cc + 2] = fmaf(T[6], px, fmaf(T[7], py, fmaf(T[8], pz, T[11])));
-          }
-        }
-      };
-      {
-        uint32_t mA[24], cA[24], mB[24], cB[24];
-        load_chunk(half, mA, cA);
-        tmem_ld_wait();
-        load_chunk(half + 2, mB, cB);
-        skin_chunk(half, mA, cA);
-        tmem_ld_wait();
-        load_chunk(half + 4, mA, cA);
-        skin_chunk(half + 2, mB, cB);
-        tmem_ld_wait();
-        skin_chunk(half + 4, mA, cA);
-      }
-      if (warp == 2 && lane == 0) ft_stamp(p.trace, 2, it, 2);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {   // accumulators are consumed: the MMAs of the next tile may overwrite them during the stores
-        if (cta_rank != 0) mbar_arrive_cluster(&tempty_bar[a], 0);   // the leader's MMA warp waits for both CTAs
-        else mbar_arrive(&tempty_bar[a]);
-      }
-      // both warps of the quarter have staged their vertices: store whole 504-byte tile rows, coalesced; four rows'
-      // shared-memory reads are issued together so the stores stream instead of paying one LDS latency per row
-      asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
-      const int ncol = min(FT_BN, p.N3 - n0);
 #pragma unroll 1
-      for (int r0 = half; r0 < 32; r0 += 8) {
-        float val[4][4];
+      for (int g = 0; g < FT_G; ++g) {
+        const float* tw = tw_all + g * TILE_W_FLOATS;
+        const int n0 = (nt0 + g) * FT_BN;
+        const uint32_t t_main = tmem_base + ((uint32_t)(q * 32) << 16) + a * (FT_G * 128) + g * 128;
+        if (g < ng) {
+          // 8-vertex chunks (24 accumulator columns); the last one (ck = 5) holds 2 vertices.  This warp takes chunks
+          // half, half + 2, half + 4; the TMEM reads of its next chunk are in flight while the current one is skinned.
+          auto load_chunk = [&](int ck, uint32_t (&m)[24]) {
+            const int c0 = ck * 3 * FT_CHUNK_V;
+            if (ck < NCHUNK - 1) {
+              tmem_ld16(t_main + c0, m); tmem_ld8(t_main + c0 + 16, m + 16);
+            } else {   // columns 120..125; an x16 load would run past the 128-column accumulator
+              tmem_ld8(t_main + c0, m);
+            }
+          };
+          auto skin_chunk = [&](int ck, const uint32_t (&m)[24]) {
+            const int nv = min(FT_CHUNK_V, FT_VERT - ck * FT_CHUNK_V);
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+            for (int v = 0; v < FT_CHUNK_V; ++v) {
+              if (v < nv) {
+                const int vv = ck * FT_CHUNK_V + v, cc = 3 * vv;
+                const float4 wa = *reinterpret_cast<const float4*>(tw + vv * 8);       // w0 w1 w2 w3   (broadcast)
+                const float4 wb = *reinterpret_cast<const float4*>(tw + vv * 8 + 4);   // w4 tx ty tz
+                constexpr float kInv = 1.0f / (kFlameScaleA * kFlameScaleB);            // the operands carried these scales
+                const float px = fmaf(__uint_as_float(m[3 * v]), kInv, wb.y);
+                const float py = fmaf(__uint_as_float(m[3 * v + 1]), kInv, wb.z);
+                const float pz = fmaf(__uint_as_float(m[3 * v + 2]), kInv, wb.w);
+                float T[12];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) val[u][k] = (lane + 32 * k < FT_BN) ? stage[(r0 + 2 * u) * FT_OUT_STRIDE + lane + 32 * k] : 0.f;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int grow = m0 + q * 32 + r0 + 2 * u;
-          if (grow < p.B) {
-            float* dst = p.out + (int64_t)grow * p.N3 + n0;
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              if (lane + 32 * k < ncol) __stcs(dst + lane + 32 * k, val[u][k]);
+                for (int e = 0; e < 12; ++e) {
+                  float s = NORM ? xf[e] : wa.x * xf[e];
+                  s = fmaf(wa.y, xf[12 + e], s);
+                  s = fmaf(wa.z, xf[24 + e], s);
+                  s = fmaf(wa.w, xf[36 + e], s);
+                  T[e] = fmaf(wb.x, xf[48 + e], s);
+                }
+                stage[lane * FT_OUT_STRIDE + cc + 0] = fmaf(T[0], px, fmaf(T[1], py, fmaf(T[2], pz, T[9])));
+                stage[lane * FT_OUT_STRIDE + cc + 1] = fmaf(T[3], px, fmaf(T[4], py, fmaf(T[5], pz, T[10])));
+                stage[lane * FT_OUT_STRIDE + cc + 2] = fmaf(T[6], px, fmaf(T[7], py, fmaf(T[8], pz, T[11])));
+              }
+            }
+          };
+          {
+            uint32_t mA[24], mB[24];
+            load_chunk(half, mA);
+            tmem_ld_wait();
+            load_chunk(half + 2, mB);
+            skin_chunk(half, mA);
+            tmem_ld_wait();
+            load_chunk(half + 4, mA);
+            skin_chunk(half + 2, mB);
+            tmem_ld_wait();
+            skin_chunk(half + 4, mA);
           }
         }
+        if (g == FT_G - 1) {
+          if (warp == 2 && lane == 0) ft_stamp(p.trace, 2, it, 2);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {   // accumulators are consumed: the MMAs of the next super-tile may overwrite them during the stores
+            if (cta_rank != 0) mbar_arrive_cluster(&tempty_bar[a], 0);   // the leader's MMA warp waits for both CTAs
+            else mbar_arrive(&tempty_bar[a]);
+          }
+        }
+        // both warps of the quarter have staged their vertices: store whole 504-byte tile rows, coalesced; four rows'
+        // shared-memory reads are issued together so the stores stream instead of paying one LDS latency per row
+        asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
+        if (g < ng) {
+          const int ncol = min(FT_BN, p.N3 - n0);
+#pragma unroll 1
+          for (int r0 = half; r0 < 32; r0 += 8) {
+            float val[4][4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+              for (int k = 0; k < 4; ++k) val[u][k] = (lane + 32 * k < FT_BN) ? stage[(r0 + 2 * u) * FT_OUT_STRIDE + lane + 32 * k] : 0.f;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int grow = m0 + q * 32 + r0 + 2 * u;
+              if (grow < p.B) {
+                float* dst = p.out + (int64_t)grow * p.N3 + n0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  if (lane + 32 * k < ncol) __stcs(dst + lane + 32 * k, val[u][k]);
+              }
+            }
+          }
+        }
+        // the quarter's staging buffer is rewritten by the next column tile: both warps are done reading it
+        asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
       }
       if (warp == 2 && lane == 0) ft_stamp(p.trace, 2, it, 3);
     }
@@ -328,13 +351,14 @@ int flame_decode_tc(msmd_flame* fh, int64_t B, float* verts_out, cudaStream_t st
   p.B = (int)B; p.V = fh->V; p.N3 = fh->N3; p.num_kb = fh->Kpad / FT_BK;
   p.tiles_m = cdiv(B, 2 * FT_BM);
   p.tiles_n = cdiv(fh->N3, FT_BN);
+  p.tiles_n2 = cdiv(p.tiles_n, FT_G);
   static bool attr = false;
   if (!attr) {
     MSMD_CHECK_CUDA(cudaFuncSetAttribute(flame_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM_BYTES));
     MSMD_CHECK_CUDA(cudaFuncSetAttribute(flame_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM_BYTES));
     attr = true;
   }
-  const int tiles = p.tiles_m * p.tiles_n;
+  const int tiles = p.tiles_m * p.tiles_n2;
   ProfileScope prof("flame_fused", st);
   const int pairs = tiles < kNumSMs / 2 ? tiles : kNumSMs / 2;
   cudaLaunchConfig_t cfg = {};
