@@ -138,15 +138,43 @@ static int launch_cfg2(const GemmDesc& d, cudaStream_t st) {
   ProfileScope prof2(profiling_on() ? strdup(shape_name) : "", st);
   if constexpr (Cfg::CTA2) {
     const int sms = (d.max_ctas > 0 && d.max_ctas < kNumSMs) ? d.max_ctas : kNumSMs;
-    const int pairs = tiles < sms / 2 ? tiles : sms / 2;
+    int pairs = tiles < sms / 2 ? tiles : sms / 2;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * pairs);
     cfg.blockDim = dim3(Cfg::THREADS);
     cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
     cfg.stream = st;
     cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    // Clusters of 4 = two pairs on neighbouring column tiles of the same rows, the A tile fetched once and multicast
+    // (default; MSMD_GEMM_CL4=0 disables).  Bit-identical results, -1.1% per sampling step on one box: the L2 reads
+    // drop by a quarter but the main loop is bound on the SM side (TMA fill 64 B/clk + MMA operand reads 64 B/clk +
+    // epilogue staging against 128 B/clk of shared-memory bandwidth at MMA peak), not by L2.  Needs an even number of
+    // column tiles (both pairs of a cluster then always have a tile) and enough co-resident 4-CTA clusters that no
+    // round is added to the persistent schedule.
+    static const int cl4_env = [] { const char* e = getenv("MSMD_GEMM_CL4"); return e ? atoi(e) : 1; }();
+    if (cl4_env && Cfg::NSPLIT == 1 && p.tiles_n % 2 == 0 && d.max_ctas <= 0 && tiles >= 4) {
+      static int max_cl4 = -1;     // per instantiation
+      if (max_cl4 < 0) {
+        cfg.gridDim = dim3(kNumSMs / 4 * 4);
+        attr[0].val.clusterDim.x = 4;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        int nc = 0;
+        if (cudaOccupancyMaxActiveClusters(&nc, kern, &cfg) != cudaSuccess) { (void)cudaGetLastError(); nc = 0; }
+        max_cl4 = nc < kNumSMs / 4 ? nc : kNumSMs / 4;
+        attr[0].val.clusterDim.x = 2;
+      }
+      const int want = pairs / 2;                                          // clusters the 2-CTA schedule would occupy
+      const int cl = want < max_cl4 ? want : max_cl4;
+      if (cl >= 1 && cdiv(tiles, 2 * cl) <= cdiv(tiles, pairs)) {          // no extra round
+        if (make_tmap_23(&p.a_half_map, d.A, in_dt, esz, d.K, d.M, d.lda, 1, 0, Cfg::BK, Cfg::BM / 2)) return MSMD_ERR_CUDA;
+        p.cl4 = 1;
+        pairs = 2 * cl;
+        attr[0].val.clusterDim.x = 4;
+      }
+    }
+    cfg.gridDim = dim3(2 * pairs);
     attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;

@@ -28,6 +28,9 @@ struct GemmParams {
   CUtensorMap a_lo_map, b_lo_map;  // MODE 1 only
   CUtensorMap out_map;             // box {128B worth of columns, 32 rows}, SWIZZLE_128B
   CUtensorMap aux_map;             // same box geometry in AuxT
+  CUtensorMap a_half_map;          // cl4: A with a 64-row box (each pair of the cluster fetches half of the shared A tile)
+  int cl4;                         // CTA-pair kernels: 1 = clusters of 4 CTAs = two pairs on neighbouring column tiles of the
+                                   // same rows; the A tile is fetched once per cluster and multicast to both pairs
   const float* bias;               // [N] or nullptr
   int M, N, K;
   int act;                         // 0 none, 1 exact-erf GELU
@@ -165,7 +168,10 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_tc_kernel(const __grid_c
 
   griddep_launch();   // PDL: let the next kernel of the stream get scheduled behind this one
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int cta_rank = Cfg::CTA2 ? (int)cluster_ctarank() : 0;
+  const int crank = Cfg::CTA2 ? (int)cluster_ctarank() : 0;   // rank in the cluster (2 CTAs, or 4 = two pairs when p.cl4)
+  const int cta_rank = crank & 1;                             // rank in the CTA pair
+  const bool cl4 = Cfg::CTA2 && p.cl4 != 0;
+  const uint16_t pair_mask = (uint16_t)(3u << (crank & ~1)); // the two CTAs of this pair, as cluster ranks
   const int tile0 = Cfg::CTA2 ? (int)blockIdx.x / 2 : (int)blockIdx.x;       // first tile of this CTA (pair)
   const int tstride = Cfg::CTA2 ? (int)gridDim.x / 2 : (int)gridDim.x;
   const int num_tiles = p.tiles_m * p.tiles_n * p.batch;
@@ -176,8 +182,10 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_tc_kernel(const __grid_c
     prefetch_tmap(&p.b_map);
     prefetch_tmap(&p.out_map);
     if (Cfg::NSPLIT == 2) { prefetch_tmap(&p.a_lo_map); prefetch_tmap(&p.b_lo_map); }
+    if (cl4) prefetch_tmap(&p.a_half_map);
     if (Cfg::HAS_AUX) prefetch_tmap(&p.aux_map);
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    // cl4: a slot is written by this pair AND (the shared A half) by the sibling pair: it is free when both pairs' MMAs retired
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], cl4 ? 2 : 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], Cfg::EPI_WARPS * (Cfg::CTA2 ? 2 : 1)); }
     for (int i = 0; i < 2 * Cfg::EPI_WARPS; ++i) mbar_init(&aux_bar[i], 1);
     fence_barrier_init();
@@ -219,7 +227,13 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_tc_kernel(const __grid_c
           uint8_t* sb = sa + Cfg::NSPLIT * Cfg::A_BYTES;
           if constexpr (Cfg::CTA2) {
             if (cta_rank == 0) mbar_expect_tx(&full_bar[s], 2 * Cfg::STAGE_BYTES);  // both CTAs' boxes land here
-            tma_load_2d_2sm(sa, &p.a_map, &full_bar[s], kb * BK, m0);
+            if (cl4) {   // rows [64j, 64j+64) of this CTA's A half, j = pair index: written here AND in the sibling pair's CTA
+              const int j = crank >> 1;
+              tma_load_2d_2sm_mc(sa + j * (Cfg::A_BYTES / 2), &p.a_half_map, &full_bar[s], kb * BK, m0 + j * (BM / 2),
+                                 (uint16_t)(5u << cta_rank));
+            } else {
+              tma_load_2d_2sm(sa, &p.a_map, &full_bar[s], kb * BK, m0);
+            }
             tma_load_2d_2sm(sb, &p.b_map, &full_bar[s], kb * BK, n0 + cta_rank * Cfg::B_ROWS);
             if (Cfg::NSPLIT == 2) {
               tma_load_2d_2sm(sa + Cfg::A_BYTES, &p.a_lo_map, &full_bar[s], kb * BK, m0);
@@ -289,7 +303,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_tc_kernel(const __grid_c
               }
             }
           }
-          if constexpr (Cfg::CTA2) umma_commit_2sm(&empty_bar[s]);
+          if constexpr (Cfg::CTA2) umma_commit_2sm(&empty_bar[s], cl4 ? (uint16_t)0xF : pair_mask);
           else umma_commit(&empty_bar[s]);  // smem slot reusable once these MMAs have read it
         }
         __syncwarp();
@@ -297,7 +311,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_tc_kernel(const __grid_c
       }
       if (lane == 0) trace_stamp(p.trace, 1, it, 3);
       if (lane == 0) {  // accumulator complete -> epilogue (of both CTAs in pair mode)
-        if constexpr (Cfg::CTA2) umma_commit_2sm(&tfull_bar[a]);
+        if constexpr (Cfg::CTA2) umma_commit_2sm(&tfull_bar[a], pair_mask);
         else umma_commit(&tfull_bar[a]);
       }
       __syncwarp();
@@ -472,7 +486,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_tc_kernel(const __grid_c
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-          if (Cfg::CTA2 && cta_rank != 0) mbar_arrive_cluster(&tempty_bar[a], 0);  // the leader's MMA warp waits for both
+          if (Cfg::CTA2 && cta_rank != 0) mbar_arrive_cluster(&tempty_bar[a], crank & ~1);  // the leader's MMA warp waits for both
           else mbar_arrive(&tempty_bar[a]);
         }
       };

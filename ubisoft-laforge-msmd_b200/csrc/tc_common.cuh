@@ -157,6 +157,17 @@ __device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMa
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
       : "memory");
 }
+// Same, written to the same shared-memory offset of every CTA in `cta_mask` (cluster ranks); each destination's bytes are
+// counted on the barrier of ITS pair's leader.  Used by clusters of two CTA pairs that share an operand tile.
+__device__ __forceinline__ void tma_load_2d_2sm_mc(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                                   uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1),
+        "h"(cta_mask)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_dst, uint32_t ncols) {  // one warp in EACH CTA of the pair
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
                : "memory");
@@ -182,9 +193,9 @@ __device__ __forceinline__ void umma_2sm_tf32(uint32_t tmem_d, uint64_t desc_a, 
       : "memory");
 }
 // arrives on the barrier at the same offset in BOTH CTAs once the pair's previously issued MMAs are done
-__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t cta_mask = 3) {   // arrives in every CTA of cta_mask
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+               ::"r"(smem_u32(bar)), "h"(cta_mask)
                : "memory");
 }
 // arrive on the barrier with the same offset in CTA `rank` of the cluster
@@ -207,6 +218,17 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
   d |= (uint64_t)(1024 >> 4) << 32;             // stride byte offset: 8 rows * 128 B
   d |= (uint64_t)1 << 46;                       // version
   d |= (uint64_t)2 << 61;                       // SWIZZLE_128B
+  return d;
+}
+// Same for rows of exactly 64 bytes, SWIZZLE_64B (TMA box {64B inner, rows}, CU_TENSOR_MAP_SWIZZLE_64B): 8-row groups
+// are 512 B apart; layout type 4.  Tile bases must be 512-byte aligned.
+__device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(512 >> 4) << 32;              // stride byte offset: 8 rows * 64 B
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;                       // SWIZZLE_64B
   return d;
 }
 // Advance along K inside the 128-byte swizzle atom: +bytes/16 on the start-address field.
