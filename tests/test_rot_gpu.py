@@ -80,7 +80,10 @@ def test_rotations_large_ragged_and_empty(rc):
         args = np.stack([1 + d.sum(-1), 1 + d[:, 0] - d[:, 1] - d[:, 2], 1 - d[:, 0] + d[:, 1] - d[:, 2],
                          1 - d[:, 0] - d[:, 1] + d[:, 2]], -1)
         ill = args.min(-1) < 2e-5
-        assert err[~ill].max(initial=0.0) < 2e-5, (n, err[~ill].max())
+        # next to that threshold the same amplification still shows: a matrix-entry rounding of ~2.4e-7 moves the reference's
+        # quaternion component by 2.4e-7 / (4 sqrt(arg)) and the angle by twice that -> tolerance max(2e-5, 2e-7 / sqrt(arg))
+        tol = np.maximum(2e-5, 2e-7 / np.sqrt(np.maximum(args.min(-1), 2e-5)))
+        assert (err[~ill] < tol[~ill]).all(), (n, err[~ill].max())
         assert err[ill].max(initial=0.0) < 5e-3 and ill.sum() <= max(5, 0.01 * n), (n, err.max(), ill.mean())
     assert rc.axis_angle_to_matrix(torch.zeros(0, 3).cuda()).shape == (0, 3, 3)
     x = torch.randn(4, 5, 3, generator=g)

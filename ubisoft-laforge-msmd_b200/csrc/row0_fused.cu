@@ -252,8 +252,6 @@ __global__ void __cluster_dims__(kHeads, 1, 1) __launch_bounds__(kThreads, 1) ro
     // order below - the arithmetic of a sequence does not depend on how many sequences share the cluster.  Lane
     // (j, qd) = (lane / 4, lane % 4) scores 16 of the 64 head dims of key 8w + j (two 16-byte loads; the 4-lane sums are
     // two shuffles); every lane owns two of the 64 head dims for P V (one coalesced 128-byte warp load per key).
-    // Four sequences' rows are requested before the first is used: the phase is bound by the K / V bytes, not by
-    // one load latency per sequence.
     r0_stamp(p.trace, 2);
     float* parts = po;                              // [seq][kParts][66]: m, l, o(64)
     if (warp < kParts) {
@@ -261,31 +259,35 @@ __global__ void __cluster_dims__(kHeads, 1, 1) __launch_bounds__(kThreads, 1) ro
       const int nk = max(0, min(kPartKeys, p.Tk - base));   // keys of this part
       const int j = lane >> 2, qd = lane & 3;
       const bool valid = j < nk;
-      for (int c0 = 0; c0 < n; c0 += 4) {
-        uint4 ka[4], kb[4];
-        uint32_t vr[4][8];
+      // two register buffers of two sequences each: the loads of the NEXT pair of sequences are in flight while the
+      // current pair is scored (with one 4-sequence buffer the phase paid a full memory latency per chunk: 24.8K cycles
+      // for 13 sequences at configuration 3)
+      struct KV { uint4 ka[2], kb[2]; uint32_t vr[2][8]; };
+      auto load2 = [&](KV& r, int c0) {
 #pragma unroll
-        for (int u4 = 0; u4 < 4; ++u4) {
-          if (c0 + u4 < n) {
-            const bf16* kbase = p.kv + ((int64_t)(s0 + c0 + u4) * p.Tk + base) * (2 * kD) + h * kDh;
-            ka[u4] = kb[u4] = make_uint4(0, 0, 0, 0);
+        for (int u2 = 0; u2 < 2; ++u2) {
+          if (c0 + u2 < n) {
+            const bf16* kbase = p.kv + ((int64_t)(s0 + c0 + u2) * p.Tk + base) * (2 * kD) + h * kDh;
+            r.ka[u2] = r.kb[u2] = make_uint4(0, 0, 0, 0);
             if (valid) {
               const uint4* kp = reinterpret_cast<const uint4*>(kbase + (int64_t)j * (2 * kD) + qd * 16);
-              ka[u4] = __ldg(kp);
-              kb[u4] = __ldg(kp + 1);
+              r.ka[u2] = __ldg(kp);
+              r.kb[u2] = __ldg(kp + 1);
             }
             const uint32_t* vbase = reinterpret_cast<const uint32_t*>(kbase + kD) + lane;
 #pragma unroll
-            for (int u = 0; u < 8; ++u) vr[u4][u] = u < nk ? __ldg(vbase + (int64_t)u * kD) : 0u;
+            for (int u = 0; u < 8; ++u) r.vr[u2][u] = u < nk ? __ldg(vbase + (int64_t)u * kD) : 0u;
           }
         }
+      };
+      auto score2 = [&](const KV& r, int c0) {
 #pragma unroll
-        for (int u4 = 0; u4 < 4; ++u4) {
-          const int seq = c0 + u4;
+        for (int u2 = 0; u2 < 2; ++u2) {
+          const int seq = c0 + u2;
           if (seq < n) {
             float kf[16];
-            up8<F16>(ka[u4], kf);
-            up8<F16>(kb[u4], kf + 8);
+            up8<F16>(r.ka[u2], kf);
+            up8<F16>(r.kb[u2], kf + 8);
             const float* qp = qs + seq * kDh + qd * 16;
             float a = 0.f;
 #pragma unroll
@@ -310,7 +312,7 @@ __global__ void __cluster_dims__(kHeads, 1, 1) __launch_bounds__(kThreads, 1) ro
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
               const float pu = __shfl_sync(0xffffffffu, pj, 4 * u);
-              const float2 f = up2<F16>(vr[u4][u]);
+              const float2 f = up2<F16>(r.vr[u2][u]);
               oa = fmaf(pu, f.x, oa);
               ob = fmaf(pu, f.y, ob);
             }
@@ -319,6 +321,14 @@ __global__ void __cluster_dims__(kHeads, 1, 1) __launch_bounds__(kThreads, 1) ro
             *reinterpret_cast<float2*>(pt + 2 + 2 * lane) = make_float2(oa, ob);
           }
         }
+      };
+      KV bufA, bufB;
+      load2(bufA, 0);
+      for (int c0 = 0; c0 < n; c0 += 4) {
+        load2(bufB, c0 + 2);
+        score2(bufA, c0);
+        load2(bufA, c0 + 4);
+        score2(bufB, c0 + 2);
       }
     }
     __syncthreads();
