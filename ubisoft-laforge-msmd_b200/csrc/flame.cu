@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(256) flame_pose_kernel(const float* __restrict
   for (int i = 0; i < NJ * 3; ++i) acc[i] = 0.f;
   for (int k = lane; k < NB; k += 32) {
     const float v = be[k];
-    Arow[k] = v;
+    if (A_hi == nullptr) Arow[k] = v;      // the fp32 copy is only read by the CUDA-core path (impl 1)
     if (A_hi) {
       const float sv = v * kFlameScaleA;
       const __half hi = __float2half_rn(sv);
@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(256) flame_pose_kernel(const float* __restrict
   }
   const int K = NB + (NJ - 1) * 9;
   for (int k = K + lane; k < Kpad; k += 32) {
-    Arow[k] = 0.f;
+    if (A_hi == nullptr) Arow[k] = 0.f;
     if (A_hi) { A_hi[b * Kpad + k] = __float2half_rn(0.f); A_lo[b * Kpad + k] = __float2half_rn(0.f); }
   }
   if (lane != 0) return;
@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(256) flame_pose_kernel(const float* __restrict
     for (int i = 0; i < 9; ++i) {
       const float v = R[j].m[i] - ((i % 4 == 0) ? 1.0f : 0.0f);
       const int k = NB + (j - 1) * 9 + i;
-      Arow[k] = v;
+      if (A_hi == nullptr) Arow[k] = v;
       if (A_hi) {
         const float sv = v * kFlameScaleA;
         const __half hi = __float2half_rn(sv);
@@ -400,10 +400,13 @@ extern "C" int msmd_flame_decode(msmd_flame* fh, const float* betas, const float
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int rc = ensure_workspace(fh, B);
   if (rc) return rc;
-  flame_pose_kernel<5><<<cdiv(B, 8), 256, 0, st>>>(betas, pose, pose2rot, B, fh->NB, fh->Kpad, fh->Jt, fh->Jb,
-                                                  fh->d_parents, fh->A, impl == 0 ? fh->A_hi : nullptr,
-                                                  impl == 0 ? fh->A_lo : nullptr, fh->xf, joints_out);
-  MSMD_CHECK_LAUNCH();
+  {
+    ProfileScope prof("flame_pose", st);
+    flame_pose_kernel<5><<<cdiv(B, 8), 256, 0, st>>>(betas, pose, pose2rot, B, fh->NB, fh->Kpad, fh->Jt, fh->Jb,
+                                                    fh->d_parents, fh->A, impl == 0 ? fh->A_hi : nullptr,
+                                                    impl == 0 ? fh->A_lo : nullptr, fh->xf, joints_out);
+    MSMD_CHECK_LAUNCH();
+  }
   MSMD_REQUIRE(impl == 0 || impl == 1, "msmd_flame_decode: unknown impl %d", impl);
   if (impl == 0) return flame_decode_tc(fh, B, verts_out, st);
   ProfileScope prof("flame_simt", st);
