@@ -201,6 +201,35 @@ __global__ void __cluster_dims__(kHeads, 1, 1) __launch_bounds__(kThreads, 1) ro
     __syncthreads();
     r0_stamp(p.trace, 1);
 
+    const int part = warp, base = part * kPartKeys;       // attention: warp w = keys [8w, 8w+8) of every sequence (w < kParts)
+    const int nk = max(0, min(kPartKeys, p.Tk - base));   // keys of this part
+    const int j = lane >> 2, qd = lane & 3;
+    const bool valid = j < nk;
+    // two register buffers of two sequences each: the loads of the NEXT pair of sequences are in flight while the
+    // current pair is scored (with one 4-sequence buffer the phase paid a full memory latency per chunk: 24.8K cycles
+    // for 13 sequences at configuration 3)
+    struct KV { uint4 ka[2], kb[2]; uint32_t vr[2][8]; };
+    auto load2 = [&](KV& r, int c0) {
+#pragma unroll
+      for (int u2 = 0; u2 < 2; ++u2) {
+        if (c0 + u2 < n) {
+          const bf16* kbase = p.kv + ((int64_t)(s0 + c0 + u2) * p.Tk + base) * (2 * kD) + h * kDh;
+          r.ka[u2] = r.kb[u2] = make_uint4(0, 0, 0, 0);
+          if (valid) {
+            const uint4* kp = reinterpret_cast<const uint4*>(kbase + (int64_t)j * (2 * kD) + qd * 16);
+            r.ka[u2] = __ldg(kp);
+            r.kb[u2] = __ldg(kp + 1);
+          }
+          const uint32_t* vbase = reinterpret_cast<const uint32_t*>(kbase + kD) + lane;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) r.vr[u2][u] = u < nk ? __ldg(vbase + (int64_t)u * kD) : 0u;
+        }
+      }
+    };
+    KV bufA, bufB;
+    // the first pair of sequences is requested NOW: K / V do not depend on q, so this latency hides under the q projection
+    if (warp < kParts) load2(bufA, 0);
+
     // ---- phase 1: q_h[s][o] = bq[64h+o] + sum_k Wq0[64h+o][k] x0c[s][k].  Warp = (output tile mt of 16, K quarter kq);
     // the four K-quarter partials of every (o, s) are summed below in a fixed order.
     {
@@ -255,31 +284,6 @@ __global__ void __cluster_dims__(kHeads, 1, 1) __launch_bounds__(kThreads, 1) ro
     r0_stamp(p.trace, 2);
     float* parts = po;                              // [seq][kParts][66]: m, l, o(64)
     if (warp < kParts) {
-      const int part = warp, base = part * kPartKeys;
-      const int nk = max(0, min(kPartKeys, p.Tk - base));   // keys of this part
-      const int j = lane >> 2, qd = lane & 3;
-      const bool valid = j < nk;
-      // two register buffers of two sequences each: the loads of the NEXT pair of sequences are in flight while the
-      // current pair is scored (with one 4-sequence buffer the phase paid a full memory latency per chunk: 24.8K cycles
-      // for 13 sequences at configuration 3)
-      struct KV { uint4 ka[2], kb[2]; uint32_t vr[2][8]; };
-      auto load2 = [&](KV& r, int c0) {
-#pragma unroll
-        for (int u2 = 0; u2 < 2; ++u2) {
-          if (c0 + u2 < n) {
-            const bf16* kbase = p.kv + ((int64_t)(s0 + c0 + u2) * p.Tk + base) * (2 * kD) + h * kDh;
-            r.ka[u2] = r.kb[u2] = make_uint4(0, 0, 0, 0);
-            if (valid) {
-              const uint4* kp = reinterpret_cast<const uint4*>(kbase + (int64_t)j * (2 * kD) + qd * 16);
-              r.ka[u2] = __ldg(kp);
-              r.kb[u2] = __ldg(kp + 1);
-            }
-            const uint32_t* vbase = reinterpret_cast<const uint32_t*>(kbase + kD) + lane;
-#pragma unroll
-            for (int u = 0; u < 8; ++u) r.vr[u2][u] = u < nk ? __ldg(vbase + (int64_t)u * kD) : 0u;
-          }
-        }
-      };
       auto score2 = [&](const KV& r, int c0) {
 #pragma unroll
         for (int u2 = 0; u2 < 2; ++u2) {
@@ -322,8 +326,6 @@ __global__ void __cluster_dims__(kHeads, 1, 1) __launch_bounds__(kThreads, 1) ro
           }
         }
       };
-      KV bufA, bufB;
-      load2(bufA, 0);
       for (int c0 = 0; c0 < n; c0 += 4) {
         load2(bufB, c0 + 2);
         score2(bufA, c0);
