@@ -317,14 +317,27 @@ __global__ void __launch_bounds__(256, 2) embed_x_mma_kernel(EmbedParams p) {
     bias[0] = b0.x; bias[1] = b0.y; bias[2] = b0.z; bias[3] = b0.w; bias[4] = b1.x; bias[5] = b1.y; bias[6] = b1.z; bias[7] = b1.w;
     wi[0] = w0.x; wi[1] = w0.y; wi[2] = w0.z; wi[3] = w0.w; wi[4] = w1.x; wi[5] = w1.y; wi[6] = w1.z; wi[7] = w1.w;
   }
-#pragma unroll 2
+  // the positional-encoding rows of all 8 row groups are requested before the first is used (the accumulators are dead
+  // by now, so the registers are free): one L2 latency instead of eight on the critical path of a 200-CTA kernel
+  float4 pe0[kEmRows / 4], pe1[kEmRows / 4];
+#pragma unroll
+  for (int it = 0; it < kEmRows / 4; ++it) {
+    const int g = g0 + it * 4 + (lane >> 3);
+    pe0[it] = pe1[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (g < rows_total) {
+      const int l = g - (g / p.L) * p.L;
+      const float* pe = p.PE + (int64_t)(1 + p.Lp + l) * p.d + col;
+      pe0[it] = __ldg(reinterpret_cast<const float4*>(pe));
+      pe1[it] = __ldg(reinterpret_cast<const float4*>(pe + 4));
+    }
+  }
+#pragma unroll
   for (int it = 0; it < kEmRows / 4; ++it) {
     const int r = it * 4 + (lane >> 3), g = g0 + r;
     if (g < rows_total) {
       const int n = g / p.L, l = g - n * p.L;
       const float4 s0 = *reinterpret_cast<const float4*>(sw + r * kEmSPitch + c8), s1 = *reinterpret_cast<const float4*>(sw + r * kEmSPitch + c8 + 4);
-      const float* pe = p.PE + (int64_t)(1 + p.Lp + l) * p.d + col;
-      const float4 p0 = __ldg(reinterpret_cast<const float4*>(pe)), p1 = __ldg(reinterpret_cast<const float4*>(pe + 4));
+      const float4 p0 = pe0[it], p1 = pe1[it];
       float v[8] = {s0.x + (bias[0] + p0.x), s0.y + (bias[1] + p0.y), s0.z + (bias[2] + p0.z), s0.w + (bias[3] + p0.w),
                     s1.x + (bias[4] + p1.x), s1.y + (bias[5] + p1.y), s1.z + (bias[6] + p1.z), s1.w + (bias[7] + p1.w)};
       for (int e = 0; e < p.E; ++e) {
