@@ -11,6 +11,7 @@
 #include "profile.cuh"
 #include <vector>
 #include <cstring>
+#include <cstdlib>
 
 namespace msmd {
 
@@ -146,6 +147,156 @@ __global__ void __launch_bounds__(256, 3) flame_pose_kernel(const float* __restr
       joints_out[b * NJ * 3 + lane * 3 + 0] = tx;
       joints_out[b * NJ * 3 + lane * 3 + 1] = ty;
       joints_out[b * NJ * 3 + lane * 3 + 2] = tz;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// The same per-frame work with the joint regression on the tensor cores: J = Jt + Jb beta is a [15 x NB] x [NB x frames]
+// product, and the one-warp-per-frame kernel above spends ~2500 instructions per frame on it (15 loads + 15 FMAs per
+// coefficient and lane).  Here a warp owns 8 frames = the N columns of mma.sync m16n8k16: the rows are the 15 joint
+// coordinates, fp16 two-term splits of both operands (three passes, 22 mantissa bits; the split of 16 beta is the very
+// operand row the blendshape GEMM needs, so it is produced once and used twice).  The per-joint section then runs on
+// lane 8 g + j for the frames 4 pass + g.  Needs NJ * 3 <= 16 and an even NB.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void pose_mma(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
+  const __half2 h = __halves2half2(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+template <int NJ>
+__global__ void __launch_bounds__(256) flame_pose_mma_kernel(const float* __restrict__ betas, const float* __restrict__ pose,
+                                                             int pose2rot, int64_t B, int NB, int KB, int Kpad,
+                                                             const float* __restrict__ Jt, const __half* __restrict__ Jb16,
+                                                             const int* __restrict__ parents_g, float* __restrict__ A,
+                                                             __half* __restrict__ A_hi, __half* __restrict__ A_lo,
+                                                             float* __restrict__ xf, float* __restrict__ joints_out) {
+  static_assert(NJ * 3 <= 16 && NJ <= 8, "one 16-row MMA tile of joint coordinates; 8 lanes per frame in the joint section");
+  __shared__ float Js[8][8][16];                 // [warp][frame of the warp][joint coordinate]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gid = lane >> 2, tig = lane & 3;
+  const int64_t f0 = ((int64_t)blockIdx.x * 8 + warp) * 8;
+  if (f0 >= B) return;
+  auto put = [&](int64_t b, int k, float v) {    // one element of the GEMM operand row: fp32 (impl 1) or the fp16 split (impl 0)
+    if (A_hi == nullptr) { A[b * Kpad + k] = v; return; }
+    const float sv = v * kFlameScaleA;
+    const __half hi = __float2half_rn(sv);
+    A_hi[b * Kpad + k] = hi;
+    A_lo[b * Kpad + k] = __float2half_rn(sv - __half2float(hi));
+  };
+  // ---- joint regression + operand split of the coefficients
+  {
+    const int64_t f = f0 + gid;
+    const bool fv = f < B;
+    const float* be = betas + f * NB;
+    const __half* JH = Jb16;
+    const __half* JL = Jb16 + 16 * KB;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 5
+    for (int k0 = 0; k0 < KB; k0 += 16) {
+      const int ka = k0 + 2 * tig, kb = ka + 8;                 // even: a pair never straddles NB (NB is even)
+      float2 xa = make_float2(0.f, 0.f), xb = make_float2(0.f, 0.f);
+      if (fv && ka < NB) xa = *reinterpret_cast<const float2*>(be + ka);
+      if (fv && kb < NB) xb = *reinterpret_cast<const float2*>(be + kb);
+      uint32_t ah[4], al[4];
+      ah[0] = __ldg(reinterpret_cast<const uint32_t*>(JH + gid * KB + ka));
+      ah[1] = __ldg(reinterpret_cast<const uint32_t*>(JH + (gid + 8) * KB + ka));
+      ah[2] = __ldg(reinterpret_cast<const uint32_t*>(JH + gid * KB + kb));
+      ah[3] = __ldg(reinterpret_cast<const uint32_t*>(JH + (gid + 8) * KB + kb));
+      al[0] = __ldg(reinterpret_cast<const uint32_t*>(JL + gid * KB + ka));
+      al[1] = __ldg(reinterpret_cast<const uint32_t*>(JL + (gid + 8) * KB + ka));
+      al[2] = __ldg(reinterpret_cast<const uint32_t*>(JL + gid * KB + kb));
+      al[3] = __ldg(reinterpret_cast<const uint32_t*>(JL + (gid + 8) * KB + kb));
+      const float s0 = xa.x * kFlameScaleA, s1 = xa.y * kFlameScaleA, s2 = xb.x * kFlameScaleA, s3 = xb.y * kFlameScaleA;
+      const __half h0 = __float2half_rn(s0), h1 = __float2half_rn(s1), h2 = __float2half_rn(s2), h3 = __float2half_rn(s3);
+      const uint32_t bh0 = pack_h2(h0, h1), bh1 = pack_h2(h2, h3);
+      const uint32_t bl0 = pack_h2(__float2half_rn(s0 - __half2float(h0)), __float2half_rn(s1 - __half2float(h1)));
+      const uint32_t bl1 = pack_h2(__float2half_rn(s2 - __half2float(h2)), __float2half_rn(s3 - __half2float(h3)));
+      if (fv) {
+        if (A_hi != nullptr) {
+          if (ka < NB) { *reinterpret_cast<uint32_t*>(A_hi + f * Kpad + ka) = bh0; *reinterpret_cast<uint32_t*>(A_lo + f * Kpad + ka) = bl0; }
+          if (kb < NB) { *reinterpret_cast<uint32_t*>(A_hi + f * Kpad + kb) = bh1; *reinterpret_cast<uint32_t*>(A_lo + f * Kpad + kb) = bl1; }
+        } else {
+          if (ka < NB) *reinterpret_cast<float2*>(A + f * Kpad + ka) = xa;
+          if (kb < NB) *reinterpret_cast<float2*>(A + f * Kpad + kb) = xb;
+        }
+      }
+      pose_mma(acc, al, bh0, bh1);     // lo * hi
+      pose_mma(acc, ah, bl0, bl1);     // hi * lo
+      pose_mma(acc, ah, bh0, bh1);     // hi * hi
+    }
+    // accumulator (row = joint coordinate, column = frame of the warp) -> shared memory, descaled, + Jt
+    constexpr float kInv = 1.0f / (kFlameScaleA * kFlameScaleJ);
+    const float jt0 = gid < NJ * 3 ? Jt[gid] : 0.f, jt1 = gid + 8 < NJ * 3 ? Jt[gid + 8] : 0.f;
+    Js[warp][2 * tig][gid] = fmaf(acc[0], kInv, jt0);
+    Js[warp][2 * tig + 1][gid] = fmaf(acc[1], kInv, jt0);
+    Js[warp][2 * tig][gid + 8] = fmaf(acc[2], kInv, jt1);
+    Js[warp][2 * tig + 1][gid + 8] = fmaf(acc[3], kInv, jt1);
+  }
+  __syncwarp();
+  const int K = NB + (NJ - 1) * 9;
+  for (int fs = 0; fs < 8; ++fs) {
+    if (f0 + fs < B)
+      for (int k = K + lane; k < Kpad; k += 32) put(f0 + fs, k, 0.f);
+  }
+  // ---- per-joint section, 4 frames per pass: lane 8 g + j owns joint j of frame 4 pass + g
+#pragma unroll 1
+  for (int pass = 0; pass < 2; ++pass) {
+    const int fs = 4 * pass + (lane >> 3), jn = lane & 7;
+    const int64_t b = f0 + fs;
+    const bool mine = jn < NJ && b < B;
+    float Jx = 0.f, Jy = 0.f, Jz = 0.f;
+    if (jn < NJ) { Jx = Js[warp][fs][3 * jn]; Jy = Js[warp][fs][3 * jn + 1]; Jz = Js[warp][fs][3 * jn + 2]; }
+    Mat3 Rj;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Rj.m[i] = (i % 4 == 0) ? 1.0f : 0.0f;
+    if (mine) {
+      if (pose2rot) {
+        const float* p = pose + b * NJ * 3 + jn * 3;
+        Rj = rodrigues(p[0], p[1], p[2]);
+      } else {
+        const float* p = pose + b * NJ * 9 + jn * 9;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) Rj.m[i] = p[i];
+      }
+    }
+    if (mine && jn >= 1) {
+#pragma unroll
+      for (int i = 0; i < 9; ++i) put(b, NB + (jn - 1) * 9 + i, Rj.m[i] - ((i % 4 == 0) ? 1.0f : 0.0f));
+    }
+    // chain (lbs.py:317-371): G_j = G_parent R_j, t_j = G_parent (J_j - J_parent) + t_parent; parents[j] < j
+    Mat3 G = Rj;
+    float tx = Jx, ty = Jy, tz = Jz;
+#pragma unroll
+    for (int j = 1; j < NJ; ++j) {
+      const int src = (lane & 24) | parents_g[j];     // the parent's lane in this lane's frame group
+      Mat3 Gp;
+#pragma unroll
+      for (int i = 0; i < 9; ++i) Gp.m[i] = __shfl_sync(0xffffffffu, G.m[i], src);
+      const float tpx = __shfl_sync(0xffffffffu, tx, src), tpy = __shfl_sync(0xffffffffu, ty, src), tpz = __shfl_sync(0xffffffffu, tz, src);
+      const float Jpx = __shfl_sync(0xffffffffu, Jx, src), Jpy = __shfl_sync(0xffffffffu, Jy, src), Jpz = __shfl_sync(0xffffffffu, Jz, src);
+      if (jn == j) {
+        const float rx = Jx - Jpx, ry = Jy - Jpy, rz = Jz - Jpz;
+        G = mat3_mul(Gp, Rj);
+        tx = Gp.m[0] * rx + Gp.m[1] * ry + Gp.m[2] * rz + tpx;
+        ty = Gp.m[3] * rx + Gp.m[4] * ry + Gp.m[5] * rz + tpy;
+        tz = Gp.m[6] * rx + Gp.m[7] * ry + Gp.m[8] * rz + tpz;
+      }
+    }
+    if (mine) {
+      float* x = xf + b * NJ * 12 + jn * 12;
+#pragma unroll
+      for (int i = 0; i < 9; ++i) x[i] = G.m[i];
+      x[9] = tx - (G.m[0] * Jx + G.m[1] * Jy + G.m[2] * Jz);
+      x[10] = ty - (G.m[3] * Jx + G.m[4] * Jy + G.m[5] * Jz);
+      x[11] = tz - (G.m[6] * Jx + G.m[7] * Jy + G.m[8] * Jz);
+      if (joints_out) {
+        joints_out[b * NJ * 3 + jn * 3 + 0] = tx;
+        joints_out[b * NJ * 3 + jn * 3 + 1] = ty;
+        joints_out[b * NJ * 3 + jn * 3 + 2] = tz;
+      }
     }
   }
 }
@@ -372,6 +523,17 @@ extern "C" int msmd_flame_create(const float* v_template, const float* shapedirs
         Jb[(size_t)(j * 3 + c) * NB + l] = (float)a;
       }
     }
+  // fp16 two-term split of kFlameScaleJ * Jb for the tensor-core joint regression: [2][16][KB], zero padded
+  const int KB = (NB + 15) / 16 * 16;
+  fh->KB = KB;
+  std::vector<__half> jb16((size_t)2 * 16 * KB, __float2half_rn(0.f));
+  for (int i = 0; i < NJ * 3 && i < 16; ++i)
+    for (int l = 0; l < NB; ++l) {
+      const float sv = Jb[(size_t)i * NB + l] * kFlameScaleJ;
+      const __half h = __float2half_rn(sv);
+      jb16[(size_t)i * KB + l] = h;
+      jb16[(size_t)16 * KB + (size_t)i * KB + l] = __float2half_rn(sv - __half2float(h));
+    }
   auto up = [&](float** d, const std::vector<float>& h) -> int {
     MSMD_CHECK_CUDA(cudaMalloc(d, h.size() * sizeof(float)));
     MSMD_CHECK_CUDA(cudaMemcpy(*d, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
@@ -396,7 +558,7 @@ extern "C" int msmd_flame_create(const float* v_template, const float* shapedirs
   fh->weights_normalised = normalised ? 1 : 0;
   if ((rc = up(&fh->basis, basis)) || (rc = up16(&fh->basis_hi, hi)) || (rc = up16(&fh->basis_lo, lo)) ||
       (rc = up(&fh->v_template, h_t)) || (rc = up(&fh->weights, h_w)) || (rc = up(&fh->Jt, Jt)) ||
-      (rc = up(&fh->Jb, Jb)) || (rc = up(&fh->vconst, vconst))) {
+      (rc = up(&fh->Jb, Jb)) || (rc = up(&fh->vconst, vconst)) || (rc = up16(&fh->Jb16, jb16))) {
     msmd_flame_destroy(fh);
     return rc;
   }
@@ -414,7 +576,7 @@ extern "C" void msmd_flame_destroy(msmd_flame* fh) {
   if (!fh) return;
   flame_tc_destroy(fh);
   cudaFree(fh->basis); cudaFree(fh->basis_hi); cudaFree(fh->basis_lo); cudaFree(fh->v_template);
-  cudaFree(fh->weights); cudaFree(fh->vconst); cudaFree(fh->Jt); cudaFree(fh->Jb); cudaFree(fh->d_parents);
+  cudaFree(fh->weights); cudaFree(fh->vconst); cudaFree(fh->Jt); cudaFree(fh->Jb); cudaFree(fh->Jb16); cudaFree(fh->d_parents);
   cudaFree(fh->A); cudaFree(fh->A_hi); cudaFree(fh->A_lo); cudaFree(fh->xf);
   delete fh;
 }
@@ -430,9 +592,15 @@ extern "C" int msmd_flame_decode(msmd_flame* fh, const float* betas, const float
   if (rc) return rc;
   {
     ProfileScope prof("flame_pose", st);
-    flame_pose_kernel<5><<<cdiv(B, 8), 256, 0, st>>>(betas, pose, pose2rot, B, fh->NB, fh->Kpad, fh->Jt, fh->Jb,
-                                                    fh->d_parents, fh->A, impl == 0 ? fh->A_hi : nullptr,
-                                                    impl == 0 ? fh->A_lo : nullptr, fh->xf, joints_out);
+    static const bool pose_mma_on = [] { const char* e = getenv("MSMD_FLAME_POSE_MMA"); return e ? atoi(e) != 0 : true; }();
+    if (pose_mma_on && fh->NB % 2 == 0 && fh->Jb16 != nullptr && reinterpret_cast<uintptr_t>(betas) % 8 == 0)   // (float2 loads of the coefficients)
+      flame_pose_mma_kernel<5><<<cdiv(B, 64), 256, 0, st>>>(betas, pose, pose2rot, B, fh->NB, fh->KB, fh->Kpad, fh->Jt, fh->Jb16,
+                                                           fh->d_parents, fh->A, impl == 0 ? fh->A_hi : nullptr,
+                                                           impl == 0 ? fh->A_lo : nullptr, fh->xf, joints_out);
+    else
+      flame_pose_kernel<5><<<cdiv(B, 8), 256, 0, st>>>(betas, pose, pose2rot, B, fh->NB, fh->Kpad, fh->Jt, fh->Jb,
+                                                      fh->d_parents, fh->A, impl == 0 ? fh->A_hi : nullptr,
+                                                      impl == 0 ? fh->A_lo : nullptr, fh->xf, joints_out);
     MSMD_CHECK_LAUNCH();
   }
   MSMD_REQUIRE(impl == 0 || impl == 1, "msmd_flame_decode: unknown impl %d", impl);

@@ -26,6 +26,8 @@ struct msmd_flame {
   int weights_normalised = 0;   // every row of the skinning weights sums to 1 (+-1e-5): the blend may use joint differences
   float* Jt = nullptr;          // [NJ*3]      J_regressor @ v_template
   float* Jb = nullptr;          // [NJ*3, NB]  J_regressor @ shapedirs (joint regression folded)
+  __half* Jb16 = nullptr;       // [2][16][KB] fp16 two-term split of kFlameScaleJ * Jb (rows >= NJ*3 and columns >= NB zero): the A
+  int KB = 0;                   // operand of the tensor-core joint regression (flame_pose_mma_kernel); KB = NB rounded up to 16
   int* d_parents = nullptr;     // [8]
   // per-call workspaces (grown on demand)
   int64_t cap_B = 0;
@@ -37,7 +39,7 @@ struct msmd_flame {
 };
 
 namespace msmd {
-constexpr float kFlameScaleA = 16.0f, kFlameScaleB = 256.0f;
+constexpr float kFlameScaleA = 16.0f, kFlameScaleB = 256.0f, kFlameScaleJ = 1024.0f;
 int flame_decode_tc(msmd_flame* fh, int64_t B, float* verts_out, cudaStream_t st);  // flame_tc.cu
 void flame_tc_destroy(msmd_flame* fh);
 }  // namespace msmd
