@@ -760,78 +760,88 @@ __global__ void __launch_bounds__(256) update_kernel(const UpdateParams* __restr
     c0 = (1.0f - abp) * sqrtf(alpha) / (1.0f - ab);
     c1 = (1.0f - alpha) * sqrtf(abp) / (1.0f - ab);
   }
-  const bool sep = p.tgt_dyn != nullptr || p.cum_static != nullptr;
+  // loop-invariant fields in registers: the stores below go through generic pointers that the compiler must assume may
+  // alias the shared-memory parameter block, so every p.field in the loop was re-read after each store
+  struct Loc {
+    const float *dec, *stat, *z, *thr; float *x, *traj, *tgt_dyn, *cum_static, *alpha_traj; const int* overflow;
+    float scale0, scale1; unsigned long long seed; long long noise_offset;
+    int NX, E, T, L, Lp, dm, nb, ldd, cfg_independent, target_noise, t_start;
+  };
+  const Loc q = {p.dec, p.stat, p.z, p.thr, p.x, p.traj, p.tgt_dyn, p.cum_static, p.alpha_traj, p.overflow,
+                 p.scale0, p.scale1, p.seed, p.noise_offset,
+                 p.NX, p.E, p.T, p.L, p.Lp, p.dm, p.nb, p.ldd, p.cfg_independent, p.target_noise, p.t_start};
+  const bool sep = q.tgt_dyn != nullptr || q.cum_static != nullptr;
   // warp = one (clip, frame) row of dm codes, lane = column c (+32, +64): no 64-bit index arithmetic per element (three
   // int64 divisions per element made this kernel instruction-bound: 600 instructions per element, 23 us per step)
   const int lane = threadIdx.x & 31;
-  const int rows = p.NX * p.L;
+  const int rows = q.NX * q.L;
   for (int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += gridDim.x * (blockDim.x >> 5)) {
-    const int n = row / p.L, l = row - n * p.L;
+    const int n = row / q.L, l = row - n * q.L;
     // per-row invariants of the (<= 3) guidance entries: decoder row, static-basis block, threshold, mixing weights
     const float* rowp[3];
     const float* stp[3];
     float thv[3], al[3][4];
 #pragma unroll
     for (int e = 0; e < 3; ++e) {
-      const int sq = (e < p.E ? e : 0) * p.NX + n;
-      rowp[e] = p.dec + ((int64_t)sq * p.T + 1 + p.Lp + l) * p.ldd;
-      stp[e] = p.stat + (int64_t)sq * p.nb * p.dm;
-      thv[e] = p.thr ? p.thr[sq] : 0.f;
+      const int sq = (e < q.E ? e : 0) * q.NX + n;
+      rowp[e] = q.dec + ((int64_t)sq * q.T + 1 + q.Lp + l) * q.ldd;
+      stp[e] = q.stat + (int64_t)sq * q.nb * q.dm;
+      thv[e] = q.thr ? q.thr[sq] : 0.f;
 #pragma unroll
-      for (int b = 0; b < 4; ++b) al[e][b] = b < p.nb ? rowp[e][p.dm + b] : 0.f;
+      for (int b = 0; b < 4; ++b) al[e][b] = b < q.nb ? rowp[e][q.dm + b] : 0.f;
     }
-   for (int c = lane; c < p.dm; c += 32) {
-    const int64_t i = (int64_t)row * p.dm + c;
-    const bool face = c < p.dm - 3;
+   for (int c = lane; c < q.dm; c += 32) {
+    const int64_t i = (int64_t)row * q.dm + c;
+    const bool face = c < q.dm - 3;
     // CFG combine (model.py:404-417); results[0] is updated in place through a view, so 'independent'
     // subtracts the running target.  The same recursion runs on the dynamic / static parts
     // (model.py:603-626) when the separate outputs are requested.
     float tgt = 0.f, prev = 0.f, td = 0.f, pd = 0.f, ts = 0.f, psv = 0.f;
 #pragma unroll
     for (int e = 0; e < 3; ++e) {
-      if (e >= p.E) break;
+      if (e >= q.E) break;
       // split_target() with the row's pointers / mixing weights held in registers (same operation order)
       const float dyn = rowp[e][c];
       float sta = 0.f;
-      if (p.nb <= 4) {
+      if (q.nb <= 4) {
 #pragma unroll
         for (int b = 0; b < 4; ++b)
-          if (b < p.nb) sta += (face ? al[e][b] : 1.0f) * stp[e][b * p.dm + c];
+          if (b < q.nb) sta += (face ? al[e][b] : 1.0f) * stp[e][b * q.dm + c];
       } else {
-        for (int b = 0; b < p.nb; ++b) sta += (face ? rowp[e][p.dm + b] : 1.0f) * stp[e][b * p.dm + c];
+        for (int b = 0; b < q.nb; ++b) sta += (face ? rowp[e][q.dm + b] : 1.0f) * stp[e][b * q.dm + c];
       }
       float r = dyn + sta;
-      if (p.thr) { const float th = thv[e]; r = fminf(fmaxf(r, -th), th); }
+      if (q.thr) { const float th = thv[e]; r = fminf(fmaxf(r, -th), th); }
       if (e == 0) {
         tgt = r; td = dyn; ts = sta;
       } else {
-        const float sc = (e == 1) ? p.scale0 : p.scale1;
-        const bool run = p.cfg_independent || e == 1;
+        const float sc = (e == 1) ? q.scale0 : q.scale1;
+        const bool run = q.cfg_independent || e == 1;
         tgt = tgt + sc * (r - (run ? tgt : prev));
         if (sep) { td = td + sc * (dyn - (run ? td : pd)); ts = ts + sc * (sta - (run ? ts : psv)); }
       }
       prev = r; pd = dyn; psv = sta;
     }
     float zt = 0.f;
-    if (t > 1) zt = p.z ? p.z[(int64_t)t * n_el + i] : philox_normal(p.seed, (uint32_t)t, (uint32_t)(i + p.noise_offset));
-    const float xo = p.x[i];
-    float xn = p.target_noise ? (c0 * (xo - c1 * tgt) + sigma * zt) : (c0 * xo + c1 * tgt + sigma * zt);
+    if (t > 1) zt = q.z ? q.z[(int64_t)t * n_el + i] : philox_normal(q.seed, (uint32_t)t, (uint32_t)(i + q.noise_offset));
+    const float xo = q.x[i];
+    float xn = q.target_noise ? (c0 * (xo - c1 * tgt) + sigma * zt) : (c0 * xo + c1 * tgt + sigma * zt);
     // fp32-grade steps: an activation left the fp16 range of the operand split -> poison the state instead of
     // returning a silently wrong sample (the host reports it at the next call, without synchronising this one)
-    if (p.overflow != nullptr && *p.overflow != 0) xn = __int_as_float(0x7fc00000);
-    p.x[i] = xn;
-    if (p.traj) p.traj[(int64_t)(t - 1) * n_el + i] = xn;
-    if (p.tgt_dyn) p.tgt_dyn[i] = td;
-    if (p.cum_static) p.cum_static[i] += c1 * ts;
-    if (p.alpha_traj && c < p.nb) {   // alphas: columns dm..dm+nb-1 of the decoder output, same CFG recursion
+    if (q.overflow != nullptr && *q.overflow != 0) xn = __int_as_float(0x7fc00000);
+    q.x[i] = xn;
+    if (q.traj) q.traj[(int64_t)(t - 1) * n_el + i] = xn;
+    if (q.tgt_dyn) q.tgt_dyn[i] = td;
+    if (q.cum_static) q.cum_static[i] += c1 * ts;
+    if (q.alpha_traj && c < q.nb) {   // alphas: columns dm..dm+nb-1 of the decoder output, same CFG recursion
       float ta = 0.f, pa = 0.f;
-      for (int e = 0; e < p.E; ++e) {
-        const float a = p.dec[((int64_t)(e * p.NX + n) * p.T + 1 + p.Lp + l) * p.ldd + p.dm + c];
+      for (int e = 0; e < q.E; ++e) {
+        const float a = q.dec[((int64_t)(e * q.NX + n) * q.T + 1 + q.Lp + l) * q.ldd + q.dm + c];
         if (e == 0) ta = a;
-        else ta = ta + ((e == 1) ? p.scale0 : p.scale1) * (a - ((p.cfg_independent || e == 1) ? ta : pa));
+        else ta = ta + ((e == 1) ? q.scale0 : q.scale1) * (a - ((q.cfg_independent || e == 1) ? ta : pa));
         pa = a;
       }
-      p.alpha_traj[(((int64_t)(p.t_start - t) * p.NX + n) * p.L + l) * p.nb + c] = ta;
+      q.alpha_traj[(((int64_t)(q.t_start - t) * q.NX + n) * q.L + l) * q.nb + c] = ta;
     }
    }
   }
