@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(256, 3) flame_pose_kernel(const float* __restr
 // coefficient and lane).  Here a warp owns 8 frames = the N columns of mma.sync m16n8k16: the rows are the 15 joint
 // coordinates, fp16 two-term splits of both operands (three passes, 22 mantissa bits; the split of 16 beta is the very
 // operand row the blendshape GEMM needs, so it is produced once and used twice).  The per-joint section then runs on
-// lane 8 g + j for the frames 4 pass + g.  Needs NJ * 3 <= 16 and an even NB.
+// lane 8 g + j.  Two warps share 8 frames (half of K each, then 4 frames each).  Needs NJ * 3 <= 16 and an even NB.
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ void pose_mma(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
@@ -175,10 +175,13 @@ __global__ void __launch_bounds__(256) flame_pose_mma_kernel(const float* __rest
                                                              __half* __restrict__ A_hi, __half* __restrict__ A_lo,
                                                              float* __restrict__ xf, float* __restrict__ joints_out) {
   static_assert(NJ * 3 <= 16 && NJ <= 8, "one 16-row MMA tile of joint coordinates; 8 lanes per frame in the joint section");
-  __shared__ float Js[8][8][16];                 // [warp][frame of the warp][joint coordinate]
+  // warps w and w + 4 share 8 frames: each takes half of the K range (the 25 k-steps of one warp were a 30 us dependent
+  // chain at 7 warps per SM) and, afterwards, 4 of the 8 frames of the per-joint section
+  __shared__ float Jp[2][4][8][16];              // [K half][frame group][frame][joint coordinate] raw partial sums
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gid = lane >> 2, tig = lane & 3;
-  const int64_t f0 = ((int64_t)blockIdx.x * 8 + warp) * 8;
-  if (f0 >= B) return;
+  const int wq = warp & 3, kh = warp >> 2;
+  const int64_t f0 = ((int64_t)blockIdx.x * 4 + wq) * 8;
+  if (f0 >= B) return;                           // (both warps of the pair leave together; the pair barrier below is theirs alone)
   auto put = [&](int64_t b, int k, float v) {    // one element of the GEMM operand row: fp32 (impl 1) or the fp16 split (impl 0)
     if (A_hi == nullptr) { A[b * Kpad + k] = v; return; }
     const float sv = v * kFlameScaleA;
@@ -194,8 +197,11 @@ __global__ void __launch_bounds__(256) flame_pose_mma_kernel(const float* __rest
     const __half* JH = Jb16;
     const __half* JL = Jb16 + 16 * KB;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 5
-    for (int k0 = 0; k0 < KB; k0 += 16) {
+    const int nks = KB / 16, ks_mid = (nks + 1) / 2;
+    const int ks_lo = kh == 0 ? 0 : ks_mid, ks_hi = kh == 0 ? ks_mid : nks;
+#pragma unroll 4
+    for (int ks = ks_lo; ks < ks_hi; ++ks) {
+      const int k0 = ks * 16;
       const int ka = k0 + 2 * tig, kb = ka + 8;                 // even: a pair never straddles NB (NB is even)
       float2 xa = make_float2(0.f, 0.f), xb = make_float2(0.f, 0.f);
       if (fv && ka < NB) xa = *reinterpret_cast<const float2*>(be + ka);
@@ -227,28 +233,30 @@ __global__ void __launch_bounds__(256) flame_pose_mma_kernel(const float* __rest
       pose_mma(acc, ah, bl0, bl1);     // hi * lo
       pose_mma(acc, ah, bh0, bh1);     // hi * hi
     }
-    // accumulator (row = joint coordinate, column = frame of the warp) -> shared memory, descaled, + Jt
-    constexpr float kInv = 1.0f / (kFlameScaleA * kFlameScaleJ);
-    const float jt0 = gid < NJ * 3 ? Jt[gid] : 0.f, jt1 = gid + 8 < NJ * 3 ? Jt[gid + 8] : 0.f;
-    Js[warp][2 * tig][gid] = fmaf(acc[0], kInv, jt0);
-    Js[warp][2 * tig + 1][gid] = fmaf(acc[1], kInv, jt0);
-    Js[warp][2 * tig][gid + 8] = fmaf(acc[2], kInv, jt1);
-    Js[warp][2 * tig + 1][gid + 8] = fmaf(acc[3], kInv, jt1);
+    // partial accumulator (row = joint coordinate, column = frame of the group) -> shared memory
+    Jp[kh][wq][2 * tig][gid] = acc[0];
+    Jp[kh][wq][2 * tig + 1][gid] = acc[1];
+    Jp[kh][wq][2 * tig][gid + 8] = acc[2];
+    Jp[kh][wq][2 * tig + 1][gid + 8] = acc[3];
   }
-  __syncwarp();
+  asm volatile("bar.sync %0, 64;" ::"r"(1 + wq) : "memory");     // the two warps of this frame group
   const int K = NB + (NJ - 1) * 9;
-  for (int fs = 0; fs < 8; ++fs) {
+  for (int fs = kh; fs < 8; fs += 2) {
     if (f0 + fs < B)
       for (int k = K + lane; k < Kpad; k += 32) put(f0 + fs, k, 0.f);
   }
-  // ---- per-joint section, 4 frames per pass: lane 8 g + j owns joint j of frame 4 pass + g
-#pragma unroll 1
-  for (int pass = 0; pass < 2; ++pass) {
-    const int fs = 4 * pass + (lane >> 3), jn = lane & 7;
+  // ---- per-joint section: this warp takes frames 4 kh .. 4 kh + 3 of the group; lane 8 g + j owns joint j of frame 4 kh + g
+  {
+    constexpr float kInv = 1.0f / (kFlameScaleA * kFlameScaleJ);
+    const int fs = 4 * kh + (lane >> 3), jn = lane & 7;
     const int64_t b = f0 + fs;
     const bool mine = jn < NJ && b < B;
     float Jx = 0.f, Jy = 0.f, Jz = 0.f;
-    if (jn < NJ) { Jx = Js[warp][fs][3 * jn]; Jy = Js[warp][fs][3 * jn + 1]; Jz = Js[warp][fs][3 * jn + 2]; }
+    if (jn < NJ) {      // J = Jt + (K half 0 + K half 1) / scale, in that order
+      Jx = fmaf(Jp[0][wq][fs][3 * jn] + Jp[1][wq][fs][3 * jn], kInv, Jt[3 * jn]);
+      Jy = fmaf(Jp[0][wq][fs][3 * jn + 1] + Jp[1][wq][fs][3 * jn + 1], kInv, Jt[3 * jn + 1]);
+      Jz = fmaf(Jp[0][wq][fs][3 * jn + 2] + Jp[1][wq][fs][3 * jn + 2], kInv, Jt[3 * jn + 2]);
+    }
     Mat3 Rj;
 #pragma unroll
     for (int i = 0; i < 9; ++i) Rj.m[i] = (i % 4 == 0) ? 1.0f : 0.0f;
@@ -594,7 +602,7 @@ extern "C" int msmd_flame_decode(msmd_flame* fh, const float* betas, const float
     ProfileScope prof("flame_pose", st);
     static const bool pose_mma_on = [] { const char* e = getenv("MSMD_FLAME_POSE_MMA"); return e ? atoi(e) != 0 : true; }();
     if (pose_mma_on && fh->NB % 2 == 0 && fh->Jb16 != nullptr && reinterpret_cast<uintptr_t>(betas) % 8 == 0)   // (float2 loads of the coefficients)
-      flame_pose_mma_kernel<5><<<cdiv(B, 64), 256, 0, st>>>(betas, pose, pose2rot, B, fh->NB, fh->KB, fh->Kpad, fh->Jt, fh->Jb16,
+      flame_pose_mma_kernel<5><<<cdiv(B, 32), 256, 0, st>>>(betas, pose, pose2rot, B, fh->NB, fh->KB, fh->Kpad, fh->Jt, fh->Jb16,
                                                            fh->d_parents, fh->A, impl == 0 ? fh->A_hi : nullptr,
                                                            impl == 0 ? fh->A_lo : nullptr, fh->xf, joints_out);
     else
